@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- the PBDServer substep hot path on B200 vs. the reference CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload headline|config2|config1|batch4096] [--backend auto|stream|tile]
+
+A "step" is one frame = one ``pbd_step(dt=1/60)`` = `substeps` XPBD substeps of the workload.
+Default workload = BASELINE.json configs[2], the configuration the metric is quoted on
+("1M tets"): Kuhn n=56 grid (V=185,193 E=1,257,704 T=1,053,696), 20 substeps x 6 iterations,
+edge + volume constraints, ground plane.  With --gpus N (launched by torchrun, one rank per GPU)
+every rank steps its own body of that size -- independent bodies, no data-path collective,
+"scaling": "weak" -- and `value` = substeps of all ranks / max-over-ranks device time.
+
+Printed (rank 0, ONE JSON line): metric/value/unit per BASELINE.json, `roofline` (algorithmic
+bytes per frame / CUDA-event frame time, against MEASURED_PEAKS.json), `cpu_baseline` (the
+reference's own CPU path timed on this box's host cores on a bounded sample), `e2e` (the same
+metric through the reference-facing stepper API with HOST buffers: step + positions D2H into
+pinned memory inside the timed region), `gpu_launches`, `clocks`.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pbd_substeps_per_s"
+UNIT = "substeps/s"
+DT = 1.0 / 60.0
+
+WORKLOADS = {
+    # name: (kuhn n or asset, substeps, iterations, description)
+    "headline": dict(kuhn=56, substeps=20, iterations=6,
+                     desc="BASELINE configs[2]: synthetic 1M-tet Kuhn cube grid n=56 (V=185193 E=1257704 T=1053696), "
+                          "20 substeps/frame x 6 iterations, edge+volume constraints, ground plane"),
+    "config2": dict(kuhn=26, substeps=10, iterations=6,
+                    desc="BASELINE configs[1]: synthetic 100k-tet Kuhn cube n=26 (V=19683 E=129194 T=105456), "
+                         "10 substeps x 6 iterations, ground plane"),
+    "config1": dict(asset="default", substeps=10, iterations=6,
+                    desc="BASELINE configs[0]: default Assets/SoftBody tet mesh (V=8613 E=41488 T=26070), 10 substeps x 6 iterations"),
+    "small": dict(kuhn=10, substeps=10, iterations=6, desc="one 6k-tet body (config-4 body), smoke-sized"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_workload(name, mg):
+    import numpy as np
+    w = WORKLOADS[name]
+    if "kuhn" in w:
+        x0, tets, edges = mg.kuhn_grid(w["kuhn"])
+    else:
+        m = np.load(os.path.join(ROOT, "tests", "golden", f"mesh_{w['asset']}.npz"))
+        x0, tets, edges = mg.place_body(m["vertices"], lowest_y=1.0), m["tets"], m["edges"]
+    return x0, edges, tets, w
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+def cpu_reference_run(x0, edges, tets, w, sample_substeps, frames, warm, threads):
+    """Time the reference's own CPU path (oracle/_ref = unmodified Sim.cpp; else the C port) on a
+    bounded sample: `frames` steps of `sample_substeps` substeps at the workload's substep dt."""
+    from oracle import pyoracle as po
+    kind = "reference" if po.have("reference") else "port"
+    if kind == "port":
+        po.build()
+    prm = po.Params.default(substeps=sample_substeps, iterations=w["iterations"])
+    dt = DT * sample_substeps / w["substeps"]            # same substep dt as the full workload
+    ora = po.Oracle(prm, x0, edges, tets, kind=kind, threads=threads if kind == "reference" else 0)
+    for _ in range(warm):
+        ora.step(dt)
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        ora.step(dt)
+    sec = time.perf_counter() - t0
+    st = ora.stats()
+    ora.close()
+    return dict(kind=kind, seconds=sec, substeps=frames * sample_substeps, stats=st, name=ora.name())
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    pkg = importlib.import_module("cs121-softbodysim_b200")
+    x0, edges, tets, w = make_workload(args.workload, pkg.meshgen)
+    ncpu = os.cpu_count() or 1
+    # each step = a bounded sample: 2 substeps of the full mesh (~0.9 s at 1M tets)
+    sample = 2 if len(tets) > 200000 else w["substeps"]
+    r = cpu_reference_run(x0, edges, tets, w, sample, args.steps, args.warmup, threads=ncpu)
+    val = r["substeps"] / r["seconds"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "iterations": w["iterations"], "substeps_per_frame": w["substeps"],
+                   "step": f"{sample} substeps of the full mesh (bounded sample of one {w['substeps']}-substep frame)"},
+        "tet_constraints_per_s": val * len(tets) * w["iterations"],
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": r["kind"],
+                         "threads_offered": ncpu,
+                         "sample": f"{args.steps} x {sample} substeps after {args.warmup} warm-up steps; "
+                                   f"ParallelStepper(threads={ncpu}) -- its constraint sweeps are serial "
+                                   "(Sim.cpp:334-337), so the hot loop uses 1 core"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--backend", default="auto", choices=["auto", "stream", "tile"])
+    ap.add_argument("--order", default="strict", choices=["strict", "interleaved"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if dist:
+        dist.barrier()
+    pkg = ge.package()
+    capi, mg = pkg.capi, pkg.meshgen
+
+    x0, edges, tets, w = make_workload(args.workload, mg)
+    V, E, T = len(x0), len(edges), len(tets)
+    S, I = w["substeps"], w["iterations"]
+    prm = capi.SolverParams.default(substeps=S, iterations=I)
+    opt = capi.Options(backend={"auto": 0, "stream": 1, "tile": 2}[args.backend],
+                       order_mode=1 if args.order == "interleaved" else 0)
+
+    t0 = time.perf_counter()
+    stepper = capi.CudaStepper(device=local, options=opt)
+    state = capi.PBDState(prm, x0, edges, tets)
+    body = stepper._bind(state)                      # MSG_INIT: plan + upload (not in the timed region)
+    init_ms = (time.perf_counter() - t0) * 1e3
+    info = body.info()
+
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    host_pos = torch.empty(3 * V, dtype=torch.float32).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-timed region: K frames, inputs resident in HBM, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        body.step_async(DT, 1)
+        body.sync()
+    sampler = ClockSampler(local)
+    sync_all()
+    sampler.start()
+    dev_ms = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.zero_()                            # evict L2 (126 MB) between timed frames; not timed
+            torch.cuda.synchronize()
+        body.step_async(DT, 1)
+        dev_ms.append(body.sync())                   # ms between the library's events around the frame
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    sync_all()
+    total_ms = sum(dev_ms)
+    if dist:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+
+    # ---- end-to-end through the stepper API with host buffers (step + pack D2H into pinned memory)
+    stats = capi.StepStats()
+    for _ in range(2):
+        stepper.step(state, DT, stats)
+        body.read_positions(out_ptr=host_pos.data_ptr())
+    sync_all()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        stepper.step(state, DT, stats)
+        body.read_positions(out_ptr=host_pos.data_ptr())
+    e2e_s = time.perf_counter() - e0
+    clocks = sampler.stop()
+    if dist:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    pos = host_pos.numpy().reshape(-1, 3)
+    sane = bool(np.isfinite(pos).all() and pos[:, 1].min() >= -1e-5)
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    substeps_total = world * args.steps * S
+    value = substeps_total / (total_ms * 1e-3)
+    bytes_sub = info["algorithmic_bytes_per_substep"]
+    frame_ms = total_ms / args.steps
+    achieved = bytes_sub * S / (frame_ms * 1e-3) / 1e9
+    peak, peak_src = load_peaks()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "V": V, "E": E, "T": T, "substeps_per_frame": S, "iterations": I,
+                   "dt": DT, "backend": body.name(), "order_mode": args.order,
+                   "parallelism": f"{world} independent bodies, one per GPU, no collective" if world > 1 else "1 GPU",
+                   "l2": "not flushed" if flush is None else "flushed between timed frames (256 MiB memset, untimed)",
+                   "working_set_bytes": info["device_bytes"]},
+        "tet_constraints_per_s": value * T * I,
+        "substeps_per_s_per_gpu": value / world,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "whole frame = %d launches of %s" % (info["launches_per_frame"], body.name()),
+                     "algorithmic_bytes_per_substep": bytes_sub, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "e2e": {"value": world * args.steps * S / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 52,
+                "d2h_bytes_per_step": 12 * V, "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "CudaStepper.step(state, dt) + pack_positions -> pinned host buffer (C ABI pbd_step + pbd_read_positions)"},
+        "gpu_launches": args.steps * info["launches_per_frame"],
+        "clocks": clocks,
+        "init_ms": init_ms, "plan_ms": info["plan_ms"], "wall_ms_timed_region": wall_ms,
+        "schedule": {k: info[k] for k in ("edge_colors", "tet_colors", "edge_phases", "tet_phases", "tiles",
+                                          "launches_per_frame", "grid_blocks", "block_threads")},
+        "sane": sane,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        sample = 2 if T > 200000 else S
+        frames = 3 if T > 200000 else max(1, int(2e8 / max(1, (20 * E + 45 * T) * I * sample)))
+        r = cpu_reference_run(x0, edges, tets, w, sample, frames, 1, threads=0)
+        cv = r["substeps"] / r["seconds"]
+        line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": 1, "kind": r["kind"],
+                                "sample": f"{frames} x {sample} substeps (same mesh, same substep dt) after 1 warm-up; "
+                                          f"SerialStepper on 1 of {os.cpu_count()} host cores",
+                                "solve_fraction": r["stats"]["solveMs"] / max(r["stats"]["totalMs"], 1e-9)}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    stepper.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

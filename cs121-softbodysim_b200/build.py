@@ -1,0 +1,57 @@
+"""Build libpbd_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with gpurun)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libpbd_b200.so")
+SOURCES = ["pbd_plan.cpp", "pbd_tileplan.cpp", "pbd_stream.cu", "pbd_tile.cu", "pbd_batch.cu", "pbd_capi.cu"]
+HEADERS = ["pbd_plan.h", "pbd_body.h", "pbd_math.cuh", os.path.join("..", "..", "include", "pbd_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only; no PTX for other archs, no fallbacks
+    "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false",                                   # belt and braces: the math uses explicit *_rn intrinsics
+    "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-Xptxas", "-v",
+    "--shared", "-cudart", "static",
+]
+
+
+def nvcc_path() -> str:
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source into cs121-softbodysim_b200/libpbd_b200.so; returns its path."""
+    if not force and not stale():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = os.path.join(HERE, "build.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed (see {log})")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

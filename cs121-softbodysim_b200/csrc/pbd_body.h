@@ -1,0 +1,66 @@
+// pbd_body.h -- device-resident state of one (or a batch of) soft bodies + backend interface.
+//
+// HBM layout (SoA of float4, SURVEY.md 7 "float4 SoA"):
+//   pos [V] float4  (xStar.x, xStar.y, xStar.z, invMass)   -- the array every projection gathers/scatters
+//   prev[V] float4  (x.x, x.y, x.z, unused)                -- committed positions
+//   vel [V] float4  (v.x, v.y, v.z, unused)
+//   edgeRest/edgeLam [E] f32, tetRest/tetLam [T] f32        -- schedule order
+//   constraint indices: backend specific (stream: uint2/uint4 vertex slots; tile: u16 tile-local)
+// "slot" = device vertex index; slotOf[callerVertex] (null = identity) maps the caller's order.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "pbd_math.cuh"
+#include "pbd_plan.h"
+
+namespace pbd {
+
+struct DeviceArrays {
+  uint32_t V = 0, E = 0, T = 0;
+  float4* pos = nullptr;
+  float4* prev = nullptr;
+  float4* vel = nullptr;
+  float* edgeRest = nullptr;
+  float* edgeLam = nullptr;
+  float* tetRest = nullptr;
+  float* tetLam = nullptr;
+  uint32_t* slotOf = nullptr;   // [V] caller vertex -> slot (nullptr: identity)
+  float* packed = nullptr;      // [3V] readback staging, caller order
+  StepConsts* consts = nullptr; // device copy of the per-frame scalars
+  uint64_t bytes = 0;
+};
+
+struct FrameShape {
+  uint32_t substeps = 1;    // already clamped to >= 1
+  uint32_t iterations = 0;
+  int groundEnabled = 0;
+};
+
+class Backend {
+ public:
+  virtual ~Backend() {}
+  virtual const char* name() const = 0;
+  // upload the backend-specific constraint tables; returns cudaSuccess or the failing error
+  virtual cudaError_t upload(const Plan& plan, const MeshView& mesh, DeviceArrays& d) = 0;
+  // enqueue one frame (all substeps) on `s`; the per-frame scalars are already in d.consts
+  virtual cudaError_t enqueue_frame(const DeviceArrays& d, const FrameShape& f, cudaStream_t s) = 0;
+  virtual uint32_t launches_per_frame(const FrameShape& f) const = 0;
+  virtual void invalidate() {}  // frame shape changed (set_params)
+  virtual uint64_t device_bytes() const = 0;
+  virtual void fill_info(pbd_info& info) const {}
+  // optional per-stage timing (stream backend); returns false if unsupported
+  virtual bool stage_ms(double& predict, double& solve, double& commit) { return false; }
+};
+
+Backend* make_stream_backend(uint32_t flags, uint32_t blockThreads);
+Backend* make_tile_backend(const pbd_options& opts, int device);
+
+// shared vertex-stage kernels (pbd_stream.cu)
+cudaError_t launch_pack(const DeviceArrays& d, cudaStream_t s);
+
+StepConsts make_consts(const pbd_params& p, float dt);
+
+}  // namespace pbd

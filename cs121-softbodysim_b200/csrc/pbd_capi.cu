@@ -1,0 +1,447 @@
+// pbd_capi.cu -- the extern "C" boundary declared in include/pbd_b200.h.
+//
+// Host side of the drop-in: what comm_loop does for MSG_INIT (CProgram/src/Server.cpp:30-114)
+// becomes pbd_create (validate, derive w / rest values on the host exactly like
+// compute_inv_mass / build_rest, build the parallel schedule, upload once); IStepper::step
+// becomes pbd_step; IStepper::pack_positions becomes pbd_read_positions.  No CPU fallback:
+// without a CUDA device every computing entry fails with PBD_ERR_NO_DEVICE.
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "pbd_body.h"
+
+using namespace pbd;
+
+namespace {
+
+thread_local std::string g_err;
+
+double wall_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int fail(int code, const std::string& msg, int* status = nullptr) {
+  g_err = msg;
+  if (status) *status = code;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what, int* status = nullptr) {
+  const int code = (e == cudaErrorMemoryAllocation) ? PBD_ERR_OOM
+                   : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? PBD_ERR_NO_DEVICE
+                                                                                   : PBD_ERR_CUDA;
+  return fail(code, std::string(what) + ": " + cudaGetErrorString(e), status);
+}
+
+#define CU(call)                                                   \
+  do {                                                             \
+    cudaError_t e__ = (call);                                      \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);          \
+  } while (0)
+
+pbd_options resolve_options(const pbd_options* in) {
+  pbd_options o;
+  std::memset(&o, 0, sizeof(o));
+  if (in) {
+    size_t n = in->struct_size ? in->struct_size : sizeof(pbd_options);
+    if (n > sizeof(pbd_options)) n = sizeof(pbd_options);
+    std::memcpy(&o, in, n);
+  }
+  o.struct_size = sizeof(pbd_options);
+  return o;
+}
+
+template <class T>
+cudaError_t dev_alloc(T** p, size_t n, uint64_t& bytes) {
+  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (n + 1));
+  if (e == cudaSuccess) bytes += sizeof(T) * n;
+  return e;
+}
+
+void free_arrays(DeviceArrays& d) {
+  cudaFree(d.pos); cudaFree(d.prev); cudaFree(d.vel);
+  cudaFree(d.edgeRest); cudaFree(d.edgeLam); cudaFree(d.tetRest); cudaFree(d.tetLam);
+  cudaFree(d.slotOf); cudaFree(d.packed); cudaFree(d.consts);
+  d = DeviceArrays{};
+}
+
+}  // namespace
+
+struct pbd_plan {
+  Plan plan;
+  pbd_options opts;
+};
+
+struct pbd_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  pbd_params params{};
+  pbd_options opts{};
+  Plan plan;
+  DeviceArrays d;
+  std::unique_ptr<Backend> be;
+  double uploadMs = 0.0;
+  bool pending = false;
+
+  ~pbd_handle() {
+    be.reset();
+    free_arrays(d);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  FrameShape shape() const {
+    FrameShape f;
+    f.substeps = params.substeps > 1u ? params.substeps : 1u;
+    f.iterations = params.iterations;
+    f.groundEnabled = params.groundEnabled ? 1 : 0;
+    return f;
+  }
+};
+
+namespace {
+
+bool build_plan(const MeshView& m, const pbd_options& o, int nSMs, uint32_t smemVerts, Plan& plan, std::string& err) {
+  uint32_t backend = o.backend;
+  if (backend == PBD_BACKEND_AUTO) backend = PBD_BACKEND_STREAM;
+  if (backend == PBD_BACKEND_STREAM) {
+    if (o.order_mode != PBD_ORDER_STRICT) { err = "stream backend supports PBD_ORDER_STRICT only"; return false; }
+    build_stream_plan(m, plan);
+    return true;
+  }
+  if (backend == PBD_BACKEND_TILE) return build_tile_plan(m, o, (uint32_t)nSMs, smemVerts, plan, err);
+  err = "unknown backend";
+  return false;
+}
+
+void base_info(const Plan& p, const pbd_params* prm, pbd_info& out) {
+  std::memset(&out, 0, sizeof(out));
+  out.V = p.V; out.E = p.E; out.T = p.T;
+  out.backend = p.backend;
+  out.edge_colors = p.edgeColorSum; out.tet_colors = p.tetColorSum;
+  out.edge_phases = p.edgePhases; out.tet_phases = p.tetPhases;
+  out.tiles = (uint32_t)p.tiles.size();
+  out.plan_ms = p.planMs;
+  out.algorithmic_bytes_per_substep = algorithmic_bytes_per_substep(p.V, p.E, p.T, prm ? prm->iterations : 6);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pbd_abi_version(void) { return PBD_ABI_VERSION; }
+const char* pbd_last_error(void) { return g_err.c_str(); }
+
+int pbd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_t T, const float* x0,
+                       const uint32_t* edgeIds, const uint32_t* tetIds, const uint32_t* pinned,
+                       uint32_t nPinned, int device, const pbd_options* opts, int* status) {
+  if (status) *status = PBD_OK;
+  if (!params) { fail(PBD_ERR_INVALID, "params is null", status); return nullptr; }
+  if (nPinned && !pinned) { fail(PBD_ERR_INVALID, "pinned is null", status); return nullptr; }
+  MeshView m{V, E, T, x0, edgeIds, tetIds};
+  std::string err;
+  if (!validate_mesh(m, err)) {
+    fail(err.find("out of range") != std::string::npos ? PBD_ERR_INDEX : PBD_ERR_INVALID, err, status);
+    return nullptr;
+  }
+  int nDev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&nDev);
+  if (ce != cudaSuccess || nDev == 0) {
+    cudaGetLastError();
+    fail(PBD_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)", status);
+    return nullptr;
+  }
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= nDev) { fail(PBD_ERR_INVALID, "device ordinal out of range", status); return nullptr; }
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) { cuda_fail(ce, "cudaSetDevice", status); return nullptr; }
+
+  std::unique_ptr<pbd_handle> h(new pbd_handle());
+  h->device = device;
+  h->params = *params;
+  h->opts = resolve_options(opts);
+
+  cudaDeviceProp prop{};
+  if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { cuda_fail(ce, "cudaGetDeviceProperties", status); return nullptr; }
+  const uint32_t smemVerts = (uint32_t)((prop.sharedMemPerBlockOptin > 4096 ? prop.sharedMemPerBlockOptin - 4096 : 0) / sizeof(float4));
+  if (!build_plan(m, h->opts, prop.multiProcessorCount, smemVerts, h->plan, err)) {
+    fail(PBD_ERR_INVALID, err, status);
+    return nullptr;
+  }
+  const Plan& plan = h->plan;
+
+  // reference init helpers on the host, caller's order (bit-exact): Sim.cpp:63-95
+  std::vector<float> w, eRest, tRest;
+  host_inverse_mass(m, pinned, nPinned, w);
+  host_rest_state(m, eRest, tRest);
+
+  const double tUp = wall_ms();
+  DeviceArrays& d = h->d;
+  d.V = V; d.E = E; d.T = T;
+  auto bail = [&](cudaError_t e, const char* what) { cuda_fail(e, what, status); return nullptr; };
+  if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
+  if ((ce = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(ce, "cudaEventCreate");
+  if ((ce = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(ce, "cudaEventCreate");
+  if ((ce = dev_alloc(&d.pos, V, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc pos");
+  if ((ce = dev_alloc(&d.prev, V, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc prev");
+  if ((ce = dev_alloc(&d.vel, V, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc vel");
+  if ((ce = dev_alloc(&d.edgeRest, E, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc edgeRest");
+  if ((ce = dev_alloc(&d.edgeLam, E, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc edgeLam");
+  if ((ce = dev_alloc(&d.tetRest, T, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc tetRest");
+  if ((ce = dev_alloc(&d.tetLam, T, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc tetLam");
+  if ((ce = dev_alloc(&d.packed, (size_t)V * 3, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc packed");
+  if ((ce = dev_alloc(&d.consts, 1, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc consts");
+
+  bool identity = true;
+  for (uint32_t i = 0; i < V && identity; ++i) identity = plan.vertexToSlot[i] == i;
+  if (!identity) {
+    if ((ce = dev_alloc(&d.slotOf, V, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc slotOf");
+    if ((ce = cudaMemcpy(d.slotOf, plan.vertexToSlot.data(), sizeof(uint32_t) * V, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload slotOf");
+  }
+  {
+    std::vector<float4> pos(V), prev(V);
+    for (uint32_t v = 0; v < V; ++v) {
+      const uint32_t s = plan.vertexToSlot[v];
+      pos[s] = make_float4(x0[3 * (size_t)v], x0[3 * (size_t)v + 1], x0[3 * (size_t)v + 2], w[v]);
+      prev[s] = make_float4(x0[3 * (size_t)v], x0[3 * (size_t)v + 1], x0[3 * (size_t)v + 2], 0.0f);
+    }
+    if (V && (ce = cudaMemcpy(d.pos, pos.data(), sizeof(float4) * V, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload pos");
+    if (V && (ce = cudaMemcpy(d.prev, prev.data(), sizeof(float4) * V, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload prev");
+    if ((ce = cudaMemset(d.vel, 0, sizeof(float4) * ((size_t)V + 1))) != cudaSuccess) return bail(ce, "memset vel");
+    std::vector<float> tmp(std::max(E, T));
+    for (uint32_t k = 0; k < E; ++k) tmp[k] = eRest[plan.edgeOrder[k]];
+    if (E && (ce = cudaMemcpy(d.edgeRest, tmp.data(), sizeof(float) * E, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload edgeRest");
+    for (uint32_t k = 0; k < T; ++k) tmp[k] = tRest[plan.tetOrder[k]];
+    if (T && (ce = cudaMemcpy(d.tetRest, tmp.data(), sizeof(float) * T, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload tetRest");
+    if ((ce = cudaMemset(d.edgeLam, 0, sizeof(float) * ((size_t)E + 1))) != cudaSuccess) return bail(ce, "memset edgeLam");
+    if ((ce = cudaMemset(d.tetLam, 0, sizeof(float) * ((size_t)T + 1))) != cudaSuccess) return bail(ce, "memset tetLam");
+  }
+  if (plan.backend == PBD_BACKEND_STREAM) h->be.reset(make_stream_backend(h->opts.flags, h->opts.block_threads));
+  else h->be.reset(make_tile_backend(h->opts, device));
+  if (!h->be) { fail(PBD_ERR_UNSUPPORTED, "backend not available", status); return nullptr; }
+  if ((ce = h->be->upload(plan, m, d)) != cudaSuccess) return bail(ce, "backend upload");
+  if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return bail(ce, "cudaDeviceSynchronize");
+  h->uploadMs = wall_ms() - tUp;
+  return h.release();
+}
+
+void pbd_destroy(pbd_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  delete h;
+}
+
+const char* pbd_backend_name(const pbd_handle* h) { return h && h->be ? h->be->name() : "none"; }
+
+static int enqueue_frames(pbd_handle* h, float dt, uint32_t frames) {
+  CU(cudaSetDevice(h->device));
+  const StepConsts k = make_consts(h->params, dt);
+  CU(cudaMemcpyAsync(h->d.consts, &k, sizeof(k), cudaMemcpyHostToDevice, h->stream));
+  const FrameShape f = h->shape();
+  CU(cudaEventRecord(h->ev0, h->stream));
+  for (uint32_t i = 0; i < frames; ++i) CU(h->be->enqueue_frame(h->d, f, h->stream));
+  CU(cudaEventRecord(h->ev1, h->stream));
+  h->pending = true;
+  return PBD_OK;
+}
+
+int pbd_step_async(pbd_handle* h, float dt, uint32_t frames) {
+  if (!h) return fail(PBD_ERR_INVALID, "handle is null");
+  return enqueue_frames(h, dt, frames);
+}
+
+int pbd_sync(pbd_handle* h, double* device_ms) {
+  if (!h) return fail(PBD_ERR_INVALID, "handle is null");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (device_ms) {
+    float ms = 0.f;
+    if (h->pending) CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *device_ms = ms;
+  }
+  h->pending = false;
+  return PBD_OK;
+}
+
+int pbd_step(pbd_handle* h, float dt, pbd_step_stats* stats) {
+  if (!h) return fail(PBD_ERR_INVALID, "handle is null");
+  const double t0 = wall_ms();
+  int rc = enqueue_frames(h, dt, 1);
+  if (rc != PBD_OK) return rc;
+  double devMs = 0.0;
+  rc = pbd_sync(h, &devMs);
+  if (rc != PBD_OK) return rc;
+  if (stats) {
+    double p = 0, s = 0, c = 0;
+    if (h->be->stage_ms(p, s, c)) { stats->predictMs += p; stats->solveMs += s; stats->commitMs += c; }
+    else stats->solveMs += devMs;
+    stats->totalMs += wall_ms() - t0;
+  }
+  return PBD_OK;
+}
+
+int pbd_read_positions(pbd_handle* h, float* out, double* packMs) {
+  if (!h || !out) return fail(PBD_ERR_INVALID, "null argument");
+  const double t0 = wall_ms();
+  CU(cudaSetDevice(h->device));
+  CU(launch_pack(h->d, h->stream));
+  if (h->d.V) CU(cudaMemcpyAsync(out, h->d.packed, sizeof(float) * 3 * (size_t)h->d.V, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (packMs) *packMs += wall_ms() - t0;
+  return PBD_OK;
+}
+
+int pbd_set_params(pbd_handle* h, const pbd_params* p) {
+  if (!h || !p) return fail(PBD_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  h->params = *p;
+  h->be->invalidate();
+  return PBD_OK;
+}
+
+int pbd_get_info(const pbd_handle* h, pbd_info* out) {
+  if (!h || !out) return fail(PBD_ERR_INVALID, "null argument");
+  base_info(h->plan, &h->params, *out);
+  h->be->fill_info(*out);
+  out->launches_per_frame = h->be->launches_per_frame(h->shape());
+  out->device_bytes = h->d.bytes + h->be->device_bytes();
+  out->upload_ms = h->uploadMs;
+  return PBD_OK;
+}
+
+int pbd_get_schedule_order(const pbd_handle* h, uint32_t* eo, uint32_t* to) {
+  if (!h) return fail(PBD_ERR_INVALID, "handle is null");
+  if (eo && h->plan.E) std::memcpy(eo, h->plan.edgeOrder.data(), sizeof(uint32_t) * h->plan.E);
+  if (to && h->plan.T) std::memcpy(to, h->plan.tetOrder.data(), sizeof(uint32_t) * h->plan.T);
+  return PBD_OK;
+}
+
+static int plan_sequence(const Plan& p, uint32_t* items) {
+  if (!items) return fail(PBD_ERR_INVALID, "items is null");
+  // strict order: all edges in schedule order, then all tets
+  if (p.orderMode == PBD_ORDER_STRICT) {
+    for (uint32_t k = 0; k < p.E; ++k) items[k] = k;
+    for (uint32_t k = 0; k < p.T; ++k) items[p.E + k] = 0x80000000u | k;
+    return PBD_OK;
+  }
+  // interleaved: walk phases -> tiles -> groups
+  size_t n = 0;
+  for (const Phase& ph : p.phases)
+    for (uint32_t t = ph.tileBegin; t < ph.tileBegin + ph.tileCount; ++t) {
+      const Tile& tl = p.tiles[t];
+      for (uint32_t g = tl.groupBegin; g < tl.groupBegin + tl.groupCount; ++g)
+        for (uint32_t j = 0; j < p.groups[g].count; ++j)
+          items[n++] = (tl.isTet ? 0x80000000u : 0u) | (p.groups[g].begin + j);
+    }
+  return PBD_OK;
+}
+
+int pbd_get_schedule_sequence(const pbd_handle* h, uint32_t* items) {
+  if (!h) return fail(PBD_ERR_INVALID, "handle is null");
+  return plan_sequence(h->plan, items);
+}
+
+int pbd_get_array(pbd_handle* h, int what, float* out) {
+  if (!h || !out) return fail(PBD_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  const Plan& p = h->plan;
+  const DeviceArrays& d = h->d;
+  auto vec4 = [&](const float4* src, int comps, bool wOnly) -> int {
+    std::vector<float4> tmp(d.V);
+    if (d.V) CU(cudaMemcpy(tmp.data(), src, sizeof(float4) * d.V, cudaMemcpyDeviceToHost));
+    for (uint32_t v = 0; v < d.V; ++v) {
+      const float4 q = tmp[p.vertexToSlot[v]];
+      if (wOnly) out[v] = q.w;
+      else { out[(size_t)comps * v] = q.x; out[(size_t)comps * v + 1] = q.y; out[(size_t)comps * v + 2] = q.z; }
+    }
+    return PBD_OK;
+  };
+  auto scal = [&](const float* src, uint32_t n, const std::vector<uint32_t>& order) -> int {
+    std::vector<float> tmp(n);
+    if (n) CU(cudaMemcpy(tmp.data(), src, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < n; ++k) out[order[k]] = tmp[k];
+    return PBD_OK;
+  };
+  switch (what) {
+    case PBD_ARRAY_INV_MASS: return vec4(d.pos, 1, true);
+    case PBD_ARRAY_XSTAR: return vec4(d.pos, 3, false);
+    case PBD_ARRAY_VELOCITY: return vec4(d.vel, 3, false);
+    case PBD_ARRAY_EDGE_REST: return scal(d.edgeRest, d.E, p.edgeOrder);
+    case PBD_ARRAY_EDGE_LAMBDA: return scal(d.edgeLam, d.E, p.edgeOrder);
+    case PBD_ARRAY_TET_REST: return scal(d.tetRest, d.T, p.tetOrder);
+    case PBD_ARRAY_TET_LAMBDA: return scal(d.tetLam, d.T, p.tetOrder);
+    default: return fail(PBD_ERR_INVALID, "unknown array id");
+  }
+}
+
+/* ---- schedule only (host) ---- */
+
+pbd_plan* pbd_plan_create(uint32_t V, uint32_t E, uint32_t T, const float* x0, const uint32_t* edgeIds,
+                          const uint32_t* tetIds, const pbd_options* opts, int* status) {
+  if (status) *status = PBD_OK;
+  MeshView m{V, E, T, x0, edgeIds, tetIds};
+  std::string err;
+  if (!validate_mesh(m, err)) {
+    fail(err.find("out of range") != std::string::npos ? PBD_ERR_INDEX : PBD_ERR_INVALID, err, status);
+    return nullptr;
+  }
+  std::unique_ptr<pbd_plan> p(new pbd_plan());
+  p->opts = resolve_options(opts);
+  // B200 defaults when no device is consulted: 148 SMs, 227 KB opt-in shared memory per CTA
+  if (!build_plan(m, p->opts, 148, (227u * 1024u - 4096u) / 16u, p->plan, err)) {
+    fail(PBD_ERR_INVALID, err, status);
+    return nullptr;
+  }
+  return p.release();
+}
+
+int pbd_plan_get_info(const pbd_plan* p, pbd_info* out) {
+  if (!p || !out) return fail(PBD_ERR_INVALID, "null argument");
+  base_info(p->plan, nullptr, *out);
+  return PBD_OK;
+}
+
+int pbd_plan_get_order(const pbd_plan* p, uint32_t* eo, uint32_t* to) {
+  if (!p) return fail(PBD_ERR_INVALID, "plan is null");
+  if (eo && p->plan.E) std::memcpy(eo, p->plan.edgeOrder.data(), sizeof(uint32_t) * p->plan.E);
+  if (to && p->plan.T) std::memcpy(to, p->plan.tetOrder.data(), sizeof(uint32_t) * p->plan.T);
+  return PBD_OK;
+}
+
+int pbd_plan_get_sequence(const pbd_plan* p, uint32_t* items) {
+  if (!p) return fail(PBD_ERR_INVALID, "plan is null");
+  return plan_sequence(p->plan, items);
+}
+
+static void copy_slots(const std::vector<uint32_t>& src, uint32_t* dst) {
+  if (dst && !src.empty()) std::memcpy(dst, src.data(), sizeof(uint32_t) * src.size());
+}
+
+int pbd_plan_get_edge_slots(const pbd_plan* p, uint32_t* phase, uint32_t* tile, uint32_t* colour) {
+  if (!p) return fail(PBD_ERR_INVALID, "plan is null");
+  copy_slots(p->plan.edgePhase, phase); copy_slots(p->plan.edgeTile, tile); copy_slots(p->plan.edgeColor, colour);
+  return PBD_OK;
+}
+
+int pbd_plan_get_tet_slots(const pbd_plan* p, uint32_t* phase, uint32_t* tile, uint32_t* colour) {
+  if (!p) return fail(PBD_ERR_INVALID, "plan is null");
+  copy_slots(p->plan.tetPhase, phase); copy_slots(p->plan.tetTile, tile); copy_slots(p->plan.tetColor, colour);
+  return PBD_OK;
+}
+
+void pbd_plan_destroy(pbd_plan* p) { delete p; }
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// pbd_math.cuh -- the per-constraint XPBD arithmetic, shared by every backend.
+//
+// IEEE binary32, round-to-nearest, in the reference's evaluation order and WITHOUT fused
+// multiply-add: the reference is built for baseline x86-64 (SSE2 scalar), so a*b+c rounds twice.
+// Every operation below is an explicit __f{add,sub,mul,div,sqrt}_rn intrinsic, which nvcc never
+// contracts into FFMA and which keeps denormals (no -ftz), so the result is bit-identical to
+// the reference given identical inputs and order.  (The path is latency/bandwidth bound; the
+// extra FADD/FMUL issue slots are not the limiter.)
+//
+// Reference lines restated:
+//   project_edge  CProgram/src/Sim.cpp:104-129   (body of solve_edges_xpbd_gs)
+//   project_tet   CProgram/src/Sim.cpp:136-172   (body of solve_tets_xpbd_gs)
+//   tet volume    CProgram/include/PBDServer.h:140-145
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pbd {
+
+#define PBD_DEV __device__ __forceinline__
+
+PBD_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
+PBD_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
+PBD_DEV float fsub(float a, float b) { return __fsub_rn(a, b); }
+PBD_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// a.y*b.z - a.z*b.y etc. (PBDServer.h:134-136), each product rounded, then the difference
+PBD_DEV float cross_c(float ay, float bz, float az, float by) { return fsub(fmul(ay, bz), fmul(az, by)); }
+// x*x' + y*y' + z*z' left to right (PBDServer.h:133)
+PBD_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+  return fadd(fadd(fmul(ax, bx), fmul(ay, by)), fmul(az, bz));
+}
+
+// Edge-distance projection.  p0/p1 carry (x, y, z, invMass).  Returns false when the reference
+// `continue`s (no write).  lambda is updated in place.
+PBD_DEV bool project_edge(float4& p0, float4& p1, float rest, float& lambda, float alpha) {
+  const float w0 = p0.w, w1 = p1.w;
+  const float wSum = fadd(w0, w1);
+  if (wSum == 0.0f) return false;
+  const float dx = fsub(p0.x, p1.x), dy = fsub(p0.y, p1.y), dz = fsub(p0.z, p1.z);
+  const float len = __fsqrt_rn(dot3(dx, dy, dz, dx, dy, dz));
+  if (len < 1e-12f) return false;
+  const float C = fsub(len, rest);
+  const float dl = fdiv(fsub(-C, fmul(alpha, lambda)), fadd(wSum, alpha));
+  lambda = fadd(lambda, dl);
+  const float inv = fdiv(1.0f, len);
+  const float cx = fmul(fmul(dx, inv), dl), cy = fmul(fmul(dy, inv), dl), cz = fmul(fmul(dz, inv), dl);
+  p0.x = fadd(p0.x, fmul(cx, w0)); p0.y = fadd(p0.y, fmul(cy, w0)); p0.z = fadd(p0.z, fmul(cz, w0));
+  p1.x = fsub(p1.x, fmul(cx, w1)); p1.y = fsub(p1.y, fmul(cy, w1)); p1.z = fsub(p1.z, fmul(cz, w1));
+  return true;
+}
+
+// Tet-volume projection.
+PBD_DEV bool project_tet(float4& pa, float4& pb, float4& pc, float4& pd, float rest, float& lambda,
+                         float alpha) {
+  const float k6 = 1.0f / 6.0f;  // the gradients MULTIPLY by 1/6 (Sim.cpp:146-149) ...
+  const float wa = pa.w, wb = pb.w, wc = pc.w, wd = pd.w;
+  if (fadd(fadd(fadd(wa, wb), wc), wd) == 0.0f) return false;
+
+  const float dbx = fsub(pd.x, pb.x), dby = fsub(pd.y, pb.y), dbz = fsub(pd.z, pb.z);  // pd - pb
+  const float cbx = fsub(pc.x, pb.x), cby = fsub(pc.y, pb.y), cbz = fsub(pc.z, pb.z);  // pc - pb
+  const float cax = fsub(pc.x, pa.x), cay = fsub(pc.y, pa.y), caz = fsub(pc.z, pa.z);  // pc - pa
+  const float dax = fsub(pd.x, pa.x), day = fsub(pd.y, pa.y), daz = fsub(pd.z, pa.z);  // pd - pa
+  const float bax = fsub(pb.x, pa.x), bay = fsub(pb.y, pa.y), baz = fsub(pb.z, pa.z);  // pb - pa
+
+  const float gax = fmul(cross_c(dby, cbz, dbz, cby), k6), gay = fmul(cross_c(dbz, cbx, dbx, cbz), k6),
+              gaz = fmul(cross_c(dbx, cby, dby, cbx), k6);
+  const float gbx = fmul(cross_c(cay, daz, caz, day), k6), gby = fmul(cross_c(caz, dax, cax, daz), k6),
+              gbz = fmul(cross_c(cax, day, cay, dax), k6);
+  const float gcx = fmul(cross_c(day, baz, daz, bay), k6), gcy = fmul(cross_c(daz, bax, dax, baz), k6),
+              gcz = fmul(cross_c(dax, bay, day, bax), k6);
+  // cross(pb-pa, pc-pa): also the normal used by the volume below
+  const float nx = cross_c(bay, caz, baz, cay), ny = cross_c(baz, cax, bax, caz), nz = cross_c(bax, cay, bay, cax);
+  const float gdx = fmul(nx, k6), gdy = fmul(ny, k6), gdz = fmul(nz, k6);
+
+  const float wSum = fadd(fadd(fadd(fmul(wa, dot3(gax, gay, gaz, gax, gay, gaz)),
+                                    fmul(wb, dot3(gbx, gby, gbz, gbx, gby, gbz))),
+                               fmul(wc, dot3(gcx, gcy, gcz, gcx, gcy, gcz))),
+                          fmul(wd, dot3(gdx, gdy, gdz, gdx, gdy, gdz)));
+  if (wSum < 1e-20f) return false;
+
+  // ... while the volume DIVIDES by 6.0f (PBDServer.h:144)
+  const float vol = fdiv(dot3(nx, ny, nz, dax, day, daz), 6.0f);
+  const float C = fsub(vol, rest);
+  const float dl = fdiv(fsub(-C, fmul(alpha, lambda)), fadd(wSum, alpha));
+  lambda = fadd(lambda, dl);
+
+  const float sa = fmul(wa, dl), sb = fmul(wb, dl), sc = fmul(wc, dl), sd = fmul(wd, dl);
+  pa.x = fadd(pa.x, fmul(gax, sa)); pa.y = fadd(pa.y, fmul(gay, sa)); pa.z = fadd(pa.z, fmul(gaz, sa));
+  pb.x = fadd(pb.x, fmul(gbx, sb)); pb.y = fadd(pb.y, fmul(gby, sb)); pb.z = fadd(pb.z, fmul(gbz, sb));
+  pc.x = fadd(pc.x, fmul(gcx, sc)); pc.y = fadd(pc.y, fmul(gcy, sc)); pc.z = fadd(pc.z, fmul(gcz, sc));
+  pd.x = fadd(pd.x, fmul(gdx, sd)); pd.y = fadd(pd.y, fmul(gdy, sd)); pd.z = fadd(pd.z, fmul(gdz, sd));
+  return true;
+}
+
+// Per-frame scalars derived on the host in float exactly as the reference does.
+struct StepConsts {
+  float sdt;          // dt / float(substeps)                      Sim.cpp:286
+  float invDt;        // sdt > 1e-12 ? 1/sdt : 0                   Sim.cpp:198
+  float alphaEdge;    // max(0,edgeCompliance) * invDt2            Sim.cpp:101-102,116
+  float alphaTet;     // max(0,volumeCompliance) * invDt2          Sim.cpp:133-134,162
+  float gdx, gdy, gdz;  // g * sdt (the product the reference forms per vertex, Sim.cpp:182)
+  float groundY;
+  float groundYEps;   // groundY + 1e-6f                            Sim.cpp:212
+  float fricScale;    // 1 - clamp(friction,0,1)                    Sim.cpp:200,213-214
+  int groundEnabled;
+};
+
+// predict for one vertex (Sim.cpp:180-184).  x: committed position, v: velocity (updated).
+PBD_DEV float4 predict_vertex(const float4 x, float4& v, float w, const StepConsts& k) {
+  float4 p;
+  p.w = w;
+  if (w == 0.0f) { p.x = x.x; p.y = x.y; p.z = x.z; return p; }
+  v.x = fadd(v.x, k.gdx); v.y = fadd(v.y, k.gdy); v.z = fadd(v.z, k.gdz);
+  p.x = fadd(x.x, fmul(v.x, k.sdt)); p.y = fadd(x.y, fmul(v.y, k.sdt)); p.z = fadd(x.z, fmul(v.z, k.sdt));
+  return p;
+}
+
+// ground clamp for one vertex (Sim.cpp:190-194)
+PBD_DEV void ground_vertex(float4& p, const StepConsts& k) {
+  if (k.groundEnabled && p.w != 0.0f && p.y < k.groundY) p.y = k.groundY;
+}
+
+// commit for one vertex (Sim.cpp:202-221).  p: xStar (+w); x: committed position, updated; v out.
+PBD_DEV void commit_vertex(float4& p, float4& x, float4& v, const StepConsts& k) {
+  if (p.w == 0.0f) {
+    v.x = v.y = v.z = 0.0f;
+    p.x = x.x; p.y = x.y; p.z = x.z;
+    return;
+  }
+  float vx = fmul(fsub(p.x, x.x), k.invDt), vy = fmul(fsub(p.y, x.y), k.invDt), vz = fmul(fsub(p.z, x.z), k.invDt);
+  if (k.groundEnabled && p.y <= k.groundYEps) {
+    vx = fmul(vx, k.fricScale);
+    vz = fmul(vz, k.fricScale);
+    if (vy < 0.0f) vy = 0.0f;
+  }
+  v.x = vx; v.y = vy; v.z = vz;
+  x.x = p.x; x.y = p.y; x.z = p.z;
+}
+
+}  // namespace pbd

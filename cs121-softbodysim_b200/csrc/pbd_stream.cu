@@ -1,0 +1,283 @@
+// pbd_stream.cu -- "stream" backend: globally graph-coloured Gauss-Seidel, one launch per colour.
+//
+// The simple, obviously-correct schedule: constraints of one global colour
+// share no vertex, so one thread per constraint gathers its float4 vertices from HBM/L2,
+// projects, and scatters them back without atomics.  A whole frame
+//     S x [ predict ; I x ( nEdgeColours launches ; nTetColours launches ; ground ) ; commit ]
+// is captured once into a CUDA graph (the per-frame scalars live in device memory, so a change
+// of dt does not invalidate it).  This backend is the right tool when each colour moves
+// tens of MB (very large meshes) and the bring-up / fallback path otherwise; the L2-resident
+// 1M-tet headline config is phase-count bound here and is served by the tile backend.
+//
+// Reference functions these kernels replace (CProgram/src/Sim.cpp): predict_serial :178-185,
+// solve_edges_xpbd_gs :100-130, solve_tets_xpbd_gs :132-173, project_ground_serial :187-195,
+// commit_serial :197-222, SerialStepper::pack_positions :307-316.
+#include <vector>
+
+#include "pbd_body.h"
+
+namespace pbd {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__global__ void __launch_bounds__(kBlock) predict_kernel(float4* __restrict__ pos, const float4* __restrict__ prev,
+                                                         float4* __restrict__ vel, uint32_t V,
+                                                         const StepConsts* __restrict__ kc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const StepConsts k = *kc;
+  const float w = pos[i].w;
+  const float4 x = prev[i];
+  if (w == 0.0f) {
+    pos[i] = make_float4(x.x, x.y, x.z, w);
+    return;
+  }
+  float4 v = vel[i];
+  const float4 p = predict_vertex(x, v, w, k);
+  vel[i] = v;
+  pos[i] = p;
+}
+
+__global__ void __launch_bounds__(kBlock) edge_colour_kernel(float4* __restrict__ pos, const uint2* __restrict__ idx,
+                                                             const float* __restrict__ rest, float* __restrict__ lam,
+                                                             uint32_t begin, uint32_t count,
+                                                             const StepConsts* __restrict__ kc) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  const uint32_t e = begin + j;
+  const uint2 id = idx[e];
+  float4 p0 = pos[id.x], p1 = pos[id.y];
+  float l = lam[e];
+  if (project_edge(p0, p1, rest[e], l, kc->alphaEdge)) {
+    lam[e] = l;
+    pos[id.x] = p0;
+    pos[id.y] = p1;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) tet_colour_kernel(float4* __restrict__ pos, const uint4* __restrict__ idx,
+                                                            const float* __restrict__ rest, float* __restrict__ lam,
+                                                            uint32_t begin, uint32_t count,
+                                                            const StepConsts* __restrict__ kc) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  const uint32_t t = begin + j;
+  const uint4 id = idx[t];
+  float4 pa = pos[id.x], pb = pos[id.y], pc = pos[id.z], pd = pos[id.w];
+  float l = lam[t];
+  if (project_tet(pa, pb, pc, pd, rest[t], l, kc->alphaTet)) {
+    lam[t] = l;
+    pos[id.x] = pa;
+    pos[id.y] = pb;
+    pos[id.z] = pc;
+    pos[id.w] = pd;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) ground_kernel(float4* __restrict__ pos, uint32_t V,
+                                                        const StepConsts* __restrict__ kc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  float4 p = pos[i];
+  if (p.w != 0.0f && p.y < kc->groundY) {
+    p.y = kc->groundY;
+    pos[i] = p;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) commit_kernel(float4* __restrict__ pos, float4* __restrict__ prev,
+                                                        float4* __restrict__ vel, uint32_t V,
+                                                        const StepConsts* __restrict__ kc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const StepConsts k = *kc;
+  float4 p = pos[i], x = prev[i], v;
+  commit_vertex(p, x, v, k);
+  v.w = 0.0f;
+  vel[i] = v;
+  if (p.w == 0.0f) pos[i] = p; else prev[i] = x;
+}
+
+__global__ void __launch_bounds__(kBlock) pack_kernel(const float4* __restrict__ prev, const uint32_t* __restrict__ slotOf,
+                                                      float* __restrict__ out, uint32_t V) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const float4 x = prev[slotOf ? slotOf[i] : i];
+  out[3 * (size_t)i + 0] = x.x;
+  out[3 * (size_t)i + 1] = x.y;
+  out[3 * (size_t)i + 2] = x.z;
+}
+
+inline uint32_t blocks_for(uint32_t n) { return (n + kBlock - 1) / kBlock; }
+
+class StreamBackend final : public Backend {
+ public:
+  StreamBackend(uint32_t flags) : flags_(flags) {}
+  ~StreamBackend() override {
+    drop_graph();
+    cudaFree(edgeIdx_);
+    cudaFree(tetIdx_);
+    for (auto& e : ev_) if (e) cudaEventDestroy(e);
+  }
+  const char* name() const override { return "b200-stream"; }
+
+  cudaError_t upload(const Plan& plan, const MeshView& m, DeviceArrays& d) override {
+    edgeOff_ = plan.edgeColorOff;
+    tetOff_ = plan.tetColorOff;
+    std::vector<uint2> e(m.E);
+    for (uint32_t k = 0; k < m.E; ++k) {
+      const uint32_t c = plan.edgeOrder[k];
+      e[k] = make_uint2(plan.vertexToSlot[m.edges[2 * (size_t)c]], plan.vertexToSlot[m.edges[2 * (size_t)c + 1]]);
+    }
+    std::vector<uint4> t(m.T);
+    for (uint32_t k = 0; k < m.T; ++k) {
+      const uint32_t* id = m.tets + 4 * (size_t)plan.tetOrder[k];
+      t[k] = make_uint4(plan.vertexToSlot[id[0]], plan.vertexToSlot[id[1]], plan.vertexToSlot[id[2]],
+                        plan.vertexToSlot[id[3]]);
+    }
+    cudaError_t err;
+    if ((err = cudaMalloc(&edgeIdx_, sizeof(uint2) * (size_t)(m.E + 1))) != cudaSuccess) return err;
+    if ((err = cudaMalloc(&tetIdx_, sizeof(uint4) * (size_t)(m.T + 1))) != cudaSuccess) return err;
+    bytes_ = sizeof(uint2) * (size_t)m.E + sizeof(uint4) * (size_t)m.T;
+    if (m.E && (err = cudaMemcpy(edgeIdx_, e.data(), sizeof(uint2) * (size_t)m.E, cudaMemcpyHostToDevice)) != cudaSuccess) return err;
+    if (m.T && (err = cudaMemcpy(tetIdx_, t.data(), sizeof(uint4) * (size_t)m.T, cudaMemcpyHostToDevice)) != cudaSuccess) return err;
+    (void)d;
+    return cudaSuccess;
+  }
+
+  uint32_t launches_per_frame(const FrameShape& f) const override {
+    const uint32_t nE = nonempty(edgeOff_), nT = nonempty(tetOff_);
+    return f.substeps * (2 + f.iterations * (nE + nT + (f.groundEnabled ? 1 : 0)));
+  }
+  uint64_t device_bytes() const override { return bytes_; }
+  void invalidate() override { drop_graph(); }
+
+  void fill_info(pbd_info& info) const override {
+    info.edge_colors = (uint32_t)(edgeOff_.empty() ? 0 : edgeOff_.size() - 1);
+    info.tet_colors = (uint32_t)(tetOff_.empty() ? 0 : tetOff_.size() - 1);
+    info.edge_phases = info.edge_colors;
+    info.tet_phases = info.tet_colors;
+    info.block_threads = kBlock;
+  }
+
+  cudaError_t enqueue_frame(const DeviceArrays& d, const FrameShape& f, cudaStream_t s) override {
+    if (flags_ & PBD_FLAG_STAGE_TIMING) return record(d, f, s, true);
+    if (flags_ & PBD_FLAG_NO_GRAPH) return record(d, f, s, false);
+    if (!exec_ || !(f.substeps == shape_.substeps && f.iterations == shape_.iterations &&
+                    f.groundEnabled == shape_.groundEnabled)) {
+      drop_graph();
+      cudaError_t err = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+      if (err != cudaSuccess) return err;
+      err = record(d, f, s, false);
+      cudaGraph_t g = nullptr;
+      cudaError_t err2 = cudaStreamEndCapture(s, &g);
+      if (err != cudaSuccess) { if (g) cudaGraphDestroy(g); return err; }
+      if (err2 != cudaSuccess) return err2;
+      err = cudaGraphInstantiate(&exec_, g, 0);
+      cudaGraphDestroy(g);
+      if (err != cudaSuccess) { exec_ = nullptr; return err; }
+      shape_ = f;
+    }
+    return cudaGraphLaunch(exec_, s);
+  }
+
+  bool stage_ms(double& predict, double& solve, double& commit) override {
+    if (!(flags_ & PBD_FLAG_STAGE_TIMING) || marks_.empty()) return false;
+    predict = solve = commit = 0.0;
+    for (size_t i = 0; i + 1 < marks_.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev_[i], ev_[i + 1]);
+      (marks_[i] == 0 ? predict : marks_[i] == 1 ? solve : commit) += ms;
+    }
+    return true;
+  }
+
+ private:
+  static uint32_t nonempty(const std::vector<uint32_t>& off) {
+    uint32_t n = 0;
+    for (size_t c = 0; c + 1 < off.size(); ++c) n += off[c + 1] > off[c];
+    return n;
+  }
+  void drop_graph() {
+    if (exec_) cudaGraphExecDestroy(exec_);
+    exec_ = nullptr;
+  }
+  void mark(int stage, cudaStream_t s) {
+    if (ev_.size() <= marks_.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_.push_back(e);
+    }
+    cudaEventRecord(ev_[marks_.size()], s);
+    marks_.push_back(stage);
+  }
+
+  // stage codes for timing marks: 0 predict, 1 solve, 2 commit, 3 end
+  cudaError_t record(const DeviceArrays& d, const FrameShape& f, cudaStream_t s, bool timed) {
+    if (timed) marks_.clear();
+    const uint32_t vb = blocks_for(d.V);
+    for (uint32_t k = 0; k < f.substeps; ++k) {
+      if (timed) mark(0, s);
+      if (d.V) predict_kernel<<<vb, kBlock, 0, s>>>(d.pos, d.prev, d.vel, d.V, d.consts);
+      if (timed) mark(1, s);
+      for (uint32_t it = 0; it < f.iterations; ++it) {
+        for (size_t c = 0; c + 1 < edgeOff_.size(); ++c) {
+          const uint32_t n = edgeOff_[c + 1] - edgeOff_[c];
+          if (n) edge_colour_kernel<<<blocks_for(n), kBlock, 0, s>>>(d.pos, edgeIdx_, d.edgeRest, d.edgeLam, edgeOff_[c], n, d.consts);
+        }
+        for (size_t c = 0; c + 1 < tetOff_.size(); ++c) {
+          const uint32_t n = tetOff_[c + 1] - tetOff_[c];
+          if (n) tet_colour_kernel<<<blocks_for(n), kBlock, 0, s>>>(d.pos, tetIdx_, d.tetRest, d.tetLam, tetOff_[c], n, d.consts);
+        }
+        if (f.groundEnabled && d.V) ground_kernel<<<vb, kBlock, 0, s>>>(d.pos, d.V, d.consts);
+      }
+      if (timed) mark(2, s);
+      if (d.V) commit_kernel<<<vb, kBlock, 0, s>>>(d.pos, d.prev, d.vel, d.V, d.consts);
+    }
+    if (timed) mark(3, s);
+    return cudaGetLastError();
+  }
+
+  uint32_t flags_;
+  uint2* edgeIdx_ = nullptr;
+  uint4* tetIdx_ = nullptr;
+  std::vector<uint32_t> edgeOff_, tetOff_;
+  uint64_t bytes_ = 0;
+  cudaGraphExec_t exec_ = nullptr;
+  FrameShape shape_{};
+  std::vector<cudaEvent_t> ev_;
+  std::vector<int> marks_;
+};
+
+}  // namespace
+
+Backend* make_stream_backend(uint32_t flags, uint32_t) { return new StreamBackend(flags); }
+
+cudaError_t launch_pack(const DeviceArrays& d, cudaStream_t s) {
+  if (d.V) pack_kernel<<<blocks_for(d.V), kBlock, 0, s>>>(d.prev, d.slotOf, d.packed, d.V);
+  return cudaGetLastError();
+}
+
+StepConsts make_consts(const pbd_params& p, float dt) {
+  // host float arithmetic, same expressions as the reference (Sim.cpp:285-286, 101-102, 198-200)
+  StepConsts k{};
+  const uint32_t ss = p.substeps > 1u ? p.substeps : 1u;
+  const float sdt = dt / float(ss);
+  const float invDt2 = (sdt > 1e-12f) ? (1.0f / (sdt * sdt)) : 0.0f;
+  k.sdt = sdt;
+  k.invDt = (sdt > 1e-12f) ? (1.0f / sdt) : 0.0f;
+  k.alphaEdge = (p.edgeCompliance > 0.0f ? p.edgeCompliance : 0.0f) * invDt2;
+  k.alphaTet = (p.volumeCompliance > 0.0f ? p.volumeCompliance : 0.0f) * invDt2;
+  k.gdx = p.gx * sdt; k.gdy = p.gy * sdt; k.gdz = p.gz * sdt;
+  k.groundY = p.groundY;
+  k.groundYEps = p.groundY + 1e-6f;
+  float fr = p.friction < 1.0f ? p.friction : 1.0f;   // fmin(1, friction)
+  fr = fr > 0.0f ? fr : 0.0f;                          // fmax(0, .)
+  k.fricScale = 1.0f - fr;
+  k.groundEnabled = p.groundEnabled ? 1 : 0;
+  return k;
+}
+
+}  // namespace pbd

@@ -1,0 +1,113 @@
+"""Host logic through the C ABI, no GPU: the library loads, exports every symbol the header
+declares, builds valid deterministic schedules, validates input, and refuses to compute without a
+device (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol(capi):
+    hdr = open(os.path.join(ROOT, "include", "pbd_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(pbd_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared == sorted(capi.ABI_SYMBOLS)
+    L = capi.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} not exported"
+    assert L.pbd_abi_version() == 1
+    assert C.sizeof(capi.SolverParams) == 48           # MSG_INIT parameter block, Server.cpp:38-50
+
+
+def _check_schedule(edges, tets, plan):
+    eo, to = plan.order()
+    E, T = len(edges), len(tets)
+    assert np.array_equal(np.sort(eo), np.arange(E)) and np.array_equal(np.sort(to), np.arange(T))
+    for ids, order, slots in ((edges, eo, plan.slots(False)), (tets, to, plan.slots(True))):
+        ph, tl, co = (s.astype(np.int64) for s in slots)
+        # a group = (phase, tile, colour): no two of its constraints share a vertex
+        key = (ph * (tl.max() + 1 if len(tl) else 1) + tl) * (co.max() + 1 if len(co) else 1) + co
+        arity = ids.shape[1]
+        gk = np.repeat(key, arity)
+        pair = gk * (int(ids.max()) + 1 if ids.size else 1) + ids.ravel().astype(np.int64)
+        assert len(np.unique(pair)) == len(pair), "two constraints of one group share a vertex"
+        # the schedule order walks groups in (phase, tile, colour) order
+        k = key[order]
+        assert (np.diff(k) >= 0).all()
+        # tiles of one phase are vertex-disjoint (they run concurrently on different SMs)
+        tk = np.repeat(ph * (tl.max() + 1 if len(tl) else 1) + tl, arity)
+        vt = np.unique(np.stack([np.repeat(ph, arity), ids.ravel().astype(np.int64), tk], 1), axis=0)
+        _, cnt = np.unique(vt[:, :2], axis=0, return_counts=True)
+        assert cnt.max(initial=1) == 1, "a vertex is touched by two tiles in the same phase"
+
+
+@pytest.mark.parametrize("backend", ["stream"])
+@pytest.mark.parametrize("mesh", ["kuhn7", "icosphere", "bunny", "default"])
+def test_schedule_is_valid_partition_and_deterministic(backend, mesh, capi, meshgen, golden):
+    if mesh.startswith("kuhn"):
+        x0, tets, edges = meshgen.kuhn_grid(int(mesh[4:]))
+    else:
+        m = golden(f"mesh_{mesh}.npz")
+        x0, tets, edges = m["vertices"], m["tets"], m["edges"]
+    opt = capi.Options(backend=getattr(capi, "BACKEND_" + backend.upper()))
+    p1, p2 = capi.Plan(x0, edges, tets, opt), capi.Plan(x0, edges, tets, opt)
+    _check_schedule(edges, tets, p1)
+    for a, b in zip(p1.order(), p2.order()):
+        assert np.array_equal(a, b)
+    info = p1.info()
+    assert info["V"] == len(x0) and info["E"] == len(edges) and info["T"] == len(tets)
+
+
+def test_stream_colour_counts_match_survey_probe(capi, meshgen, golden):
+    """greedy first-fit needs 30 tet + 15 edge colours on the Kuhn grid and
+    101 tet + 54 edge colours on default_Tet."""
+    x0, tets, edges = meshgen.kuhn_grid(8)
+    i = capi.Plan(x0, edges, tets, capi.Options(backend=capi.BACKEND_STREAM)).info()
+    assert 24 <= i["tet_colors"] <= 30 and 14 <= i["edge_colors"] <= 15   # valence 24 / 14 is the floor
+    m = golden("mesh_default.npz")
+    i = capi.Plan(m["vertices"], m["edges"], m["tets"], capi.Options(backend=capi.BACKEND_STREAM)).info()
+    assert (i["tet_colors"], i["edge_colors"]) == (101, 54)
+
+
+def test_input_validation(capi, meshgen):
+    x0, tets, edges = meshgen.kuhn_grid(2)
+    bad = tets.copy()
+    bad[3, 2] = len(x0)
+    with pytest.raises(capi.PBDError) as e:
+        capi.Plan(x0, edges, bad)
+    assert e.value.code == capi.PBD_ERR_INDEX
+    bad_e = edges.copy()
+    bad_e[0, 0] = 2 ** 31
+    with pytest.raises(capi.PBDError) as e:
+        capi.Plan(x0, bad_e, tets)
+    assert e.value.code == capi.PBD_ERR_INDEX
+    # empty inputs are legal (V=0 / E=0 / T=0)
+    capi.Plan(np.zeros((0, 3), np.float32), np.zeros((0, 2), np.uint32), np.zeros((0, 4), np.uint32))
+    capi.Plan(x0, np.zeros((0, 2), np.uint32), tets)
+    capi.Plan(x0, edges, np.zeros((0, 4), np.uint32))
+
+
+def test_no_cpu_fallback(capi, meshgen):
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    x0, tets, edges = meshgen.kuhn_grid(2)
+    with pytest.raises(capi.PBDError) as e:
+        capi.Body(capi.SolverParams.default(), x0, edges, tets)
+    assert e.value.code == capi.PBD_ERR_NO_DEVICE
+    with pytest.raises(capi.PBDError):
+        capi.CudaStepper().step(capi.PBDState(capi.SolverParams.default(), x0, edges, tets), 1 / 60, capi.StepStats())
+
+
+def test_product_code_never_touches_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may use oracle/ (task rule)."""
+    pk = os.path.join(ROOT, "cs121-softbodysim_b200")
+    for dp, _, fns in os.walk(pk):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                src = open(os.path.join(dp, fn)).read()
+                assert "pyoracle" not in src and "pbdo_" not in src and "pbdr_" not in src, fn
+                assert "libpbdoracle" not in src and "libpbdref" not in src, fn
