@@ -71,6 +71,8 @@ struct Plan {
   std::vector<uint16_t> edgeLocal;     // 2E
   std::vector<uint16_t> tetLocal;      // 4T
   uint32_t tileVertexCapacity = 0;     // max vertCount over tiles
+  std::vector<uint32_t> tile0Begin;    // K1+1 slot offsets of the phase-0 (RCB) tiles: a partition of all slots
+  uint32_t blockThreads = 0;           // groups are split so that none exceeds this
   uint32_t edgePhases = 0, tetPhases = 0;
   uint32_t edgeColorSum = 0, tetColorSum = 0;  // sum over phases of the max local colour count
 

@@ -45,7 +45,7 @@ def _check_schedule(edges, tets, plan):
         assert cnt.max(initial=1) == 1, "a vertex is touched by two tiles in the same phase"
 
 
-@pytest.mark.parametrize("backend", ["stream"])
+@pytest.mark.parametrize("backend", ["stream", "tile"])
 @pytest.mark.parametrize("mesh", ["kuhn7", "icosphere", "bunny", "default"])
 def test_schedule_is_valid_partition_and_deterministic(backend, mesh, capi, meshgen, golden):
     if mesh.startswith("kuhn"):
