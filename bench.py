@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--backend", default="auto", choices=["auto", "stream", "tile"])
     ap.add_argument("--order", default="strict", choices=["strict", "interleaved"])
+    ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--tile-vertices", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
     args = ap.parse_args()
@@ -216,7 +218,8 @@ def main():
     S, I = w["substeps"], w["iterations"]
     prm = capi.SolverParams.default(substeps=S, iterations=I)
     opt = capi.Options(backend={"auto": 0, "stream": 1, "tile": 2}[args.backend],
-                       order_mode=1 if args.order == "interleaved" else 0)
+                       order_mode=1 if args.order == "interleaved" else 0,
+                       block_threads=args.block_threads, tile_vertices=args.tile_vertices)
 
     t0 = time.perf_counter()
     stepper = capi.CudaStepper(device=local, options=opt)

@@ -48,7 +48,8 @@ class Backend {
   // enqueue one frame (all substeps) on `s`; the per-frame scalars are already in d.consts
   virtual cudaError_t enqueue_frame(const DeviceArrays& d, const FrameShape& f, cudaStream_t s) = 0;
   virtual uint32_t launches_per_frame(const FrameShape& f) const = 0;
-  virtual void invalidate() {}  // frame shape changed (set_params)
+  virtual void invalidate() {}
+  virtual void debug_dump() {}  // PBD_TILE_TRACE: per-phase timing of the last frame to stderr  // frame shape changed (set_params)
   virtual uint64_t device_bytes() const = 0;
   virtual void fill_info(pbd_info& info) const {}
   // optional per-stage timing (stream backend); returns false if unsupported

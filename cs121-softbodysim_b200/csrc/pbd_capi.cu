@@ -173,7 +173,7 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
 
   cudaDeviceProp prop{};
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { cuda_fail(ce, "cudaGetDeviceProperties", status); return nullptr; }
-  const uint32_t smemVerts = (uint32_t)((prop.sharedMemPerBlockOptin > 4096 ? prop.sharedMemPerBlockOptin - 4096 : 0) / sizeof(float4));
+  const uint32_t smemVerts = (uint32_t)((prop.sharedMemPerBlockOptin > 12288 ? prop.sharedMemPerBlockOptin - 12288 : 0) / sizeof(float4));
   if (!build_plan(m, h->opts, prop.multiProcessorCount, smemVerts, h->plan, err)) {
     fail(PBD_ERR_INVALID, err, status);
     return nullptr;
@@ -271,6 +271,8 @@ int pbd_sync(pbd_handle* h, double* device_ms) {
     *device_ms = ms;
   }
   h->pending = false;
+  static const bool trace = getenv("PBD_TILE_TRACE") != nullptr;
+  if (trace) h->be->debug_dump();
   return PBD_OK;
 }
 
@@ -401,7 +403,7 @@ pbd_plan* pbd_plan_create(uint32_t V, uint32_t E, uint32_t T, const float* x0, c
   std::unique_ptr<pbd_plan> p(new pbd_plan());
   p->opts = resolve_options(opts);
   // B200 defaults when no device is consulted: 148 SMs, 227 KB opt-in shared memory per CTA
-  if (!build_plan(m, p->opts, 148, (227u * 1024u - 4096u) / 16u, p->plan, err)) {
+  if (!build_plan(m, p->opts, 148, (227u * 1024u - 12288u) / 16u, p->plan, err)) {
     fail(PBD_ERR_INVALID, err, status);
     return nullptr;
   }

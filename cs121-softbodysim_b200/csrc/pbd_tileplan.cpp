@@ -361,7 +361,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   plan.orderMode = opts.order_mode;
   if (opts.order_mode != PBD_ORDER_STRICT) { err = "interleaved order is not implemented yet"; return false; }
   const uint32_t blockThreads = opts.block_threads ? opts.block_threads : 512;
-  if (blockThreads % 32 || blockThreads > 1024) { err = "block_threads must be a multiple of 32, <= 1024"; return false; }
+  if (blockThreads % 32 || blockThreads > 512) { err = "block_threads must be a multiple of 32, <= 512"; return false; }
 
   // ---- phase-0 tile count: one tile per SM (a whole number of waves) unless the tiles would
   // not fit in shared memory or the body is small enough for fewer tiles
@@ -458,7 +458,8 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
         while (i < tb.cons.size()) {
           size_t j = i;
           while (j < tb.cons.size() && tb.colour[j] == tb.colour[i]) ++j;
-          const uint32_t n = (uint32_t)(j - i), parts = (n + blockThreads - 1) / blockThreads;
+          const uint32_t lim = ty ? blockThreads / 4 : blockThreads;   // a tet is swept by 4 lanes
+          const uint32_t n = (uint32_t)(j - i), parts = (n + lim - 1) / lim;
           for (uint32_t q = 0; q < parts; ++q) {
             Group g;
             g.begin = (uint32_t)order.size() + (uint32_t)(((uint64_t)n * q) / parts);

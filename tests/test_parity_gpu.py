@@ -238,7 +238,7 @@ def test_full_size_1m_tets_properties_and_one_frame_bit_exact(backend, capi, po,
     body.close()
 
 
-@pytest.mark.parametrize("tile_vertices,block_threads", [(64, 64), (200, 128), (1000, 1024), (0, 256)])
+@pytest.mark.parametrize("tile_vertices,block_threads", [(64, 64), (200, 128), (1000, 512), (0, 256)])
 @pytest.mark.parametrize("mesh", ["kuhn8", "icosphere001"])
 def test_p1_tile_backend_many_small_tiles_bit_exact(mesh, tile_vertices, block_threads, capi, po, meshgen, golden):
     """Forces many tiles / several re-partitioned phases / split colour groups on small meshes, so the
