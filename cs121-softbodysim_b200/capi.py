@@ -87,7 +87,8 @@ class StepStats(C.Structure):
 class Options(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("backend", C.c_uint32), ("order_mode", C.c_uint32),
                 ("flags", C.c_uint32), ("tile_vertices", C.c_uint32), ("block_threads", C.c_uint32),
-                ("max_phases", C.c_uint32), ("reserved", C.c_uint32 * 9)]
+                ("max_phases", C.c_uint32), ("partitions", C.c_uint32), ("lanes_per_tet", C.c_uint32),
+                ("reserved", C.c_uint32 * 7)]
 
     def __init__(self, **kw):
         super().__init__()
@@ -103,7 +104,7 @@ class Info(C.Structure):
                 ("edge_colors", C.c_uint32), ("tet_colors", C.c_uint32),
                 ("edge_phases", C.c_uint32), ("tet_phases", C.c_uint32), ("tiles", C.c_uint32),
                 ("launches_per_frame", C.c_uint32), ("grid_blocks", C.c_uint32), ("block_threads", C.c_uint32),
-                ("reserved32", C.c_uint32 * 4),
+                ("partitions", C.c_uint32), ("lanes_per_tet", C.c_uint32), ("reserved32", C.c_uint32 * 2),
                 ("device_bytes", C.c_uint64), ("algorithmic_bytes_per_substep", C.c_uint64),
                 ("plan_ms", C.c_double), ("upload_ms", C.c_double)]
 

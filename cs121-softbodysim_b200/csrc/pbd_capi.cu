@@ -19,6 +19,9 @@ namespace {
 
 thread_local std::string g_err;
 
+// shared memory the tile kernel keeps for itself (static variables, alignment slack)
+constexpr uint32_t kSmemReserve = 2048;
+
 double wall_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -106,7 +109,7 @@ struct pbd_handle {
 
 namespace {
 
-bool build_plan(const MeshView& m, const pbd_options& o, int nSMs, uint32_t smemVerts, Plan& plan, std::string& err) {
+bool build_plan(const MeshView& m, const pbd_options& o, int nSMs, uint32_t smemBytes, Plan& plan, std::string& err) {
   uint32_t backend = o.backend;
   if (backend == PBD_BACKEND_AUTO) backend = PBD_BACKEND_STREAM;
   if (backend == PBD_BACKEND_STREAM) {
@@ -114,7 +117,7 @@ bool build_plan(const MeshView& m, const pbd_options& o, int nSMs, uint32_t smem
     build_stream_plan(m, plan);
     return true;
   }
-  if (backend == PBD_BACKEND_TILE) return build_tile_plan(m, o, (uint32_t)nSMs, smemVerts, plan, err);
+  if (backend == PBD_BACKEND_TILE) return build_tile_plan(m, o, (uint32_t)nSMs, smemBytes, plan, err);
   err = "unknown backend";
   return false;
 }
@@ -126,6 +129,7 @@ void base_info(const Plan& p, const pbd_params* prm, pbd_info& out) {
   out.edge_colors = p.edgeColorSum; out.tet_colors = p.tetColorSum;
   out.edge_phases = p.edgePhases; out.tet_phases = p.tetPhases;
   out.tiles = (uint32_t)p.tiles.size();
+  out.partitions = p.partitions;
   out.plan_ms = p.planMs;
   out.algorithmic_bytes_per_substep = algorithmic_bytes_per_substep(p.V, p.E, p.T, prm ? prm->iterations : 6);
 }
@@ -173,8 +177,8 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
 
   cudaDeviceProp prop{};
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { cuda_fail(ce, "cudaGetDeviceProperties", status); return nullptr; }
-  const uint32_t smemVerts = (uint32_t)((prop.sharedMemPerBlockOptin > 12288 ? prop.sharedMemPerBlockOptin - 12288 : 0) / sizeof(float4));
-  if (!build_plan(m, h->opts, prop.multiProcessorCount, smemVerts, h->plan, err)) {
+  const uint32_t smemBytes = (uint32_t)(prop.sharedMemPerBlockOptin > kSmemReserve ? prop.sharedMemPerBlockOptin - kSmemReserve : 0);
+  if (!build_plan(m, h->opts, prop.multiProcessorCount, smemBytes, h->plan, err)) {
     fail(PBD_ERR_INVALID, err, status);
     return nullptr;
   }
@@ -195,10 +199,13 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
   if ((ce = dev_alloc(&d.pos, V, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc pos");
   if ((ce = dev_alloc(&d.prev, V, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc prev");
   if ((ce = dev_alloc(&d.vel, V, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc vel");
-  if ((ce = dev_alloc(&d.edgeRest, E, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc edgeRest");
-  if ((ce = dev_alloc(&d.edgeLam, E, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc edgeLam");
-  if ((ce = dev_alloc(&d.tetRest, T, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc tetRest");
-  if ((ce = dev_alloc(&d.tetLam, T, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc tetLam");
+  // constraint arrays live at the plan's device indices (schedule order; the tile backend pads
+  // every tile's range to 16 bytes)
+  const size_t nE = plan.edgeDevCount, nT = plan.tetDevCount;
+  if ((ce = dev_alloc(&d.edgeRest, nE, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc edgeRest");
+  if ((ce = dev_alloc(&d.edgeLam, nE, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc edgeLam");
+  if ((ce = dev_alloc(&d.tetRest, nT, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc tetRest");
+  if ((ce = dev_alloc(&d.tetLam, nT, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc tetLam");
   if ((ce = dev_alloc(&d.packed, (size_t)V * 3, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc packed");
   if ((ce = dev_alloc(&d.consts, 1, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc consts");
 
@@ -218,13 +225,14 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
     if (V && (ce = cudaMemcpy(d.pos, pos.data(), sizeof(float4) * V, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload pos");
     if (V && (ce = cudaMemcpy(d.prev, prev.data(), sizeof(float4) * V, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload prev");
     if ((ce = cudaMemset(d.vel, 0, sizeof(float4) * ((size_t)V + 1))) != cudaSuccess) return bail(ce, "memset vel");
-    std::vector<float> tmp(std::max(E, T));
-    for (uint32_t k = 0; k < E; ++k) tmp[k] = eRest[plan.edgeOrder[k]];
-    if (E && (ce = cudaMemcpy(d.edgeRest, tmp.data(), sizeof(float) * E, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload edgeRest");
-    for (uint32_t k = 0; k < T; ++k) tmp[k] = tRest[plan.tetOrder[k]];
-    if (T && (ce = cudaMemcpy(d.tetRest, tmp.data(), sizeof(float) * T, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload tetRest");
-    if ((ce = cudaMemset(d.edgeLam, 0, sizeof(float) * ((size_t)E + 1))) != cudaSuccess) return bail(ce, "memset edgeLam");
-    if ((ce = cudaMemset(d.tetLam, 0, sizeof(float) * ((size_t)T + 1))) != cudaSuccess) return bail(ce, "memset tetLam");
+    std::vector<float> tmp(std::max(nE, nT), 0.0f);
+    for (uint32_t k = 0; k < E; ++k) tmp[plan.edgeDev[k]] = eRest[plan.edgeOrder[k]];
+    if (nE && (ce = cudaMemcpy(d.edgeRest, tmp.data(), sizeof(float) * nE, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload edgeRest");
+    std::fill(tmp.begin(), tmp.end(), 0.0f);
+    for (uint32_t k = 0; k < T; ++k) tmp[plan.tetDev[k]] = tRest[plan.tetOrder[k]];
+    if (nT && (ce = cudaMemcpy(d.tetRest, tmp.data(), sizeof(float) * nT, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce, "upload tetRest");
+    if ((ce = cudaMemset(d.edgeLam, 0, sizeof(float) * (nE + 1))) != cudaSuccess) return bail(ce, "memset edgeLam");
+    if ((ce = cudaMemset(d.tetLam, 0, sizeof(float) * (nT + 1))) != cudaSuccess) return bail(ce, "memset tetLam");
   }
   if (plan.backend == PBD_BACKEND_STREAM) h->be.reset(make_stream_backend(h->opts.flags, h->opts.block_threads));
   else h->be.reset(make_tile_backend(h->opts, device));
@@ -332,20 +340,19 @@ int pbd_get_schedule_order(const pbd_handle* h, uint32_t* eo, uint32_t* to) {
 
 static int plan_sequence(const Plan& p, uint32_t* items) {
   if (!items) return fail(PBD_ERR_INVALID, "items is null");
-  // strict order: all edges in schedule order, then all tets
-  if (p.orderMode == PBD_ORDER_STRICT) {
+  if (p.backend != PBD_BACKEND_TILE) {
+    // stream backend: all edges in schedule order, then all tets
     for (uint32_t k = 0; k < p.E; ++k) items[k] = k;
     for (uint32_t k = 0; k < p.T; ++k) items[p.E + k] = 0x80000000u | k;
     return PBD_OK;
   }
-  // interleaved: walk phases -> tiles -> groups
+  // tile backend: phases -> tiles -> [edge groups, tet groups] (strict order yields the same list as above)
   size_t n = 0;
   for (const Phase& ph : p.phases)
     for (uint32_t t = ph.tileBegin; t < ph.tileBegin + ph.tileCount; ++t) {
       const Tile& tl = p.tiles[t];
-      for (uint32_t g = tl.groupBegin; g < tl.groupBegin + tl.groupCount; ++g)
-        for (uint32_t j = 0; j < p.groups[g].count; ++j)
-          items[n++] = (tl.isTet ? 0x80000000u : 0u) | (p.groups[g].begin + j);
+      for (uint32_t j = 0; j < tl.edgeCount; ++j) items[n++] = tl.edgeBegin + j;
+      for (uint32_t j = 0; j < tl.tetCount; ++j) items[n++] = 0x80000000u | (tl.tetBegin + j);
     }
   return PBD_OK;
 }
@@ -371,20 +378,21 @@ int pbd_get_array(pbd_handle* h, int what, float* out) {
     }
     return PBD_OK;
   };
-  auto scal = [&](const float* src, uint32_t n, const std::vector<uint32_t>& order) -> int {
-    std::vector<float> tmp(n);
-    if (n) CU(cudaMemcpy(tmp.data(), src, sizeof(float) * n, cudaMemcpyDeviceToHost));
-    for (uint32_t k = 0; k < n; ++k) out[order[k]] = tmp[k];
+  auto scal = [&](const float* src, uint32_t n, uint32_t nDev, const std::vector<uint32_t>& order,
+                  const std::vector<uint32_t>& dev) -> int {
+    std::vector<float> tmp(nDev);
+    if (nDev) CU(cudaMemcpy(tmp.data(), src, sizeof(float) * nDev, cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < n; ++k) out[order[k]] = tmp[dev[k]];
     return PBD_OK;
   };
   switch (what) {
     case PBD_ARRAY_INV_MASS: return vec4(d.pos, 1, true);
     case PBD_ARRAY_XSTAR: return vec4(d.pos, 3, false);
     case PBD_ARRAY_VELOCITY: return vec4(d.vel, 3, false);
-    case PBD_ARRAY_EDGE_REST: return scal(d.edgeRest, d.E, p.edgeOrder);
-    case PBD_ARRAY_EDGE_LAMBDA: return scal(d.edgeLam, d.E, p.edgeOrder);
-    case PBD_ARRAY_TET_REST: return scal(d.tetRest, d.T, p.tetOrder);
-    case PBD_ARRAY_TET_LAMBDA: return scal(d.tetLam, d.T, p.tetOrder);
+    case PBD_ARRAY_EDGE_REST: return scal(d.edgeRest, d.E, p.edgeDevCount, p.edgeOrder, p.edgeDev);
+    case PBD_ARRAY_EDGE_LAMBDA: return scal(d.edgeLam, d.E, p.edgeDevCount, p.edgeOrder, p.edgeDev);
+    case PBD_ARRAY_TET_REST: return scal(d.tetRest, d.T, p.tetDevCount, p.tetOrder, p.tetDev);
+    case PBD_ARRAY_TET_LAMBDA: return scal(d.tetLam, d.T, p.tetDevCount, p.tetOrder, p.tetDev);
     default: return fail(PBD_ERR_INVALID, "unknown array id");
   }
 }
@@ -403,7 +411,7 @@ pbd_plan* pbd_plan_create(uint32_t V, uint32_t E, uint32_t T, const float* x0, c
   std::unique_ptr<pbd_plan> p(new pbd_plan());
   p->opts = resolve_options(opts);
   // B200 defaults when no device is consulted: 148 SMs, 227 KB opt-in shared memory per CTA
-  if (!build_plan(m, p->opts, 148, (227u * 1024u - 12288u) / 16u, p->plan, err)) {
+  if (!build_plan(m, p->opts, 148, 227u * 1024u - kSmemReserve, p->plan, err)) {
     fail(PBD_ERR_INVALID, err, status);
     return nullptr;
   }

@@ -85,6 +85,10 @@ void build_stream_plan(const MeshView& m, Plan& p) {
   p.tetPhase.assign(m.T, 0); p.tetTile.assign(m.T, 0);
   p.edgePhases = ne; p.tetPhases = nt;       // one grid-wide phase (= launch) per colour
   p.edgeColorSum = ne; p.tetColorSum = nt;
+  p.edgeDev.resize(m.E); p.tetDev.resize(m.T);
+  for (uint32_t k = 0; k < m.E; ++k) p.edgeDev[k] = k;
+  for (uint32_t k = 0; k < m.T; ++k) p.tetDev[k] = k;
+  p.edgeDevCount = m.E; p.tetDevCount = m.T;
   p.slotToVertex.resize(m.V); p.vertexToSlot.resize(m.V);
   for (uint32_t i = 0; i < m.V; ++i) p.slotToVertex[i] = p.vertexToSlot[i] = i;
   p.planMs = now_ms() - t0;

@@ -35,18 +35,22 @@ struct Group {
   uint32_t count = 0;
 };
 
+// One (phase, tile): a set of vertices that fits in one SM's shared memory together with the
+// constraints projected on it in this phase.  A tile may carry edges, tets or both; its edge colour
+// groups run first, then its tet colour groups.
 struct Tile {
   uint32_t vertBegin = 0;   // into Plan::tileVerts (device vertex slots), or a contiguous range
   uint32_t vertCount = 0;
   uint32_t contiguous = 0;  // 1: the tile's vertices are the slot range [vertBegin, vertBegin+vertCount)
-  uint32_t groupBegin = 0;  // into Plan::groups
-  uint32_t groupCount = 0;
-  uint32_t isTet = 0;       // strict order: a tile carries one constraint type
+  uint32_t edgeBegin = 0, edgeCount = 0;            // schedule positions of this tile's edges
+  uint32_t tetBegin = 0, tetCount = 0;
+  uint32_t edgeGroupBegin = 0, edgeGroupCount = 0;  // into Plan::groups (one group per local colour)
+  uint32_t tetGroupBegin = 0, tetGroupCount = 0;
+  uint32_t edgeDevBegin = 0, tetDevBegin = 0;       // first device index (16-byte aligned ranges)
 };
 
 struct Phase {
   uint32_t tileBegin = 0, tileCount = 0;
-  uint32_t isTet = 0;
 };
 
 struct Plan {
@@ -71,8 +75,15 @@ struct Plan {
   std::vector<uint16_t> edgeLocal;     // 2E
   std::vector<uint16_t> tetLocal;      // 4T
   uint32_t tileVertexCapacity = 0;     // max vertCount over tiles
+  uint32_t tileRecordBytes = 0;        // max tile_record_bytes over tiles (one shared-memory record buffer)
+  uint32_t partitions = 0;             // number of shifted vertex partitions (main phases per sweep)
+  uint32_t tilesPerPartition = 0;
+  // device index of schedule position k (tile backend pads every tile's range to 16 bytes so it
+  // can be moved with bulk copies; identity for the stream backend)
+  std::vector<uint32_t> edgeDev, tetDev;
+  uint32_t edgeDevCount = 0, tetDevCount = 0;
   std::vector<uint32_t> tile0Begin;    // K1+1 slot offsets of the phase-0 (RCB) tiles: a partition of all slots
-  uint32_t blockThreads = 0;           // groups are split so that none exceeds this
+  uint32_t blockThreads = 0;
   uint32_t edgePhases = 0, tetPhases = 0;
   uint32_t edgeColorSum = 0, tetColorSum = 0;  // sum over phases of the max local colour count
 
@@ -93,8 +104,24 @@ uint32_t greedy_colour(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t
 bool validate_mesh(const MeshView& m, std::string& err);
 
 void build_stream_plan(const MeshView& m, Plan& plan);
-bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, uint32_t smemVertexLimit,
+bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, uint32_t smemBytes,
                      Plan& plan, std::string& err);
+
+// Shared-memory record block of one tile (built by pbd_tile.cu, sized here so the planner can keep
+// every tile within the SM's capacity).  Sections, each padded to 16 bytes:
+//   header 64 B | gathered vertex slots u32[nVertGather] | edge groups uint2[] | tet groups uint2[]
+//   | edge idx u32[nE] | edge rest f32[nE] | tet idx uint2[nT] | tet rest f32[nT]
+//   | edge lambda f32[nE] | tet lambda f32[nT]            (the last two come from the lambda arrays)
+inline uint32_t pad4(uint32_t n) { return (n + 3u) & ~3u; }
+inline uint32_t tile_static_bytes(uint32_t nVertGather, uint32_t nEdgeGroups, uint32_t nTetGroups, uint32_t nE,
+                                  uint32_t nT) {
+  return 64u + 4u * pad4(nVertGather) + 8u * (pad4(nEdgeGroups * 2) / 2) + 8u * (pad4(nTetGroups * 2) / 2) +
+         8u * pad4(nE) + 8u * (pad4(nT * 2) / 2) + 4u * pad4(nT);
+}
+inline uint32_t tile_record_bytes(uint32_t nVertGather, uint32_t nEdgeGroups, uint32_t nTetGroups, uint32_t nE,
+                                  uint32_t nT) {
+  return tile_static_bytes(nVertGather, nEdgeGroups, nTetGroups, nE, nT) + 4u * pad4(nE) + 4u * pad4(nT);
+}
 
 // Reference init helpers restated for the host (bit-exact, caller's constraint order):
 //   inverse masses  CProgram/src/Sim.cpp:63-79 ; rest state  CProgram/src/Sim.cpp:81-95

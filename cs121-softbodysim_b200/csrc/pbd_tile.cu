@@ -1,23 +1,26 @@
 // pbd_tile.cu -- "tile" backend: ONE persistent cooperative kernel per frame.
 //
-// Each CTA owns one shared-memory vertex tile per phase (schedule: pbd_tileplan.cpp):
+// Every CTA walks the schedule of pbd_tileplan.cpp:
 //
 //   for substep, iteration, phase:                        (reference loop nest, Sim.cpp:288-301)
-//     for each tile of the phase assigned to this CTA:
-//        load the tile's float4 (xStar, invMass) vertices HBM/L2 -> shared memory
+//     for each tile of the phase assigned to this CTA (normally exactly one):
+//        wait for the tile's RECORD BLOCK in shared memory.  It was fetched one tile ahead by
+//             cp.async.bulk (TMA bulk copies completing on an mbarrier): tile-local u16 vertex
+//             indices, rest values, colour-group table, gathered vertex slots, and the tile's
+//             lambdas -- everything a sweep needs except the vertex positions
+//        load the tile's float4 (xStar, invMass) vertices L2 -> shared memory
 //             phase 0 of iteration 0 fuses   [ground + commit of the previous substep] + predict
 //             phase 0 of iteration > 0 fuses the ground clamp of the previous iteration
-//        for each local colour group:  one thread per constraint, gather 2/4 vertices from shared
-//             memory, project (pbd_math.cuh), scatter back;  __syncthreads()
-//        store the tile back
+//        for each local colour group of edges, then of tets: one thread (or four lanes) per
+//             constraint, gather 2/4 vertices from shared memory, project (pbd_math.cuh),
+//             scatter back;  __syncthreads()
+//        store the vertices back; bulk-store the tile's lambdas
 //     grid barrier (release/acquire on one L2 counter)
 //   final pass: ground + commit of the last substep.
 //
-// Vertex traffic is coalesced float4 for phase-0 tiles (slots are tile-major) and 16-byte gathers
-// for the re-partitioned phases; constraint records stream as 8-byte (2x/4x u16 tile-local index
-// [+ rest]) coalesced loads, prefetched one colour group ahead so the only latency on the
-// dependent chain is shared memory + arithmetic + the block barrier.  Mutable arrays are accessed
-// with .cg (L2) loads/stores so no stale L1 line can be observed after a grid barrier.
+// The dependent chain of a sweep is therefore shared memory + arithmetic + block barrier per
+// colour, and L2 only once per phase.  Mutable vertex arrays are accessed with .cg (L2)
+// loads/stores so no stale L1 line can be observed after a grid barrier.
 //
 // Replaces (CProgram/src/Sim.cpp): predict_serial :178-185, solve_edges_xpbd_gs :100-130,
 // solve_tets_xpbd_gs :132-173, project_ground_serial :187-195, commit_serial :197-222 and the
@@ -35,40 +38,51 @@ namespace pbd {
 
 namespace {
 
-struct TileDesc {
-  uint32_t vertBegin, vertCount, groupBegin, groupCount;
-  uint32_t contiguous, isTet, pad0, pad1;
+// first 64 bytes of a tile's record block (shared memory); offsets in bytes from the block start
+struct TileHdr {
+  uint32_t vertCount, contiguous, vertBegin, nEdgeGroups;
+  uint32_t nTetGroups, nEdges, nTets, offVertIdx;
+  uint32_t offEdgeGroups, offTetGroups, offEdgeIdx, offEdgeRest;
+  uint32_t offTetIdx, offTetRest, offEdgeLam, offTetLam;
 };
-struct GroupDesc {
-  uint32_t begin, count;
+static_assert(sizeof(TileHdr) == 64, "TileHdr is the 64-byte block header");
+
+// what the copy-issuing thread needs per tile (global memory)
+struct TileCopy {
+  unsigned long long blobOff;   // byte offset of the static part in the blob
+  uint32_t staticBytes;
+  uint32_t edgeDevBegin, edgeLamBytes;   // lambda range: first device index, bytes (multiple of 16)
+  uint32_t tetDevBegin, tetLamBytes;
+  uint32_t pad;
 };
+
 struct PhaseDesc {
   uint32_t tileBegin, tileCount;
 };
+
+constexpr uint32_t kMaxItems = 128;   // tiles one CTA visits per iteration
 
 struct TileParams {
   float4* pos;
   float4* prev;
   float4* vel;
-  const uint2* edgeRec;   // {a | b << 16, float bits of rest}
+  const unsigned char* blob;
+  const TileCopy* copies;
   float* edgeLam;
-  const uint2* tetIdx;    // {a | b << 16, c | d << 16}
-  const float* tetRest;
   float* tetLam;
-  const TileDesc* tiles;
-  const GroupDesc* groups;
   const PhaseDesc* phases;
-  const uint32_t* tileVerts;
   const uint32_t* tile0Begin;   // nTile0 + 1
   const StepConsts* consts;
   unsigned* barrier;
-  long long* ftrace;           // debug: fine-grained clock64 stamps of CTA 0 (phase-major, 128 per phase)
-  unsigned long long* trace;   // debug: [phase][cta][2] globaltimer ns of (start, arrive) in substep 0, last iteration
+  unsigned long long* trace;    // debug: [phase][cta][2] globaltimer ns of (start, arrive), substep 0, last iteration
+  long long* ftrace;            // debug: clock64 stamps of CTA 0, 128 per phase
   uint32_t nTile0, nPhases, substeps, iterations;
-  uint32_t dbgFlags;   // experiments only (PBD_TILE_DBG): 1 = skip lambda stores, 2 = default-policy stores
+  uint32_t recStride;           // bytes of one record buffer
 };
 
 enum LoadMode { LOAD_PLAIN = 0, LOAD_GROUND = 1, LOAD_PREDICT = 2, LOAD_COMMIT_PREDICT = 3 };
+
+// ---------------------------------------------------------------- PTX helpers
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -78,12 +92,48 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void red_release(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// TMA bulk copy global -> shared memory of this CTA, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void* dstSmem, const void* srcGlobal, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dstSmem)),
+               "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// TMA bulk copy shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void* dstGlobal, const void* srcSmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGlobal), "r"(smem_u32(srcSmem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make this thread's generic-proxy shared-memory writes visible to the async proxy (bulk copies)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // All CTAs are co-resident (cooperative launch).  The counter is zeroed before the launch.
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
@@ -96,7 +146,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
   __syncthreads();
 }
 
-// Vertex stage applied while a phase-0 tile is loaded.  p arrives as (xStar, w) from HBM.
+// ---------------------------------------------------------------- vertex stages
+
+// Vertex stage applied while a phase-0 tile is loaded.  p arrives as (xStar, w) from HBM/L2.
 __device__ __forceinline__ float4 load_transform(const TileParams& P, const StepConsts& k, uint32_t s, int mode,
                                                  bool clampFirst) {
   float4 p = __ldcg(P.pos + s);
@@ -117,153 +169,6 @@ __device__ __forceinline__ float4 load_transform(const TileParams& P, const Step
     __stcg(P.vel + s, v);
   }
   return p;
-}
-
-// One prefetched constraint record (registers).  id == NONE32: this thread idles in that group.
-constexpr uint32_t NONE32 = 0xffffffffu;
-constexpr int kPrefetch = 3;        // colour groups in flight per thread (hides ~L2 latency)
-constexpr uint32_t kMaxGroupsSmem = 1024;  // group descriptors staged in shared memory per tile
-
-struct Rec {
-  uint32_t id;
-  uint2 idx;
-  float rest, lam;
-};
-
-template <bool TET>
-__device__ __forceinline__ void fetch_rec(const TileParams& P, const uint2* sg, uint32_t g, uint32_t gcount, Rec& r) {
-  r.id = NONE32;
-  if (g < gcount) {
-    const uint2 gd = sg[g];
-    const uint32_t item = TET ? (threadIdx.x >> 2) : threadIdx.x;   // a tet is shared by 4 lanes
-    if (item < gd.y) {
-      r.id = gd.x + item;
-      if (TET) {
-        r.idx = __ldg(P.tetIdx + r.id);
-        r.rest = __ldg(P.tetRest + r.id);
-        r.lam = __ldcg(P.tetLam + r.id);
-      } else {
-        r.idx = __ldg(P.edgeRec + r.id);
-        r.rest = __uint_as_float(r.idx.y);
-        r.lam = __ldcg(P.edgeLam + r.id);
-      }
-    }
-  }
-}
-
-// `z` is a zero read from shared memory AFTER the preceding block barrier.  Mixing it into the
-// prefetched record makes every use of the record data-dependent on a post-barrier load, so
-// neither nvcc nor ptxas can hoist the consumers (index unpacking, alpha*lambda) up to the point
-// right after the global load -- where an in-order warp would stall for the whole L2 latency
-// and defeat the prefetch (measured: ~1 us per colour step before this, see profiles/).
-template <bool TET>
-__device__ __forceinline__ void apply_rec(const TileParams& P, float4* sv, Rec& r, float alpha, uint32_t z) {
-  if (r.id == NONE32) return;
-  r.idx.x ^= z; r.idx.y ^= z;
-  r.rest = __uint_as_float(__float_as_uint(r.rest) ^ z);
-  r.lam = __uint_as_float(__float_as_uint(r.lam) ^ z);
-  if (TET) {
-    // One tet per 4 adjacent lanes, lane `role` owns vertex `role` (a,b,c,d).  All four gradients
-    // have the form cross(x - o, y - o)/6 (Sim.cpp:146-149):
-    //   ga: o=b x=d y=c | gb: o=a x=c y=d | gc: o=a x=d y=b | gd: o=a x=b y=c
-    // so every lane runs the same instructions on role-selected operands; the reduction terms are
-    // exchanged with quad shuffles and summed in the reference's order, which keeps the result
-    // bit-identical while cutting the per-step dependent instruction stream ~3x.
-    const uint32_t role = threadIdx.x & 3u;
-    const uint32_t lane = threadIdx.x & 31u, base = lane & ~3u;
-    const unsigned m = __activemask();
-    auto pick = [&](uint32_t f) -> uint32_t { return (((f & 2u) ? r.idx.y : r.idx.x) >> ((f & 1u) * 16u)) & 0xffffu; };
-    const uint32_t fo = (0x00000001u >> (role * 8u)) & 3u;        // {1,0,0,0}
-    const uint32_t fx = (0x01030203u >> (role * 8u)) & 3u;        // {3,2,3,1}
-    const uint32_t fy = (0x02010302u >> (role * 8u)) & 3u;        // {2,3,1,2}
-    const uint32_t iown = pick(role);
-    float4 own = sv[iown];
-    const float4 o = sv[pick(fo)], x = sv[pick(fx)], y = sv[pick(fy)];
-    const float wa = __shfl_sync(m, own.w, base), wb = __shfl_sync(m, own.w, base + 1),
-                wc = __shfl_sync(m, own.w, base + 2), wd = __shfl_sync(m, own.w, base + 3);
-    if (fadd(fadd(fadd(wa, wb), wc), wd) != 0.0f) {               // quad-uniform
-      const float k6 = 1.0f / 6.0f;
-      const float ux = fsub(x.x, o.x), uy = fsub(x.y, o.y), uz = fsub(x.z, o.z);
-      const float vx = fsub(y.x, o.x), vy = fsub(y.y, o.y), vz = fsub(y.z, o.z);
-      const float nx = cross_c(uy, vz, uz, vy), ny = cross_c(uz, vx, ux, vz), nz = cross_c(ux, vy, uy, vx);
-      const float gx = fmul(nx, k6), gy = fmul(ny, k6), gz = fmul(nz, k6);
-      const float t = fmul(own.w, dot3(gx, gy, gz, gx, gy, gz));
-      const float ta = __shfl_sync(m, t, base), tb = __shfl_sync(m, t, base + 1), tc = __shfl_sync(m, t, base + 2),
-                  td = __shfl_sync(m, t, base + 3);
-      const float wSum = fadd(fadd(fadd(ta, tb), tc), td);
-      // role 3 holds n = cross(pb-pa, pc-pa) and own - o = pd - pa: the volume numerator
-      const float vn = dot3(nx, ny, nz, fsub(own.x, o.x), fsub(own.y, o.y), fsub(own.z, o.z));
-      const float vol = fdiv(__shfl_sync(m, vn, base + 3), 6.0f);
-      if (!(wSum < 1e-20f)) {                                      // quad-uniform
-        const float C = fsub(vol, r.rest);
-        const float dl = fdiv(fsub(-C, fmul(alpha, r.lam)), fadd(wSum, alpha));
-        const float sc = fmul(own.w, dl);
-        own.x = fadd(own.x, fmul(gx, sc)); own.y = fadd(own.y, fmul(gy, sc)); own.z = fadd(own.z, fmul(gz, sc));
-        sv[iown] = own;
-        if (role == 0) {
-          const float l = fadd(r.lam, dl);
-          if (P.dbgFlags & 2) P.tetLam[r.id] = l; else if (!(P.dbgFlags & 1)) __stcg(P.tetLam + r.id, l);
-        }
-      }
-    }
-  } else {
-    const uint32_t a = r.idx.x & 0xffffu, b = r.idx.x >> 16;
-    float4 p0 = sv[a], p1 = sv[b];
-    if (project_edge(p0, p1, r.rest, r.lam, alpha)) {
-      sv[a] = p0; sv[b] = p1;
-      if (P.dbgFlags & 2) P.edgeLam[r.id] = r.lam; else if (!(P.dbgFlags & 1)) __stcg(P.edgeLam + r.id, r.lam);
-    }
-  }
-}
-
-// Sweep the colour groups of one tile.  sg: the tile's group descriptors in shared memory.
-template <bool TET>
-__device__ __forceinline__ void sweep(const TileParams& P, const uint2* sg, uint32_t gcount, float4* sv, float alpha,
-                                      const volatile uint32_t* zero, long long* ft) {
-  Rec r[kPrefetch];
-  int fi = 4;
-#pragma unroll
-  for (int d = 0; d < kPrefetch; ++d) fetch_rec<TET>(P, sg, d, gcount, r[d]);
-  for (uint32_t g = 0; g < gcount; g += kPrefetch) {
-#pragma unroll
-    for (int d = 0; d < kPrefetch; ++d) {
-      if (g + d < gcount) {   // block-uniform
-        apply_rec<TET>(P, sv, r[d], alpha, *zero);
-        __syncthreads();
-        if (ft && threadIdx.x == 0 && fi < 120) ft[fi++] = clock64();
-        fetch_rec<TET>(P, sg, g + d + kPrefetch, gcount, r[d]);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void run_tile(const TileParams& P, const StepConsts& k, uint32_t tile, int mode,
-                                         float4* sv, uint2* sg, const volatile uint32_t* zero, long long* ft) {
-  if (ft && threadIdx.x == 0) ft[0] = clock64();
-  const TileDesc td = P.tiles[tile];
-  const uint32_t tid = threadIdx.x, nth = blockDim.x;
-  if (td.contiguous) {
-    for (uint32_t i = tid; i < td.vertCount; i += nth) sv[i] = load_transform(P, k, td.vertBegin + i, mode, true);
-  } else {
-    for (uint32_t i = tid; i < td.vertCount; i += nth) sv[i] = __ldcg(P.pos + __ldg(P.tileVerts + td.vertBegin + i));
-  }
-  if (ft && threadIdx.x == 0) ft[1] = clock64();
-  // group descriptors -> shared memory (the record prefetch must not wait on a dependent global load)
-  for (uint32_t gb = 0; gb < td.groupCount; gb += kMaxGroupsSmem) {
-    const uint32_t gn = min(kMaxGroupsSmem, td.groupCount - gb);
-    for (uint32_t i = tid; i < gn; i += nth) sg[i] = __ldg(reinterpret_cast<const uint2*>(P.groups + td.groupBegin + gb + i));
-    __syncthreads();
-    if (ft && threadIdx.x == 0) ft[2] = clock64();
-    if (td.isTet) sweep<true>(P, sg, gn, sv, k.alphaTet, zero, ft); else sweep<false>(P, sg, gn, sv, k.alphaEdge, zero, ft);
-  }
-  if (td.groupCount == 0) __syncthreads();
-  if (td.contiguous) {
-    for (uint32_t i = tid; i < td.vertCount; i += nth) __stcg(P.pos + td.vertBegin + i, sv[i]);
-  } else {
-    for (uint32_t i = tid; i < td.vertCount; i += nth) __stcg(P.pos + __ldg(P.tileVerts + td.vertBegin + i), sv[i]);
-  }
-  __syncthreads();   // sv is reused by the next tile of this CTA
-  if (ft && threadIdx.x == 0) { ft[3] = clock64(); ft[127] = td.groupCount; }
 }
 
 // vertex-only pass over the phase-0 partition (no constraints): used when there is nothing to
@@ -289,34 +194,239 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
   }
 }
 
+// ---------------------------------------------------------------- sweeps (shared memory only)
+
+__device__ __forceinline__ void sweep_edges(const TileHdr& h, unsigned char* rec, float4* sv, float alpha) {
+  const uint2* groups = reinterpret_cast<const uint2*>(rec + h.offEdgeGroups);
+  const uint32_t* idx = reinterpret_cast<const uint32_t*>(rec + h.offEdgeIdx);
+  const float* rest = reinterpret_cast<const float*>(rec + h.offEdgeRest);
+  float* lam = reinterpret_cast<float*>(rec + h.offEdgeLam);
+  for (uint32_t g = 0; g < h.nEdgeGroups; ++g) {
+    const uint2 gd = groups[g];
+    for (uint32_t i = threadIdx.x; i < gd.y; i += blockDim.x) {
+      const uint32_t e = gd.x + i;
+      const uint32_t id = idx[e];
+      const uint32_t a = id & 0xffffu, b = id >> 16;
+      float4 p0 = sv[a], p1 = sv[b];
+      float l = lam[e];
+      if (project_edge(p0, p1, rest[e], l, alpha)) {
+        sv[a] = p0;
+        sv[b] = p1;
+        lam[e] = l;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// LANES == 1: one thread per tet (project_tet).
+// LANES == 4: one tet per 4 adjacent lanes, lane `role` owns vertex `role` (a,b,c,d).  All four
+// gradients have the form cross(x - o, y - o)/6 (Sim.cpp:146-149):
+//   ga: o=b x=d y=c | gb: o=a x=c y=d | gc: o=a x=d y=b | gd: o=a x=b y=c
+// so every lane runs the same instructions on role-selected operands; the reduction terms are
+// exchanged with quad shuffles and summed in the reference's order, which keeps the result
+// bit-identical while shortening the dependent instruction stream of a colour step ~3x.
+template <int LANES>
+__device__ __forceinline__ void sweep_tets(const TileHdr& h, unsigned char* rec, float4* sv, float alpha) {
+  const uint2* groups = reinterpret_cast<const uint2*>(rec + h.offTetGroups);
+  const uint2* idx = reinterpret_cast<const uint2*>(rec + h.offTetIdx);
+  const float* rest = reinterpret_cast<const float*>(rec + h.offTetRest);
+  float* lam = reinterpret_cast<float*>(rec + h.offTetLam);
+  for (uint32_t g = 0; g < h.nTetGroups; ++g) {
+    const uint2 gd = groups[g];
+    if (LANES == 1) {
+      for (uint32_t i = threadIdx.x; i < gd.y; i += blockDim.x) {
+        const uint32_t t = gd.x + i;
+        const uint2 id = idx[t];
+        const uint32_t a = id.x & 0xffffu, b = id.x >> 16, c = id.y & 0xffffu, d = id.y >> 16;
+        float4 pa = sv[a], pb = sv[b], pc = sv[c], pd = sv[d];
+        float l = lam[t];
+        if (project_tet(pa, pb, pc, pd, rest[t], l, alpha)) {
+          sv[a] = pa; sv[b] = pb; sv[c] = pc; sv[d] = pd;
+          lam[t] = l;
+        }
+      }
+    } else {
+      const uint32_t role = threadIdx.x & 3u, lane = threadIdx.x & 31u, qbase = lane & ~3u;
+      const uint32_t fo = (0x00000001u >> (role * 8u)) & 3u;        // {1,0,0,0}
+      const uint32_t fx = (0x01030203u >> (role * 8u)) & 3u;        // {3,2,3,1}
+      const uint32_t fy = (0x02010302u >> (role * 8u)) & 3u;        // {2,3,1,2}
+      const uint32_t quads = blockDim.x >> 2;
+      // warp-uniform trip count: every lane of a warp takes part in the shuffles
+      for (uint32_t i0 = (threadIdx.x >> 5) << 3; i0 < gd.y; i0 += quads) {
+        const uint32_t i = i0 + (lane >> 2);
+        const bool live = i < gd.y;
+        const uint32_t t = gd.x + (live ? i : gd.y - 1u);
+        const uint2 id = idx[t];
+        auto pick = [&](uint32_t f) -> uint32_t { return (((f & 2u) ? id.y : id.x) >> ((f & 1u) * 16u)) & 0xffffu; };
+        const uint32_t iown = pick(role);
+        float4 own = sv[iown];
+        const float4 o = sv[pick(fo)], x = sv[pick(fx)], y = sv[pick(fy)];
+        const float r = rest[t], l0 = lam[t];
+        const unsigned m = 0xffffffffu;
+        const float wa = __shfl_sync(m, own.w, qbase), wb = __shfl_sync(m, own.w, qbase + 1),
+                    wc = __shfl_sync(m, own.w, qbase + 2), wd = __shfl_sync(m, own.w, qbase + 3);
+        const bool massive = fadd(fadd(fadd(wa, wb), wc), wd) != 0.0f;   // quad-uniform
+        const float k6 = 1.0f / 6.0f;
+        const float ux = fsub(x.x, o.x), uy = fsub(x.y, o.y), uz = fsub(x.z, o.z);
+        const float vx = fsub(y.x, o.x), vy = fsub(y.y, o.y), vz = fsub(y.z, o.z);
+        const float nx = cross_c(uy, vz, uz, vy), ny = cross_c(uz, vx, ux, vz), nz = cross_c(ux, vy, uy, vx);
+        const float gx = fmul(nx, k6), gy = fmul(ny, k6), gz = fmul(nz, k6);
+        const float tt = fmul(own.w, dot3(gx, gy, gz, gx, gy, gz));
+        const float ta = __shfl_sync(m, tt, qbase), tb = __shfl_sync(m, tt, qbase + 1), tc = __shfl_sync(m, tt, qbase + 2),
+                    td = __shfl_sync(m, tt, qbase + 3);
+        const float wSum = fadd(fadd(fadd(ta, tb), tc), td);
+        // role 3 holds n = cross(pb-pa, pc-pa) and own - o = pd - pa: the volume numerator
+        const float vn = dot3(nx, ny, nz, fsub(own.x, o.x), fsub(own.y, o.y), fsub(own.z, o.z));
+        const float vol = fdiv(__shfl_sync(m, vn, qbase + 3), 6.0f);
+        if (live && massive && !(wSum < 1e-20f)) {
+          const float C = fsub(vol, r);
+          const float dl = fdiv(fsub(-C, fmul(alpha, l0)), fadd(wSum, alpha));
+          const float sc = fmul(own.w, dl);
+          own.x = fadd(own.x, fmul(gx, sc)); own.y = fadd(own.y, fmul(gy, sc)); own.z = fadd(own.z, fmul(gz, sc));
+          sv[iown] = own;
+          if (role == 0) lam[t] = fadd(l0, dl);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- the frame kernel
+
+template <int LANES>
 __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) {
-  extern __shared__ float4 sv[];
-  __shared__ uint2 sg[kMaxGroupsSmem];
-  __shared__ uint32_t szero;
-  if (threadIdx.x == 0) szero = 0u;
-  __syncthreads();
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long mbar[2];
+  __shared__ uint32_t itemTile[kMaxItems];
+  __shared__ uint32_t nItemsS;
+  unsigned char* const recBuf[2] = {smem, smem + P.recStride};
+  float4* const sv = reinterpret_cast<float4*>(smem + 2 * (size_t)P.recStride);
+
   const StepConsts k = *P.consts;
-  unsigned epoch = 0;
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
   const bool sweeping = P.iterations > 0 && P.nPhases > 0;
   const bool clamp = P.iterations > 0;   // the reference clamps once per iteration (Sim.cpp:296)
-  for (uint32_t sub = 0; sub < P.substeps; ++sub) {
-    if (!sweeping) {
-      // vertex-local work only: a vertex always belongs to the same CTA, no grid barrier needed
-      vertex_pass(P, k, sub == 0 ? LOAD_PREDICT : LOAD_COMMIT_PREDICT, clamp, false);
-      continue;
+
+  if (!sweeping) {
+    // vertex-local work only: a vertex always belongs to the same CTA, no grid barrier needed
+    for (uint32_t sub = 0; sub < P.substeps; ++sub) vertex_pass(P, k, sub == 0 ? LOAD_PREDICT : LOAD_COMMIT_PREDICT, clamp, false);
+    vertex_pass(P, k, LOAD_PLAIN, clamp, true);
+    return;
+  }
+
+  // the tiles this CTA visits in one iteration, in order
+  if (tid == 0) {
+    uint32_t n = 0;
+    for (uint32_t ph = 0; ph < P.nPhases; ++ph) {
+      const PhaseDesc pd = P.phases[ph];
+      for (uint32_t t = blockIdx.x; t < pd.tileCount; t += gridDim.x)
+        if (n < kMaxItems) itemTile[n++] = pd.tileBegin + t;
     }
+    nItemsS = n;
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  __syncthreads();
+  const uint32_t nItems = nItemsS;
+  const uint32_t totalItems = nItems * P.iterations * P.substeps;
+
+  // fetch the record block of tile `t` into buffer `b` (thread 0 only)
+  auto fetch = [&](uint32_t t, uint32_t b) -> TileCopy {
+    const TileCopy c = P.copies[t];
+    unsigned char* dst = recBuf[b];
+    mbar_expect_tx(&mbar[b], c.staticBytes + c.edgeLamBytes + c.tetLamBytes);
+    bulk_load(dst, P.blob + c.blobOff, c.staticBytes, &mbar[b]);
+    if (c.edgeLamBytes) bulk_load(dst + c.staticBytes, P.edgeLam + c.edgeDevBegin, c.edgeLamBytes, &mbar[b]);
+    if (c.tetLamBytes) bulk_load(dst + c.staticBytes + c.edgeLamBytes, P.tetLam + c.tetDevBegin, c.tetLamBytes, &mbar[b]);
+    return c;
+  };
+
+  TileCopy curCopy{}, nextCopy{};   // thread 0 only: lambda ranges of the current / prefetched tile
+  if (tid == 0 && nItems) curCopy = fetch(itemTile[0], 0);
+
+  unsigned epoch = 0;
+  uint32_t item = 0;      // items processed so far by this CTA
+  uint32_t buf = 0;
+  uint32_t parity[2] = {0, 0};
+  bool needWait = true;
+  uint32_t j = 0;         // position in itemTile
+
+  for (uint32_t sub = 0; sub < P.substeps; ++sub) {
     for (uint32_t it = 0; it < P.iterations; ++it) {
       for (uint32_t ph = 0; ph < P.nPhases; ++ph) {
         const PhaseDesc pd = P.phases[ph];
         const int mode = ph != 0 ? LOAD_PLAIN : it != 0 ? LOAD_GROUND : sub != 0 ? LOAD_COMMIT_PREDICT : LOAD_PREDICT;
-        const bool tr = P.trace && sub == 0 && it + 1 == P.iterations && threadIdx.x == 0;
+        const bool tr = P.trace && sub == 0 && it + 1 == P.iterations && tid == 0;
+        long long* ft = (P.ftrace && tr && blockIdx.x == 0) ? P.ftrace + 128 * ph : nullptr;
         if (tr) P.trace[2 * ((size_t)ph * gridDim.x + blockIdx.x)] = globaltimer_ns();
-        for (uint32_t t = blockIdx.x; t < pd.tileCount; t += gridDim.x) run_tile(P, k, pd.tileBegin + t, mode, sv, sg, &szero, (P.ftrace && tr && blockIdx.x == 0) ? P.ftrace + 128 * ph : nullptr);
+        for (uint32_t t = blockIdx.x; t < pd.tileCount; t += gridDim.x) {
+          if (ft) ft[0] = clock64();
+          // ---- record block
+          if (needWait) {
+            while (!mbar_try_wait(&mbar[buf], parity[buf])) {}
+            parity[buf] ^= 1u;
+          }
+          unsigned char* rec = recBuf[buf];
+          const TileHdr h = *reinterpret_cast<const TileHdr*>(rec);
+          if (ft) ft[1] = clock64();
+          // ---- prefetch the next tile's block into the other buffer
+          const uint32_t jn = (j + 1 == nItems) ? 0u : j + 1;
+          const bool hasNext = item + 1 < totalItems;
+          if (tid == 0 && hasNext && nItems > 1) {
+            bulk_wait_all();   // the lambda write-back that last read the other buffer (and its global writes) is complete
+            nextCopy = fetch(itemTile[jn], buf ^ 1u);
+          }
+          // ---- vertices L2 -> shared memory
+          if (h.contiguous) {
+            for (uint32_t i = tid; i < h.vertCount; i += nth) sv[i] = load_transform(P, k, h.vertBegin + i, mode, true);
+          } else {
+            const uint32_t* vidx = reinterpret_cast<const uint32_t*>(rec + h.offVertIdx);
+            for (uint32_t i = tid; i < h.vertCount; i += nth) sv[i] = __ldcg(P.pos + vidx[i]);
+          }
+          __syncthreads();
+          if (ft) ft[2] = clock64();
+          // ---- sweeps
+          sweep_edges(h, rec, sv, k.alphaEdge);
+          if (ft) ft[3] = clock64();
+          sweep_tets<LANES>(h, rec, sv, k.alphaTet);
+          if (ft) ft[4] = clock64();
+          // ---- write back
+          if (h.contiguous) {
+            for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + h.vertBegin + i, sv[i]);
+          } else {
+            const uint32_t* vidx = reinterpret_cast<const uint32_t*>(rec + h.offVertIdx);
+            for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + vidx[i], sv[i]);
+          }
+          fence_async_smem();   // lambdas written by the sweeps -> visible to the bulk store
+          __syncthreads();      // also: sv and rec are free for the next tile
+          if (tid == 0) {
+            const TileCopy c = curCopy;
+            if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
+            if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
+            bulk_commit();
+            if (nItems == 1) bulk_wait_read();   // the block stays resident and is swept again next iteration
+          }
+          if (nItems == 1) {
+            __syncthreads();
+            needWait = false;
+          } else {
+            buf ^= 1u;
+            curCopy = nextCopy;
+          }
+          j = jn;
+          ++item;
+          if (ft) { ft[5] = clock64(); ft[6] = h.nEdgeGroups; ft[7] = h.nTetGroups; ft[8] = h.vertCount; ft[9] = h.nEdges; ft[10] = h.nTets; }
+        }
         if (tr) P.trace[2 * ((size_t)ph * gridDim.x + blockIdx.x) + 1] = globaltimer_ns();
         grid_barrier(P.barrier, epoch);
       }
     }
   }
+  if (tid == 0) bulk_wait_all();
   vertex_pass(P, k, LOAD_PLAIN, clamp, true);
 }
 
@@ -324,94 +434,145 @@ class TileBackend final : public Backend {
  public:
   TileBackend(const pbd_options& o, int device) : opts_(o), device_(device) {}
   ~TileBackend() override {
-    cudaFree(edgeRec_); cudaFree(tetIdx_); cudaFree(tiles_); cudaFree(groups_); cudaFree(phases_);
-    cudaFree(tileVerts_); cudaFree(tile0Begin_); cudaFree(barrier_);
+    cudaFree(blob_); cudaFree(copies_); cudaFree(phases_); cudaFree(tile0Begin_); cudaFree(barrier_);
+    cudaFree(trace_); cudaFree(ftrace_);
   }
   const char* name() const override { return "b200-tile"; }
 
   cudaError_t upload(const Plan& plan, const MeshView& m, DeviceArrays& d) override {
     (void)m;
     cudaError_t err;
-    block_ = plan.blockThreads ? plan.blockThreads : 512;
+    block_ = plan.blockThreads ? std::min(plan.blockThreads, 512u) : 512u;
     nPhases_ = (uint32_t)plan.phases.size();
     nTile0_ = (uint32_t)plan.tile0Begin.size() - 1;
-    nTiles_ = (uint32_t)plan.tiles.size();
-    smemBytes_ = sizeof(float4) * (size_t)std::max(plan.tileVertexCapacity, 1u);
+    lanes_ = opts_.lanes_per_tet == 1 ? 1u : opts_.lanes_per_tet == 4 ? 4u : 4u;
+    if (lanes_ == 4 && block_ % 32) return cudaErrorInvalidValue;
 
-    // device copies of the rest values are already in schedule order (pbd_capi.cu); pack the
-    // edge rest next to the indices so one 8-byte load fetches the whole edge record
-    std::vector<float> eRest(plan.E);
-    if (plan.E && (err = cudaMemcpy(eRest.data(), d.edgeRest, sizeof(float) * plan.E, cudaMemcpyDeviceToHost)) != cudaSuccess) return err;
-    std::vector<uint2> er(plan.E), ti(plan.T);
-    for (uint32_t k = 0; k < plan.E; ++k) {
-      uint32_t bits;
-      memcpy(&bits, &eRest[k], 4);
-      er[k] = make_uint2((uint32_t)plan.edgeLocal[2 * (size_t)k] | ((uint32_t)plan.edgeLocal[2 * (size_t)k + 1] << 16), bits);
+    // rest values are already on the device at the plan's device indices (pbd_capi.cu)
+    std::vector<float> eRest(plan.edgeDevCount), tRest(plan.tetDevCount);
+    if (plan.edgeDevCount && (err = cudaMemcpy(eRest.data(), d.edgeRest, sizeof(float) * plan.edgeDevCount, cudaMemcpyDeviceToHost)) != cudaSuccess) return err;
+    if (plan.tetDevCount && (err = cudaMemcpy(tRest.data(), d.tetRest, sizeof(float) * plan.tetDevCount, cudaMemcpyDeviceToHost)) != cudaSuccess) return err;
+
+    // ---- record blocks
+    std::vector<TileCopy> copies(plan.tiles.size());
+    std::vector<unsigned char> blob;
+    uint32_t recMax = 64;
+    for (size_t ti = 0; ti < plan.tiles.size(); ++ti) {
+      const Tile& t = plan.tiles[ti];
+      const uint32_t nVG = t.contiguous ? 0u : t.vertCount;
+      TileHdr h{};
+      h.vertCount = t.vertCount; h.contiguous = t.contiguous; h.vertBegin = t.contiguous ? t.vertBegin : 0u;
+      h.nEdgeGroups = t.edgeGroupCount; h.nTetGroups = t.tetGroupCount; h.nEdges = t.edgeCount; h.nTets = t.tetCount;
+      uint32_t off = 64;
+      h.offVertIdx = off; off += 4u * pad4(nVG);
+      h.offEdgeGroups = off; off += 8u * (pad4(t.edgeGroupCount * 2) / 2);
+      h.offTetGroups = off; off += 8u * (pad4(t.tetGroupCount * 2) / 2);
+      h.offEdgeIdx = off; off += 4u * pad4(t.edgeCount);
+      h.offEdgeRest = off; off += 4u * pad4(t.edgeCount);
+      h.offTetIdx = off; off += 8u * (pad4(t.tetCount * 2) / 2);
+      h.offTetRest = off; off += 4u * pad4(t.tetCount);
+      const uint32_t staticBytes = off;
+      h.offEdgeLam = off; off += 4u * pad4(t.edgeCount);
+      h.offTetLam = off; off += 4u * pad4(t.tetCount);
+      if (staticBytes != tile_static_bytes(nVG, t.edgeGroupCount, t.tetGroupCount, t.edgeCount, t.tetCount)) return cudaErrorUnknown;
+      recMax = std::max(recMax, off);
+
+      const size_t base = blob.size();
+      blob.resize(base + staticBytes, 0);
+      unsigned char* b = blob.data() + base;
+      memcpy(b, &h, sizeof(h));
+      if (nVG) memcpy(b + h.offVertIdx, &plan.tileVerts[t.vertBegin], 4u * nVG);
+      uint32_t* eg = reinterpret_cast<uint32_t*>(b + h.offEdgeGroups);
+      for (uint32_t g = 0; g < t.edgeGroupCount; ++g) {
+        eg[2 * g] = plan.groups[t.edgeGroupBegin + g].begin - t.edgeBegin;
+        eg[2 * g + 1] = plan.groups[t.edgeGroupBegin + g].count;
+      }
+      uint32_t* tg = reinterpret_cast<uint32_t*>(b + h.offTetGroups);
+      for (uint32_t g = 0; g < t.tetGroupCount; ++g) {
+        tg[2 * g] = plan.groups[t.tetGroupBegin + g].begin - t.tetBegin;
+        tg[2 * g + 1] = plan.groups[t.tetGroupBegin + g].count;
+      }
+      uint32_t* ei = reinterpret_cast<uint32_t*>(b + h.offEdgeIdx);
+      float* er = reinterpret_cast<float*>(b + h.offEdgeRest);
+      for (uint32_t q = 0; q < t.edgeCount; ++q) {
+        const size_t kk = (size_t)t.edgeBegin + q;
+        ei[q] = (uint32_t)plan.edgeLocal[2 * kk] | ((uint32_t)plan.edgeLocal[2 * kk + 1] << 16);
+        er[q] = eRest[plan.edgeDev[kk]];
+      }
+      uint32_t* tix = reinterpret_cast<uint32_t*>(b + h.offTetIdx);
+      float* trs = reinterpret_cast<float*>(b + h.offTetRest);
+      for (uint32_t q = 0; q < t.tetCount; ++q) {
+        const size_t kk = (size_t)t.tetBegin + q;
+        const uint16_t* l = &plan.tetLocal[4 * kk];
+        tix[2 * q] = (uint32_t)l[0] | ((uint32_t)l[1] << 16);
+        tix[2 * q + 1] = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+        trs[q] = tRest[plan.tetDev[kk]];
+      }
+      TileCopy& c = copies[ti];
+      c.blobOff = base;
+      c.staticBytes = staticBytes;
+      c.edgeDevBegin = t.edgeDevBegin; c.edgeLamBytes = 4u * pad4(t.edgeCount);
+      c.tetDevBegin = t.tetDevBegin; c.tetLamBytes = 4u * pad4(t.tetCount);
+      c.pad = 0;
     }
-    for (uint32_t k = 0; k < plan.T; ++k) {
-      const uint16_t* l = &plan.tetLocal[4 * (size_t)k];
-      ti[k] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
-    }
-    std::vector<TileDesc> td(plan.tiles.size());
-    for (size_t i = 0; i < td.size(); ++i) {
-      const Tile& t = plan.tiles[i];
-      td[i] = TileDesc{t.vertBegin, t.vertCount, t.groupBegin, t.groupCount, t.contiguous, t.isTet, 0, 0};
-    }
-    std::vector<GroupDesc> gd(plan.groups.size());
-    for (size_t i = 0; i < gd.size(); ++i) gd[i] = GroupDesc{plan.groups[i].begin, plan.groups[i].count};
+    recStride_ = (recMax + 127u) & ~127u;
+    smemBytes_ = 2 * (size_t)recStride_ + sizeof(float4) * (size_t)std::max(plan.tileVertexCapacity, 1u);
+
     std::vector<PhaseDesc> pd(plan.phases.size());
     maxTilesPerPhase_ = nTile0_;
+    std::vector<uint32_t> perCta;
     for (size_t i = 0; i < pd.size(); ++i) {
       pd[i] = PhaseDesc{plan.phases[i].tileBegin, plan.phases[i].tileCount};
       maxTilesPerPhase_ = std::max(maxTilesPerPhase_, plan.phases[i].tileCount);
     }
     auto up = [&](auto** dst, const auto& src) -> cudaError_t {
       using T = typename std::remove_reference<decltype(src)>::type::value_type;
-      cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * (src.size() + 1));
+      cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * src.size() + 256);
       if (e != cudaSuccess) return e;
       bytes_ += sizeof(T) * src.size();
       if (!src.empty()) e = cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice);
       return e;
     };
-    if ((err = up(&edgeRec_, er)) != cudaSuccess) return err;
-    if ((err = up(&tetIdx_, ti)) != cudaSuccess) return err;
-    if ((err = up(&tiles_, td)) != cudaSuccess) return err;
-    if ((err = up(&groups_, gd)) != cudaSuccess) return err;
+    if ((err = up(&blob_, blob)) != cudaSuccess) return err;
+    if ((err = up(&copies_, copies)) != cudaSuccess) return err;
     if ((err = up(&phases_, pd)) != cudaSuccess) return err;
-    if ((err = up(&tileVerts_, plan.tileVerts)) != cudaSuccess) return err;
     if ((err = up(&tile0Begin_, plan.tile0Begin)) != cudaSuccess) return err;
     if ((err = cudaMalloc((void**)&barrier_, 256)) != cudaSuccess) return err;
     if (getenv("PBD_TILE_TRACE")) {
       traceN_ = 2 * (size_t)(nPhases_ + 1) * 4096;
       if ((err = cudaMalloc((void**)&trace_, sizeof(unsigned long long) * traceN_)) != cudaSuccess) return err;
       cudaMemset(trace_, 0, sizeof(unsigned long long) * traceN_);
-      cudaMalloc((void**)&ftrace_, sizeof(long long) * 128 * (nPhases_ + 1));
+      if ((err = cudaMalloc((void**)&ftrace_, sizeof(long long) * 128 * (nPhases_ + 1))) != cudaSuccess) return err;
       cudaMemset(ftrace_, 0, sizeof(long long) * 128 * (nPhases_ + 1));
     }
 
-    if ((err = cudaFuncSetAttribute(tile_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_)) != cudaSuccess) return err;
+    const void* fn = kernel();
+    if ((err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_)) != cudaSuccess) return err;
     int perSM = 0, nSM = 0, coop = 0;
-    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, tile_frame_kernel, (int)block_, smemBytes_)) != cudaSuccess) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, (int)block_, smemBytes_)) != cudaSuccess) return err;
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, device_);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_);
     if (!coop || perSM < 1) return cudaErrorCooperativeLaunchTooLarge;
-    grid_ = std::max(1u, std::min(maxTilesPerPhase_, (uint32_t)(perSM * nSM)));
+    grid_ = std::max(1u, std::min(maxTilesPerPhase_, (uint32_t)nSM));   // one CTA per SM: a tile owns the SM's shared memory
+    // every CTA's per-iteration tile list must fit the kernel's item table
+    uint64_t items = 0;
+    for (const PhaseDesc& p : pd) items += (p.tileCount + grid_ - 1) / grid_;
+    if (items > kMaxItems) return cudaErrorInvalidConfiguration;
     return cudaSuccess;
   }
 
   cudaError_t enqueue_frame(const DeviceArrays& d, const FrameShape& f, cudaStream_t s) override {
     TileParams P{};
     P.pos = d.pos; P.prev = d.prev; P.vel = d.vel;
-    P.edgeRec = edgeRec_; P.edgeLam = d.edgeLam;
-    P.tetIdx = tetIdx_; P.tetRest = d.tetRest; P.tetLam = d.tetLam;
-    P.tiles = tiles_; P.groups = groups_; P.phases = phases_; P.tileVerts = tileVerts_;
-    P.tile0Begin = tile0Begin_; P.consts = d.consts; P.barrier = barrier_; P.trace = trace_; P.ftrace = ftrace_;
-    P.dbgFlags = getenv("PBD_TILE_DBG") ? (uint32_t)atoi(getenv("PBD_TILE_DBG")) : 0u;
+    P.blob = blob_; P.copies = copies_; P.edgeLam = d.edgeLam; P.tetLam = d.tetLam;
+    P.phases = phases_; P.tile0Begin = tile0Begin_; P.consts = d.consts; P.barrier = barrier_;
+    P.trace = trace_; P.ftrace = ftrace_;
     P.nTile0 = nTile0_; P.nPhases = nPhases_; P.substeps = f.substeps; P.iterations = f.iterations;
+    P.recStride = recStride_;
     cudaError_t err = cudaMemsetAsync(barrier_, 0, sizeof(unsigned), s);
     if (err != cudaSuccess) return err;
     void* args[] = {&P};
-    return cudaLaunchCooperativeKernel((const void*)tile_frame_kernel, dim3(grid_), dim3(block_), args, smemBytes_, s);
+    return cudaLaunchCooperativeKernel(kernel(), dim3(grid_), dim3(block_), args, smemBytes_, s);
   }
 
   void debug_dump() override {
@@ -437,10 +598,8 @@ class TileBackend final : public Backend {
     cudaMemcpy(f.data(), ftrace_, sizeof(long long) * f.size(), cudaMemcpyDeviceToHost);
     for (uint32_t ph = 0; ph < nPhases_; ++ph) {
       const long long* q = &f[128 * (size_t)ph];
-      fprintf(stderr, "[pbd-ftrace] phase %u CTA0: groups %lld | vertex load %lld cyc | desc staging %lld | sweep+store %lld | steps:", ph, q[127], q[1] - q[0], q[2] - q[1], q[3] - q[2]);
-      long long prev = q[2];
-      for (int i = 4; i < 120 && q[i]; ++i) { fprintf(stderr, " %lld", q[i] - prev); prev = q[i]; }
-      fprintf(stderr, "\n");
+      fprintf(stderr, "[pbd-ftrace] phase %u CTA0: verts %lld edges %lld tets %lld | groups %lld+%lld | wait rec %lld cyc | vertex load %lld | edge sweep %lld | tet sweep %lld | store %lld\n",
+              ph, q[8], q[9], q[10], q[6], q[7], q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4]);
     }
   }
   uint32_t launches_per_frame(const FrameShape&) const override { return 1; }
@@ -448,23 +607,24 @@ class TileBackend final : public Backend {
   void fill_info(pbd_info& info) const override {
     info.grid_blocks = grid_;
     info.block_threads = block_;
+    info.lanes_per_tet = lanes_;
   }
 
  private:
+  const void* kernel() const {
+    return lanes_ == 1 ? (const void*)tile_frame_kernel<1> : (const void*)tile_frame_kernel<4>;
+  }
   pbd_options opts_;
   int device_;
-  uint2* edgeRec_ = nullptr;
-  uint2* tetIdx_ = nullptr;
-  TileDesc* tiles_ = nullptr;
-  GroupDesc* groups_ = nullptr;
+  unsigned char* blob_ = nullptr;
+  TileCopy* copies_ = nullptr;
   PhaseDesc* phases_ = nullptr;
-  uint32_t* tileVerts_ = nullptr;
   uint32_t* tile0Begin_ = nullptr;
   unsigned* barrier_ = nullptr;
   unsigned long long* trace_ = nullptr;
   long long* ftrace_ = nullptr;
   size_t traceN_ = 0;
-  uint32_t block_ = 512, grid_ = 1, nPhases_ = 0, nTile0_ = 0, nTiles_ = 0, maxTilesPerPhase_ = 0;
+  uint32_t block_ = 512, grid_ = 1, nPhases_ = 0, nTile0_ = 0, maxTilesPerPhase_ = 0, lanes_ = 4, recStride_ = 128;
   size_t smemBytes_ = 0;
   uint64_t bytes_ = 0;
 };

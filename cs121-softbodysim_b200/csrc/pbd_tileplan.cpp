@@ -1,26 +1,36 @@
-// pbd_tileplan.cpp -- the "tile" schedule: multi-phase shared-memory tiles.
+// pbd_tileplan.cpp -- the "tile" schedule: shifted shared-memory tiles.
 //
 // Why: a globally coloured sweep needs one grid-wide barrier per colour (~46 per iteration on the
-// Kuhn grid, 155 on default_Tet), which caps an L2-resident mesh at ~10 % of the HBM roofline
-// (SURVEY.md 7 "dependent-phase count vs. bytes").  Here the vertices are partitioned into tiles
-// that fit in one SM's shared memory.  A constraint whose vertices all lie in one tile is swept
-// inside that tile with LOCAL colours and block barriers only.  Constraints that straddle tiles
-// form a residual; the residual's own vertices are re-partitioned (graph Voronoi, so the new cuts
-// fall away from the old ones), which makes most of it tile-interior again; and so on until
-// nothing is left.  Per constraint type this takes a handful of grid-wide phases (4-6 on the
-// Kuhn grid) instead of one per colour.
+// Kuhn grid, 155 on default_Tet), which caps an L2-resident mesh at a few % of the HBM roofline
+// (SURVEY.md 7 "dependent-phase count vs. bytes").  Here one iteration is K grid-wide phases
+// (K = 4 by default).  Phase p uses vertex partition P_p: the vertices are cut into as many tiles
+// as there are SMs (k-d style multi-way splits in rank space), and P_1..P_{K-1} are the same cuts
+// CYCLICALLY SHIFTED by p/K of a tile along every axis.  A constraint can run in phase p when all
+// its vertices fall into one tile of P_p ("interior"); with four shifts every constraint of a
+// grid-like mesh is interior to at least one partition, usually to several.  Each constraint is
+// then assigned to ONE of its admissible phases so that every vertex sees about 1/K of its
+// incident constraints per phase: the dependent chain of an iteration (sum over phases of the
+// local colour count) stays close to the vertex valence instead of multiplying with the phases.
+// Inside a (phase, tile) the constraints are coloured locally and swept in shared memory with
+// block barriers only.  Constraints interior to no partition (rare) go through residual phases
+// that re-partition just their own vertices (graph Voronoi), as many as needed.
 //
-// Order: phase by phase, tile by tile, colour by colour, caller index inside a colour.  Tiles of
-// one phase are vertex-disjoint and colour groups are conflict-free, so executing them in
-// parallel equals executing them sequentially in that order: still Gauss-Seidel over the same
-// set, just permuted (disclosed through pbd_get_schedule_order).  PBD_ORDER_STRICT keeps "all
-// edges, then all tets" per iteration like the reference (CProgram/src/Sim.cpp:293-297).
+// Order: phase by phase, tile by tile, [edge colours, then tet colours], caller index inside a
+// colour.  Tiles of one phase are vertex-disjoint and colour groups are conflict-free, so running
+// them in parallel equals running them sequentially in that order: still Gauss-Seidel over the
+// same constraint set, only permuted (disclosed through pbd_get_schedule_order / _sequence).
+//   PBD_ORDER_STRICT       every iteration projects all edges (K phases), then all tets (K phases),
+//                          like the reference (CProgram/src/Sim.cpp:293-297) up to a permutation
+//                          inside each type: the unmodified reference reproduces it bit for bit.
+//   PBD_ORDER_INTERLEAVED  a tile visit projects its edges and then its tets (K phases per
+//                          iteration instead of 2K); checked against the oracle's sequence sweep.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
-#include <queue>
 
 #include "pbd_plan.h"
 
@@ -29,48 +39,60 @@ namespace pbd {
 namespace {
 
 constexpr uint32_t NONE = 0xffffffffu;
+constexpr uint32_t kMaxPartitions = 8;
 
 double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-// ------------------------------------------------------------------ phase 0: RCB vertex tiles
+// ------------------------------------------------------------------ shifted k-d partitions
 
-struct Rcb {
-  const float* x;                 // 3V
-  std::vector<uint32_t> idx;      // permutation being partitioned
-  std::vector<uint32_t> tileOf;   // per vertex
-  std::vector<uint32_t> tileBegin;  // tile -> first position in idx (tiles are contiguous in idx)
-  uint32_t next = 0;
+// Multi-way k-d split in rank space.  Level L sorts the current vertex set along the L-th longest
+// axis of the body and cuts it into parts that receive equal shares of the tiles; `offset` (a
+// fraction of one part) rotates the cuts cyclically, so the last part wraps around to the first.
+struct Partitioner {
+  const float* x = nullptr;
+  int axis[3] = {0, 1, 2};
+  double ext[3] = {1, 1, 1};
+  double offset = 0.0;
+  std::vector<uint32_t> idx;        // permutation being partitioned
+  std::vector<uint32_t> tileBegin;  // leaf ranges in idx
+  uint32_t* tileOf = nullptr;       // per caller vertex
 
-  void split(uint32_t lo, uint32_t hi, uint32_t parts) {
-    if (parts <= 1 || hi - lo <= 1) {
-      const uint32_t t = next++;
-      tileBegin.push_back(lo);
-      std::sort(idx.begin() + lo, idx.begin() + hi);   // caller order inside a tile
-      for (uint32_t i = lo; i < hi; ++i) tileOf[idx[i]] = t;
-      return;
-    }
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (uint32_t i = lo; i < hi; ++i)
-      for (int a = 0; a < 3; ++a) {
-        const float c = x[3 * (size_t)idx[i] + a];
-        mn[a] = std::min(mn[a], c);
-        mx[a] = std::max(mx[a], c);
-      }
-    int ax = 0;
-    for (int a = 1; a < 3; ++a)
-      if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
-    const uint32_t pl = parts / 2, pr = parts - pl;
-    const uint32_t mid = lo + (uint32_t)(((uint64_t)(hi - lo) * pl) / parts);
-    auto cmp = [&](uint32_t a, uint32_t b) {
+  void leaf(uint32_t lo, uint32_t hi) {
+    const uint32_t t = (uint32_t)tileBegin.size();
+    tileBegin.push_back(lo);
+    std::sort(idx.begin() + lo, idx.begin() + hi);   // caller order inside a tile
+    for (uint32_t i = lo; i < hi; ++i) tileOf[idx[i]] = t;
+  }
+
+  void split(uint32_t lo, uint32_t hi, uint32_t nTiles, int level) {
+    const uint32_t n = hi - lo;
+    if (n == 0) return;
+    if (nTiles <= 1 || n <= 1 || level > 2) { leaf(lo, hi); return; }
+    double want;
+    if (level == 2) want = nTiles;
+    else if (level == 1) want = std::sqrt((double)nTiles * ext[1] / ext[2]);
+    else want = std::cbrt((double)nTiles * ext[0] * ext[0] / (ext[1] * ext[2]));
+    uint32_t parts = (uint32_t)std::llround(want);
+    parts = std::max(1u, std::min(parts, std::min(nTiles, n)));
+    if (parts == 1 && level < 2) { split(lo, hi, nTiles, level + 1); return; }
+    const int ax = axis[level];
+    std::sort(idx.begin() + lo, idx.begin() + hi, [&](uint32_t a, uint32_t b) {
       const float ca = x[3 * (size_t)a + ax], cb = x[3 * (size_t)b + ax];
       return ca < cb || (ca == cb && a < b);   // total order -> the split is unique
-    };
-    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, cmp);
-    split(lo, mid, pl);
-    split(mid, hi, pr);
+    });
+    const uint32_t shift = (uint32_t)((offset * n) / parts) % n;
+    if (shift) std::rotate(idx.begin() + lo, idx.begin() + lo + shift, idx.begin() + hi);
+    uint32_t cum = 0;
+    for (uint32_t j = 0; j < parts; ++j) {
+      const uint32_t tj = nTiles / parts + (j < nTiles % parts ? 1u : 0u);
+      const uint32_t b = lo + (uint32_t)(((uint64_t)n * cum) / nTiles);
+      const uint32_t e = lo + (uint32_t)(((uint64_t)n * (cum + tj)) / nTiles);
+      cum += tj;
+      split(b, e, tj, level + 1);
+    }
   }
 };
 
@@ -89,12 +111,11 @@ struct GrownTiles {
 
 // Partition the vertices touched by the residual constraints `res` into tiles of at most `cap`
 // vertices (aiming at `target`), growing them over the residual's own connectivity so that cuts
-// avoid the previous phase's cuts.  tileOfSlot (size V, all NONE on entry) receives the result
-// and is reset by the caller afterwards.
-void grow_tiles(const CSet& cs, const std::vector<uint32_t>& res, uint32_t V, uint32_t cap, uint32_t target,
+// avoid the previous cuts.  tileOfSlot (size V, all NONE on entry) receives the result and is
+// reset by the caller afterwards.
+void grow_tiles(const CSet& cs, const std::vector<uint32_t>& res, uint32_t cap, uint32_t target,
                 std::vector<uint32_t>& compactOf /* size V scratch, all NONE */, GrownTiles& out,
                 std::vector<uint32_t>& tileOfSlot) {
-  // compact vertex set U and CSR vertex -> residual constraints
   std::vector<uint32_t> slots;
   for (uint32_t k : res)
     for (uint32_t j = 0; j < cs.arity; ++j) {
@@ -122,12 +143,11 @@ void grow_tiles(const CSet& cs, const std::vector<uint32_t>& res, uint32_t V, ui
     }
   };
 
-  std::vector<uint32_t> tileOf(U, NONE);   // compact vertex -> tile
+  std::vector<uint32_t> tileOf(U, NONE);
   std::vector<uint32_t> tileSize;
   std::vector<uint32_t> comp(U, NONE), dist(U), queue;
   queue.reserve(U);
 
-  // pending = vertices not yet in a tile; processed as connected components, repeatedly
   std::vector<uint8_t> pending(U, 1);
   uint32_t binTile = NONE;   // tile currently collecting small components
   for (int round = 0; round < 64; ++round) {
@@ -136,7 +156,6 @@ void grow_tiles(const CSet& cs, const std::vector<uint32_t>& res, uint32_t V, ui
     for (uint32_t s0 = 0; s0 < U; ++s0) {
       if (!pending[s0] || comp[s0] != NONE) continue;
       any = true;
-      // BFS the component of s0 among pending vertices
       queue.clear();
       queue.push_back(s0);
       comp[s0] = s0;
@@ -156,16 +175,14 @@ void grow_tiles(const CSet& cs, const std::vector<uint32_t>& res, uint32_t V, ui
         tileSize[binTile] += n;
         continue;
       }
-      // large component: k seeds by farthest-point sampling over hop distance, then
+      // large component: seeds by farthest-point sampling over hop distance, then
       // capacity-limited multi-source BFS (graph Voronoi)
       const uint32_t k = (n + target - 1) / target;
       for (uint32_t u : members) dist[u] = NONE;
       std::vector<uint32_t> seeds;
-      // first seed: the vertex farthest from an arbitrary start (a peripheral vertex)
-      uint32_t far = members.back();   // last vertex reached by the component BFS
+      uint32_t far = members.back();   // last vertex reached by the BFS: a peripheral vertex
       for (uint32_t si = 0; si < k; ++si) {
         seeds.push_back(far);
-        // relax distances from the new seed (bounded: only where it improves)
         queue.clear();
         queue.push_back(far);
         dist[far] = 0;
@@ -205,7 +222,6 @@ void grow_tiles(const CSet& cs, const std::vector<uint32_t>& res, uint32_t V, ui
     }
     if (!any) break;
   }
-  // any vertex still pending after the rounds (pathological) becomes its own bin tiles
   for (uint32_t u = 0; u < U; ++u)
     if (pending[u]) {
       if (binTile == NONE || tileSize[binTile] + 1 > target) { binTile = (uint32_t)tileSize.size(); tileSize.push_back(0); }
@@ -223,75 +239,79 @@ void grow_tiles(const CSet& cs, const std::vector<uint32_t>& res, uint32_t V, ui
   for (uint32_t s : slots) compactOf[s] = NONE;  // leave the scratch clean
 }
 
-// ------------------------------------------------------------------ per-type phase construction
+// ------------------------------------------------------------------ tile construction
+
+struct TypeList {
+  std::vector<uint32_t> cons;     // constraint ids, sorted by (colour, id) after colour_list()
+  std::vector<uint32_t> colour;   // parallel to cons
+  uint32_t nColours = 0;
+};
 
 struct TileBuild {
   bool contiguous = false;
   uint32_t rangeBegin = 0, rangeCount = 0;   // contiguous tiles
   std::vector<uint32_t> verts;               // gathered tiles: slots, ascending
-  std::vector<uint32_t> cons;                // constraint ids of this type, sorted by (colour, id)
-  std::vector<uint32_t> colour;              // parallel to cons
-  uint32_t nColours = 0;
-};
-
-struct TypeSchedule {
-  std::vector<std::vector<TileBuild>> phases;
-  uint32_t colourSum = 0;   // sum over phases of the largest local colour count
+  TypeList ty[2];                            // 0 = edges, 1 = tets
 };
 
 // colour the constraints of one tile locally and sort them by (colour, id)
-void colour_tile(const CSet& cs, TileBuild& tb, const std::vector<uint32_t>& localOf /* slot -> local */,
-                 std::vector<uint32_t>& scratchIds) {
-  const uint32_t n = (uint32_t)tb.cons.size();
-  std::sort(tb.cons.begin(), tb.cons.end());
-  scratchIds.resize((size_t)n * cs.arity);
-  const uint32_t nLocal = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
+void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vector<uint32_t>& localOf,
+                 std::vector<uint32_t>& scratch) {
+  const uint32_t n = (uint32_t)tl.cons.size();
+  std::sort(tl.cons.begin(), tl.cons.end());
+  scratch.resize((size_t)n * cs.arity);
   for (uint32_t i = 0; i < n; ++i)
-    for (uint32_t j = 0; j < cs.arity; ++j) scratchIds[(size_t)i * cs.arity + j] = localOf[cs.at(tb.cons[i])[j]];
+    for (uint32_t j = 0; j < cs.arity; ++j) scratch[(size_t)i * cs.arity + j] = localOf[cs.at(tl.cons[i])[j]];
   std::vector<uint32_t> col;
-  tb.nColours = greedy_colour(scratchIds.data(), n, cs.arity, nLocal, col);
+  tl.nColours = greedy_colour(scratch.data(), n, cs.arity, nLocal, col);
   std::vector<uint32_t> order(n);
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return col[a] < col[b]; });
   std::vector<uint32_t> c2(n), k2(n);
-  for (uint32_t i = 0; i < n; ++i) { c2[i] = tb.cons[order[i]]; k2[i] = col[order[i]]; }
-  tb.cons.swap(c2);
-  tb.colour.swap(k2);
+  for (uint32_t i = 0; i < n; ++i) { c2[i] = tl.cons[order[i]]; k2[i] = col[order[i]]; }
+  tl.cons.swap(c2);
+  tl.colour.swap(k2);
 }
 
-void build_type_schedule(const CSet& cs, uint32_t V, const std::vector<uint32_t>& tile0Begin /* K1+1 */,
-                         const std::vector<uint32_t>& tile0OfSlot, uint32_t cap, uint32_t target,
-                         uint32_t maxPhases, TypeSchedule& ts) {
-  const uint32_t K1 = (uint32_t)tile0Begin.size() - 1;
-  std::vector<uint32_t> localOf(V, NONE), compactOf(V, NONE), tileOfSlot(V, NONE), scratch;
-
-  // phase 0: the RCB tiles (contiguous slot ranges); constraints interior to one tile
-  std::vector<TileBuild> p0(K1);
-  for (uint32_t t = 0; t < K1; ++t) {
-    p0[t].contiguous = true;
-    p0[t].rangeBegin = tile0Begin[t];
-    p0[t].rangeCount = tile0Begin[t + 1] - tile0Begin[t];
+// Finish a tile: vertex list (gathered tiles: the slots its constraints touch), local numbering,
+// colouring of both lists.  localOf is scratch of size V.
+void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& localOf, std::vector<uint32_t>& scratch) {
+  uint32_t nLocal;
+  if (tb.contiguous) {
+    nLocal = tb.rangeCount;
+    for (uint32_t i = 0; i < tb.rangeCount; ++i) localOf[tb.rangeBegin + i] = i;
+  } else {
+    std::vector<uint32_t> used;
+    for (int ty = 0; ty < 2; ++ty)
+      for (uint32_t k : tb.ty[ty].cons)
+        for (uint32_t j = 0; j < sets[ty].arity; ++j) used.push_back(sets[ty].at(k)[j]);
+    std::sort(used.begin(), used.end());
+    used.erase(std::unique(used.begin(), used.end()), used.end());
+    tb.verts.swap(used);
+    nLocal = (uint32_t)tb.verts.size();
+    for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.verts[i]] = i;
   }
-  std::vector<uint32_t> res;
-  for (uint32_t k = 0; k < cs.n; ++k) {
-    const uint32_t* id = cs.at(k);
-    const uint32_t t = tile0OfSlot[id[0]];
-    bool same = true;
-    for (uint32_t j = 1; j < cs.arity; ++j) same &= tile0OfSlot[id[j]] == t;
-    if (same) p0[t].cons.push_back(k); else res.push_back(k);
-  }
-  for (uint32_t s = 0; s < V; ++s) localOf[s] = s - tile0Begin[tile0OfSlot[s]];
-  uint32_t mx = 0;
-  for (auto& tb : p0) { colour_tile(cs, tb, localOf, scratch); mx = std::max(mx, tb.nColours); }
-  ts.colourSum += mx;
-  ts.phases.push_back(std::move(p0));
+  for (int ty = 0; ty < 2; ++ty)
+    if (!tb.ty[ty].cons.empty()) colour_list(sets[ty], tb.ty[ty], nLocal, localOf, scratch);
+}
 
-  // later phases: re-partition the residual
+uint32_t tile_bytes(const TileBuild& tb) {
+  const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
+  const uint32_t rec = tile_record_bytes(tb.contiguous ? 0u : nv, tb.ty[0].nColours, tb.ty[1].nColours,
+                                         (uint32_t)tb.ty[0].cons.size(), (uint32_t)tb.ty[1].cons.size());
+  return 16u * nv + 2u * rec;   // vertices + double-buffered record block
+}
+
+// Residual phases of one type: re-partition until nothing is left.
+void build_residual_phases(const CSet sets[2], int ty, std::vector<uint32_t> res, uint32_t V, uint32_t cap,
+                           std::vector<std::vector<TileBuild>>& phases, std::vector<uint32_t>& localOf,
+                           std::vector<uint32_t>& scratch) {
+  const CSet& cs = sets[ty];
+  std::vector<uint32_t> compactOf(V, NONE), tileOfSlot(V, NONE);
+  const uint32_t target = std::max(16u, (uint32_t)(cap * 0.75));
   while (!res.empty()) {
     GrownTiles g;
-    const bool last = maxPhases && ts.phases.size() + 1 >= maxPhases;
-    (void)last;
-    grow_tiles(cs, res, V, cap, target, compactOf, g, tileOfSlot);
+    grow_tiles(cs, res, cap, target, compactOf, g, tileOfSlot);
     std::vector<TileBuild> ph(g.verts.size());
     std::vector<uint32_t> next;
     for (uint32_t k : res) {
@@ -299,195 +319,339 @@ void build_type_schedule(const CSet& cs, uint32_t V, const std::vector<uint32_t>
       const uint32_t t = tileOfSlot[id[0]];
       bool same = t != NONE;
       for (uint32_t j = 1; j < cs.arity && same; ++j) same = tileOfSlot[id[j]] == t;
-      if (same) ph[t].cons.push_back(k); else next.push_back(k);
+      if (same) ph[t].ty[ty].cons.push_back(k); else next.push_back(k);
     }
     if (next.size() == res.size()) {
       // no progress (cannot happen with hop-distance Voronoi on a connected residual, but stay
       // safe): peel off a vertex-disjoint set of single-constraint tiles
+      for (auto& vs : g.verts)
+        for (uint32_t s : vs) tileOfSlot[s] = NONE;
       ph.clear();
       g.verts.clear();
       next.clear();
-      for (uint32_t s = 0; s < V; ++s) tileOfSlot[s] = NONE;
       for (uint32_t k : res) {
         const uint32_t* id = cs.at(k);
         bool free = true;
         for (uint32_t j = 0; j < cs.arity; ++j) free &= tileOfSlot[id[j]] == NONE;
         if (!free) { next.push_back(k); continue; }
         std::vector<uint32_t> vs(id, id + cs.arity);
-        std::sort(vs.begin(), vs.end());
-        vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
         for (uint32_t s : vs) tileOfSlot[s] = (uint32_t)g.verts.size();
         g.verts.push_back(vs);
         ph.emplace_back();
-        ph.back().cons.push_back(k);
+        ph.back().ty[ty].cons.push_back(k);
       }
     }
-    // drop tiles that received no constraint; fix local numbering; colour
     std::vector<TileBuild> kept;
-    mx = 0;
-    for (uint32_t t = 0; t < ph.size(); ++t) {
-      if (ph[t].cons.empty()) continue;
-      TileBuild& tb = ph[t];
-      // keep only vertices that a constraint of this tile touches
-      std::vector<uint32_t> used;
-      for (uint32_t k : tb.cons)
-        for (uint32_t j = 0; j < cs.arity; ++j) used.push_back(cs.at(k)[j]);
-      std::sort(used.begin(), used.end());
-      used.erase(std::unique(used.begin(), used.end()), used.end());
-      tb.verts.swap(used);
-      for (uint32_t i = 0; i < tb.verts.size(); ++i) localOf[tb.verts[i]] = i;
-      colour_tile(cs, tb, localOf, scratch);
-      mx = std::max(mx, tb.nColours);
+    for (auto& tb : ph) {
+      if (tb.ty[ty].cons.empty()) continue;
+      finish_tile(sets, tb, localOf, scratch);
       kept.push_back(std::move(tb));
     }
     for (auto& vs : g.verts)
       for (uint32_t s : vs) tileOfSlot[s] = NONE;
-    ts.colourSum += mx;
-    ts.phases.push_back(std::move(kept));
+    phases.push_back(std::move(kept));
     res.swap(next);
   }
 }
 
 }  // namespace
 
-bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, uint32_t smemVertexLimit,
-                     Plan& plan, std::string& err) {
+bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, uint32_t smemBytes, Plan& plan,
+                     std::string& err) {
   const double t0 = now_ms();
   if (nSMs == 0) nSMs = 148;
-  if (smemVertexLimit < 64) { err = "shared memory too small for a vertex tile"; return false; }
-  if (smemVertexLimit > 65535) smemVertexLimit = 65535;   // tile-local indices are 16 bit
+  if (smemBytes < 16384) { err = "shared memory too small for a vertex tile"; return false; }
+  plan = Plan();
   plan.V = m.V; plan.E = m.E; plan.T = m.T;
   plan.backend = PBD_BACKEND_TILE;
   plan.orderMode = opts.order_mode;
-  if (opts.order_mode != PBD_ORDER_STRICT) { err = "interleaved order is not implemented yet"; return false; }
+  if (opts.order_mode != PBD_ORDER_STRICT && opts.order_mode != PBD_ORDER_INTERLEAVED) { err = "unknown order_mode"; return false; }
+  const bool fused = opts.order_mode == PBD_ORDER_INTERLEAVED;
   const uint32_t blockThreads = opts.block_threads ? opts.block_threads : 512;
-  if (blockThreads % 32 || blockThreads > 512) { err = "block_threads must be a multiple of 32, <= 512"; return false; }
+  if (blockThreads % 32 || blockThreads > 1024) { err = "block_threads must be a multiple of 32, <= 1024"; return false; }
+  plan.blockThreads = blockThreads;
+  if (opts.partitions > kMaxPartitions) { err = "partitions must be <= 8"; return false; }
 
-  // ---- phase-0 tile count: one tile per SM (a whole number of waves) unless the tiles would
-  // not fit in shared memory or the body is small enough for fewer tiles
-  uint32_t tv = opts.tile_vertices;
+  // body extents -> axis order for the k-d levels
+  Partitioner base;
+  base.x = m.x0;
+  {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t v = 0; v < m.V; ++v)
+      for (int a = 0; a < 3; ++a) {
+        const float c = m.x0[3 * (size_t)v + a];
+        mn[a] = std::min(mn[a], c);
+        mx[a] = std::max(mx[a], c);
+      }
+    double e[3];
+    for (int a = 0; a < 3; ++a) e[a] = m.V ? std::max(0.0, (double)mx[a] - (double)mn[a]) : 1.0;
+    const double big = std::max({e[0], e[1], e[2], 1e-30});
+    for (int a = 0; a < 3; ++a) e[a] = std::max(e[a], big * 1e-3);   // flat bodies: keep the ratios finite
+    std::sort(base.axis, base.axis + 3, [&](int a, int b) { return e[a] > e[b] || (e[a] == e[b] && a < b); });
+    for (int l = 0; l < 3; ++l) base.ext[l] = e[base.axis[l]];
+  }
+
+  // ---- tiles per partition: one tile per SM unless the body is small (fewer, fuller tiles) or
+  // a tile would not fit in shared memory (more tiles, whole waves)
   uint32_t K1;
-  if (tv) {
-    tv = std::min(tv, smemVertexLimit);
-    K1 = std::max(1u, (m.V + tv - 1) / tv);
+  if (opts.tile_vertices) {
+    K1 = std::max(1u, (m.V + opts.tile_vertices - 1) / opts.tile_vertices);
   } else {
     const uint32_t minTile = 1024;   // below this a tile is all interface: use fewer SMs instead
     K1 = std::max(1u, std::min(nSMs, m.V / minTile));
-    if ((uint64_t)K1 * smemVertexLimit < m.V) {
-      K1 = (m.V + smemVertexLimit - 1) / smemVertexLimit;
-      K1 = ((K1 + nSMs - 1) / nSMs) * nSMs;
+  }
+
+  std::vector<uint32_t> localOf(m.V, NONE), scratch;
+  for (int attempt = 0;; ++attempt) {
+    if (attempt > 24) { err = "could not fit the tiles into shared memory"; return false; }
+    const uint32_t K = K1 <= 1 ? 1u : (opts.partitions ? opts.partitions : 4u);
+
+    // ---- partitions (per caller vertex), P_0 also defines the slot numbering
+    std::vector<std::vector<uint32_t>> tileOfV(K, std::vector<uint32_t>(m.V, 0));
+    std::vector<uint32_t> tile0Begin, slotToVertex;
+    uint32_t nTilesMax = 1;
+    for (uint32_t p = 0; p < K; ++p) {
+      Partitioner pt = base;
+      pt.offset = (double)p / K;
+      pt.idx.resize(m.V);
+      std::iota(pt.idx.begin(), pt.idx.end(), 0u);
+      pt.tileOf = tileOfV[p].data();
+      if (m.V) pt.split(0, m.V, K1, 0); else pt.tileBegin.push_back(0);
+      nTilesMax = std::max(nTilesMax, (uint32_t)pt.tileBegin.size());
+      if (p == 0) {
+        tile0Begin = pt.tileBegin;
+        tile0Begin.push_back(m.V);
+        slotToVertex = pt.idx;
+      }
     }
-    tv = (m.V + K1 - 1) / K1;
-  }
-  if (m.V == 0) K1 = 1;
+    const uint32_t nTile0 = (uint32_t)tile0Begin.size() - 1;
+    std::vector<uint32_t> vertexToSlot(m.V);
+    for (uint32_t s = 0; s < m.V; ++s) vertexToSlot[slotToVertex[s]] = s;
 
-  // ---- RCB, slot numbering (tile-major, caller order inside a tile)
-  Rcb rcb;
-  rcb.x = m.x0;
-  rcb.idx.resize(m.V);
-  std::iota(rcb.idx.begin(), rcb.idx.end(), 0u);
-  rcb.tileOf.assign(m.V, 0);
-  if (m.V) rcb.split(0, m.V, K1); else rcb.tileBegin.push_back(0);
-  K1 = (uint32_t)rcb.tileBegin.size();
-  std::vector<uint32_t> tile0Begin = rcb.tileBegin;
-  tile0Begin.push_back(m.V);
-  plan.slotToVertex = rcb.idx;
-  plan.vertexToSlot.resize(m.V);
-  for (uint32_t s = 0; s < m.V; ++s) plan.vertexToSlot[rcb.idx[s]] = s;
-  std::vector<uint32_t> tile0OfSlot(m.V);
-  uint32_t cap0 = 0;
-  for (uint32_t t = 0; t < K1; ++t) {
-    for (uint32_t s = tile0Begin[t]; s < tile0Begin[t + 1]; ++s) tile0OfSlot[s] = t;
-    cap0 = std::max(cap0, tile0Begin[t + 1] - tile0Begin[t]);
-  }
-  if (cap0 > smemVertexLimit) { err = "tile does not fit in shared memory"; return false; }
+    // constraints in slot numbering; per-partition tile of a slot
+    std::vector<uint32_t> eSlots((size_t)m.E * 2), tSlots((size_t)m.T * 4);
+    for (size_t i = 0; i < eSlots.size(); ++i) eSlots[i] = vertexToSlot[m.edges[i]];
+    for (size_t i = 0; i < tSlots.size(); ++i) tSlots[i] = vertexToSlot[m.tets[i]];
+    const CSet sets[2] = {{eSlots.data(), m.E, 2}, {tSlots.data(), m.T, 4}};
+    std::vector<std::vector<uint32_t>> tileOfS(K, std::vector<uint32_t>(m.V));
+    for (uint32_t p = 0; p < K; ++p)
+      for (uint32_t s = 0; s < m.V; ++s) tileOfS[p][s] = tileOfV[p][slotToVertex[s]];
 
-  // constraints in slot numbering
-  std::vector<uint32_t> eSlots((size_t)m.E * 2), tSlots((size_t)m.T * 4);
-  for (size_t i = 0; i < eSlots.size(); ++i) eSlots[i] = plan.vertexToSlot[m.edges[i]];
-  for (size_t i = 0; i < tSlots.size(); ++i) tSlots[i] = plan.vertexToSlot[m.tets[i]];
+    // ---- assign every constraint to one admissible phase, balancing the per-vertex load
+    std::vector<std::vector<TileBuild>> mainPh(K);
+    for (uint32_t p = 0; p < K; ++p) mainPh[p].resize(nTilesMax);
+    std::vector<uint32_t> resid[2];
+    std::vector<uint16_t> load((size_t)m.V * K);
+    for (int ty = 0; ty < 2; ++ty) {
+      const CSet& cs = sets[ty];
+      std::fill(load.begin(), load.end(), (uint16_t)0);
+      std::vector<uint8_t> mask(cs.n, 0);
+      std::vector<uint32_t> bucket[kMaxPartitions + 1];
+      for (uint32_t k = 0; k < cs.n; ++k) {
+        const uint32_t* id = cs.at(k);
+        uint8_t mk = 0;
+        for (uint32_t p = 0; p < K; ++p) {
+          const uint32_t t = tileOfS[p][id[0]];
+          bool same = true;
+          for (uint32_t j = 1; j < cs.arity; ++j) same &= tileOfS[p][id[j]] == t;
+          if (same) mk |= (uint8_t)(1u << p);
+        }
+        mask[k] = mk;
+        bucket[__builtin_popcount(mk)].push_back(k);
+      }
+      resid[ty] = bucket[0];
+      if (getenv("PBD_PLAN_DEBUG")) {
+        fprintf(stderr, "[plan] type %d admissible-phase popcount histogram:", ty);
+        for (uint32_t f = 0; f <= K; ++f) fprintf(stderr, " %zu", bucket[f].size());
+        fprintf(stderr, "\n");
+      }
+      // least flexible first; the flexible ones then fill the valleys
+      for (uint32_t f = 1; f <= K; ++f)
+        for (uint32_t k : bucket[f]) {
+          const uint32_t* id = cs.at(k);
+          uint32_t bestP = 0, bestMax = NONE, bestSum = NONE;
+          for (uint32_t p = 0; p < K; ++p) {
+            if (!(mask[k] >> p & 1)) continue;
+            uint32_t mxl = 0, sum = 0;
+            for (uint32_t j = 0; j < cs.arity; ++j) {
+              const uint32_t l = load[(size_t)id[j] * K + p];
+              mxl = std::max(mxl, l);
+              sum += l;
+            }
+            if (mxl < bestMax || (mxl == bestMax && sum < bestSum)) { bestP = p; bestMax = mxl; bestSum = sum; }
+          }
+          for (uint32_t j = 0; j < cs.arity; ++j) load[(size_t)id[j] * K + bestP]++;
+          mainPh[bestP][tileOfS[bestP][id[0]]].ty[ty].cons.push_back(k);
+        }
+      if (getenv("PBD_PLAN_DEBUG")) {
+        // forced load: constraints with a single admissible phase
+        std::vector<uint16_t> forced((size_t)m.V * K, 0);
+        for (uint32_t k : bucket[1]) {
+          const uint32_t p = (uint32_t)__builtin_ctz(mask[k]);
+          for (uint32_t j = 0; j < cs.arity; ++j) forced[(size_t)cs.at(k)[j] * K + p]++;
+        }
+        uint32_t mxF = 0, mxL = 0;
+        for (size_t i = 0; i < forced.size(); ++i) { mxF = std::max<uint32_t>(mxF, forced[i]); mxL = std::max<uint32_t>(mxL, load[i]); }
+        fprintf(stderr, "[plan] type %d max forced load %u, max load %u\n", ty, mxF, mxL);
+      }
+    }
 
-  // later phases may use larger tiles: their sweeps are latency-bound, so fewer, larger tiles
-  // cost nothing and leave fewer straddling constraints
-  const uint32_t cap = std::min(smemVertexLimit, std::max(2 * tv, 2048u));
-  const uint32_t target = std::max(64u, (uint32_t)(cap * 0.75));
+    // ---- finish the main tiles
+    bool fits = true;
+    for (uint32_t p = 0; p < K && fits; ++p)
+      for (uint32_t t = 0; t < mainPh[p].size() && fits; ++t) {
+        TileBuild& tb = mainPh[p][t];
+        if (p == 0 && t < nTile0) {
+          tb.contiguous = true;
+          tb.rangeBegin = tile0Begin[t];
+          tb.rangeCount = tile0Begin[t + 1] - tile0Begin[t];
+        }
+        finish_tile(sets, tb, localOf, scratch);
+        const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
+        if (nv > 65535u || tile_bytes(tb) > smemBytes) fits = false;
+      }
+    if (!fits) {
+      uint32_t next = K1 + (K1 + 1) / 2;
+      if (next > nSMs) next = ((next + nSMs - 1) / nSMs) * nSMs;   // whole waves
+      K1 = std::max(K1 + 1, next);
+      continue;
+    }
 
-  TypeSchedule sched[2];
-  CSet sets[2] = {{eSlots.data(), m.E, 2}, {tSlots.data(), m.T, 4}};
-  for (int ty = 0; ty < 2; ++ty) build_type_schedule(sets[ty], m.V, tile0Begin, tile0OfSlot, cap, target, opts.max_phases, sched[ty]);
+    // ---- residual phases (constraints interior to no partition)
+    const uint32_t avgTile = std::max(64u, (m.V + nTile0 - 1) / std::max(1u, nTile0));
+    uint32_t resCap = std::min(65535u, std::min(2u * avgTile, smemBytes / 128u));
+    std::vector<std::vector<TileBuild>> resPh[2];
+    for (;;) {
+      bool ok = true;
+      for (int ty = 0; ty < 2; ++ty) {
+        resPh[ty].clear();
+        build_residual_phases(sets, ty, resid[ty], m.V, resCap, resPh[ty], localOf, scratch);
+        for (auto& ph : resPh[ty])
+          for (auto& tb : ph)
+            if (tile_bytes(tb) > smemBytes) ok = false;
+      }
+      if (ok) break;
+      if (resCap <= 16) { err = "a residual tile does not fit in shared memory"; return false; }
+      resCap /= 2;   // high-valence vertices: smaller tiles carry fewer constraints
+    }
 
-  // ---- flatten
-  plan.tile0Begin = tile0Begin;
-  plan.edgeOrder.clear(); plan.tetOrder.clear();
-  plan.edgeOrder.reserve(m.E); plan.tetOrder.reserve(m.T);
-  plan.edgeLocal.clear(); plan.tetLocal.clear();
-  plan.edgeLocal.reserve((size_t)m.E * 2); plan.tetLocal.reserve((size_t)m.T * 4);
-  plan.edgePhase.assign(m.E, 0); plan.edgeTile.assign(m.E, 0); plan.edgeColor.assign(m.E, 0);
-  plan.tetPhase.assign(m.T, 0); plan.tetTile.assign(m.T, 0); plan.tetColor.assign(m.T, 0);
-  plan.tileVertexCapacity = cap0;
-  std::vector<uint32_t> localOf(m.V, NONE);
-  for (int ty = 0; ty < 2; ++ty) {
-    const CSet& cs = sets[ty];
-    std::vector<uint32_t>& order = ty ? plan.tetOrder : plan.edgeOrder;
-    std::vector<uint16_t>& local = ty ? plan.tetLocal : plan.edgeLocal;
-    std::vector<uint32_t>& cPhase = ty ? plan.tetPhase : plan.edgePhase;
-    std::vector<uint32_t>& cTile = ty ? plan.tetTile : plan.edgeTile;
-    std::vector<uint32_t>& cCol = ty ? plan.tetColor : plan.edgeColor;
-    for (auto& ph : sched[ty].phases) {
-      if (cs.n == 0) break;   // a type without constraints contributes no phase
+    // ---- phase list in execution order.  A "view" selects which constraint types of a tile run.
+    struct PhaseRef { std::vector<TileBuild>* tiles; bool useE, useT, home; };
+    std::vector<PhaseRef> seq;
+    if (fused) {
+      for (uint32_t p = 0; p < K; ++p) seq.push_back({&mainPh[p], true, true, p == 0});
+      for (auto& ph : resPh[0]) seq.push_back({&ph, true, false, false});
+      for (auto& ph : resPh[1]) seq.push_back({&ph, false, true, false});
+    } else {
+      if (m.E) {
+        for (uint32_t p = 0; p < K; ++p) seq.push_back({&mainPh[p], true, false, p == 0});
+        for (auto& ph : resPh[0]) seq.push_back({&ph, true, false, false});
+      }
+      if (m.T) {
+        for (uint32_t p = 0; p < K; ++p) seq.push_back({&mainPh[p], false, true, p == 0});
+        for (auto& ph : resPh[1]) seq.push_back({&ph, false, true, false});
+      }
+    }
+    if (m.E == 0 && m.T == 0) seq.clear();
+
+    // ---- flatten
+    plan.slotToVertex = slotToVertex;
+    plan.vertexToSlot = vertexToSlot;
+    plan.tile0Begin = tile0Begin;
+    plan.partitions = K;
+    plan.tilesPerPartition = nTile0;
+    plan.edgeOrder.reserve(m.E); plan.tetOrder.reserve(m.T);
+    plan.edgeLocal.reserve((size_t)m.E * 2); plan.tetLocal.reserve((size_t)m.T * 4);
+    plan.edgeDev.reserve(m.E); plan.tetDev.reserve(m.T);
+    plan.edgePhase.assign(m.E, 0); plan.edgeTile.assign(m.E, 0); plan.edgeColor.assign(m.E, 0);
+    plan.tetPhase.assign(m.T, 0); plan.tetTile.assign(m.T, 0); plan.tetColor.assign(m.T, 0);
+    for (uint32_t t = 0; t < nTile0; ++t) plan.tileVertexCapacity = std::max(plan.tileVertexCapacity, tile0Begin[t + 1] - tile0Begin[t]);
+    uint32_t devCur[2] = {0, 0};
+    for (size_t pi = 0; pi < seq.size(); ++pi) {
+      const PhaseRef& pr = seq[pi];
       Phase P;
       P.tileBegin = (uint32_t)plan.tiles.size();
-      P.isTet = (uint32_t)ty;
-      for (auto& tb : ph) {
+      uint32_t mxCol[2] = {0, 0};
+      bool anyE = false, anyT = false;
+      for (size_t ti = 0; ti < pr.tiles->size(); ++ti) {
+        TileBuild& tb = (*pr.tiles)[ti];
+        const bool hasE = pr.useE && !tb.ty[0].cons.empty(), hasT = pr.useT && !tb.ty[1].cons.empty();
+        const bool isHome = pr.home && pi == 0;   // the very first phase covers every slot (vertex stages are fused into it)
+        if (!hasE && !hasT && !(isHome && tb.contiguous)) continue;
         Tile tl;
-        tl.isTet = (uint32_t)ty;
         tl.contiguous = tb.contiguous ? 1u : 0u;
+        uint32_t nLocal;
         if (tb.contiguous) {
           tl.vertBegin = tb.rangeBegin;
-          tl.vertCount = tb.rangeCount;
-          for (uint32_t i = 0; i < tb.rangeCount; ++i) localOf[tb.rangeBegin + i] = i;
+          tl.vertCount = nLocal = tb.rangeCount;
+          for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.rangeBegin + i] = i;
         } else {
           tl.vertBegin = (uint32_t)plan.tileVerts.size();
-          tl.vertCount = (uint32_t)tb.verts.size();
-          for (uint32_t i = 0; i < tb.verts.size(); ++i) { localOf[tb.verts[i]] = i; plan.tileVerts.push_back(tb.verts[i]); }
+          tl.vertCount = nLocal = (uint32_t)tb.verts.size();
+          for (uint32_t i = 0; i < nLocal; ++i) { localOf[tb.verts[i]] = i; plan.tileVerts.push_back(tb.verts[i]); }
         }
-        plan.tileVertexCapacity = std::max(plan.tileVertexCapacity, tl.vertCount);
-        tl.groupBegin = (uint32_t)plan.groups.size();
-        // one group per colour, split so that no group exceeds the block size
-        size_t i = 0;
-        while (i < tb.cons.size()) {
-          size_t j = i;
-          while (j < tb.cons.size() && tb.colour[j] == tb.colour[i]) ++j;
-          const uint32_t lim = ty ? blockThreads / 4 : blockThreads;   // a tet is swept by 4 lanes
-          const uint32_t n = (uint32_t)(j - i), parts = (n + lim - 1) / lim;
-          for (uint32_t q = 0; q < parts; ++q) {
+        plan.tileVertexCapacity = std::max(plan.tileVertexCapacity, nLocal);
+        for (int ty = 0; ty < 2; ++ty) {
+          const bool use = ty ? hasT : hasE;
+          const CSet& cs = sets[ty];
+          std::vector<uint32_t>& order = ty ? plan.tetOrder : plan.edgeOrder;
+          std::vector<uint32_t>& dev = ty ? plan.tetDev : plan.edgeDev;
+          std::vector<uint16_t>& local = ty ? plan.tetLocal : plan.edgeLocal;
+          std::vector<uint32_t>& cPhase = ty ? plan.tetPhase : plan.edgePhase;
+          std::vector<uint32_t>& cTile = ty ? plan.tetTile : plan.edgeTile;
+          std::vector<uint32_t>& cCol = ty ? plan.tetColor : plan.edgeColor;
+          uint32_t& begin = ty ? tl.tetBegin : tl.edgeBegin;
+          uint32_t& count = ty ? tl.tetCount : tl.edgeCount;
+          uint32_t& gBegin = ty ? tl.tetGroupBegin : tl.edgeGroupBegin;
+          uint32_t& gCount = ty ? tl.tetGroupCount : tl.edgeGroupCount;
+          uint32_t& devBegin = ty ? tl.tetDevBegin : tl.edgeDevBegin;
+          begin = (uint32_t)order.size();
+          gBegin = (uint32_t)plan.groups.size();
+          devCur[ty] = pad4(devCur[ty]);
+          devBegin = devCur[ty];
+          if (!use) continue;
+          const TypeList& L = tb.ty[ty];
+          size_t i = 0;
+          while (i < L.cons.size()) {
+            size_t j = i;
+            while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
             Group g;
-            g.begin = (uint32_t)order.size() + (uint32_t)(((uint64_t)n * q) / parts);
-            g.count = (uint32_t)(((uint64_t)n * (q + 1)) / parts - ((uint64_t)n * q) / parts);
+            g.begin = (uint32_t)order.size();
+            g.count = (uint32_t)(j - i);
             plan.groups.push_back(g);
+            for (size_t k = i; k < j; ++k) {
+              const uint32_t c = L.cons[k];
+              cPhase[c] = (uint32_t)plan.phases.size();
+              cTile[c] = (uint32_t)plan.tiles.size();
+              cCol[c] = L.colour[k];
+              for (uint32_t a = 0; a < cs.arity; ++a) local.push_back((uint16_t)localOf[cs.at(c)[a]]);
+              order.push_back(c);
+              dev.push_back(devCur[ty]++);
+            }
+            i = j;
           }
-          for (size_t k = i; k < j; ++k) {
-            const uint32_t c = tb.cons[k];
-            cPhase[c] = (uint32_t)plan.phases.size();
-            cTile[c] = (uint32_t)plan.tiles.size();
-            cCol[c] = tb.colour[k];
-            for (uint32_t a = 0; a < cs.arity; ++a) local.push_back((uint16_t)localOf[cs.at(c)[a]]);
-          }
-          for (size_t k = i; k < j; ++k) order.push_back(tb.cons[k]);
-          i = j;
+          count = (uint32_t)order.size() - begin;
+          gCount = (uint32_t)plan.groups.size() - gBegin;
+          mxCol[ty] = std::max(mxCol[ty], gCount);
+          (ty ? anyT : anyE) = true;
         }
-        tl.groupCount = (uint32_t)plan.groups.size() - tl.groupBegin;
+        plan.tileRecordBytes = std::max(plan.tileRecordBytes,
+                                        tile_record_bytes(tl.contiguous ? 0u : tl.vertCount, tl.edgeGroupCount,
+                                                          tl.tetGroupCount, tl.edgeCount, tl.tetCount));
         plan.tiles.push_back(tl);
       }
       P.tileCount = (uint32_t)plan.tiles.size() - P.tileBegin;
+      if (P.tileCount == 0) continue;
       plan.phases.push_back(P);
+      plan.edgeColorSum += mxCol[0];
+      plan.tetColorSum += mxCol[1];
+      plan.edgePhases += anyE ? 1u : 0u;
+      plan.tetPhases += anyT ? 1u : 0u;
     }
+    plan.edgeDevCount = pad4(devCur[0]);
+    plan.tetDevCount = pad4(devCur[1]);
+    break;
   }
-  plan.edgePhases = m.E ? (uint32_t)sched[0].phases.size() : 0;
-  plan.tetPhases = m.T ? (uint32_t)sched[1].phases.size() : 0;
-  plan.edgeColorSum = sched[0].colourSum;
-  plan.tetColorSum = sched[1].colourSum;
-  plan.blockThreads = blockThreads;
   plan.planMs = now_ms() - t0;
   return true;
 }

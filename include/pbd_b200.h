@@ -98,8 +98,10 @@ typedef struct pbd_options {
   uint32_t flags;          /* PBD_FLAG_*                                                         */
   uint32_t tile_vertices;  /* tile backend: target vertices per shared-memory tile, 0 = auto     */
   uint32_t block_threads;  /* 0 = auto                                                           */
-  uint32_t max_phases;     /* tile backend: cap on tile phases per constraint type, 0 = auto     */
-  uint32_t reserved[9];
+  uint32_t max_phases;     /* reserved (ignored)                                                 */
+  uint32_t partitions;     /* tile backend: shifted vertex partitions per sweep, 0 = auto (4)    */
+  uint32_t lanes_per_tet;  /* tile backend: 1 or 4 lanes cooperate on one tet, 0 = auto          */
+  uint32_t reserved[7];
 } pbd_options;
 
 typedef struct pbd_info {
@@ -107,12 +109,14 @@ typedef struct pbd_info {
   uint32_t backend;             /* resolved PBD_BACKEND_*                                    */
   uint32_t edge_colors;         /* stream: global colours; tile: max local colours summed over phases */
   uint32_t tet_colors;
-  uint32_t edge_phases;         /* tile backend: grid-wide phases per iteration for edges    */
+  uint32_t edge_phases;         /* tile backend: grid-wide phases per iteration that carry edges */
   uint32_t tet_phases;
   uint32_t tiles;               /* tile backend: total tiles over all phases                 */
   uint32_t launches_per_frame;  /* kernels launched by one pbd_step at the current params    */
   uint32_t grid_blocks, block_threads;
-  uint32_t reserved32[4];
+  uint32_t partitions;          /* tile backend: shifted vertex partitions (main phases per sweep) */
+  uint32_t lanes_per_tet;       /* tile backend: lanes cooperating on one tet                      */
+  uint32_t reserved32[2];
   uint64_t device_bytes;        /* HBM held by this handle                                    */
   uint64_t algorithmic_bytes_per_substep; /* 104 V + I (20 E + 28 T + 84 V), SURVEY.md 8(d)   */
   double plan_ms;               /* host time spent building the schedule                     */

@@ -62,6 +62,35 @@ def test_schedule_is_valid_partition_and_deterministic(backend, mesh, capi, mesh
     assert info["V"] == len(x0) and info["E"] == len(edges) and info["T"] == len(tets)
 
 
+@pytest.mark.parametrize("mesh,tile_vertices,partitions", [("kuhn7", 0, 0), ("kuhn7", 60, 0), ("kuhn10", 200, 3),
+                                                           ("icosphere001", 150, 0), ("default", 0, 0), ("default", 500, 6)])
+def test_interleaved_tile_schedule_is_valid_and_sequence_consistent(mesh, tile_vertices, partitions, capi, meshgen, golden):
+    if mesh.startswith("kuhn"):
+        x0, tets, edges = meshgen.kuhn_grid(int(mesh[4:]))
+    else:
+        m = golden(f"mesh_{mesh}.npz")
+        x0, tets, edges = m["vertices"], m["tets"], m["edges"]
+    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_INTERLEAVED, tile_vertices=tile_vertices,
+                       partitions=partitions)
+    p = capi.Plan(x0, edges, tets, opt)
+    _check_schedule(edges, tets, p)
+    E, T = len(edges), len(tets)
+    seq = p.sequence().astype(np.int64)
+    is_tet = (seq >> 31) & 1
+    pos = seq & 0x7FFFFFFF
+    # every schedule position exactly once, each type in increasing schedule order
+    assert np.array_equal(pos[is_tet == 0], np.arange(E)) and np.array_equal(pos[is_tet == 1], np.arange(T))
+    # the sequence walks (phase, tile) pairs in order; inside a pair edges come before tets
+    eo, to = p.order()
+    (eph, etl, _), (tph, ttl, _) = p.slots(False), p.slots(True)
+    ph = np.where(is_tet == 1, tph[to][np.minimum(pos, T - 1)] if T else 0, eph[eo][np.minimum(pos, E - 1)] if E else 0).astype(np.int64)
+    tl = np.where(is_tet == 1, ttl[to][np.minimum(pos, T - 1)] if T else 0, etl[eo][np.minimum(pos, E - 1)] if E else 0).astype(np.int64)
+    key = (ph * (tl.max() + 1) + tl) * 2 + is_tet
+    assert (np.diff(key) >= 0).all()
+    info = p.info()
+    assert info["partitions"] >= 1 and info["tiles"] >= 1
+
+
 def test_stream_colour_counts_match_survey_probe(capi, meshgen, golden):
     """greedy first-fit needs 30 tet + 15 edge colours on the Kuhn grid and
     101 tet + 54 edge colours on default_Tet."""

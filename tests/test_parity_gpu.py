@@ -256,3 +256,61 @@ def test_p1_tile_backend_many_small_tiles_bit_exact(mesh, tile_vertices, block_t
         ora.step(1 / 60, fr - while_done)
         _assert_state_equal(capi, po, body, ora, f"{mesh} tv={tile_vertices} bt={block_threads} frame {fr}")
     body.close()
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+@pytest.mark.parametrize("mesh,tile_vertices,partitions,frames", [
+    ("kuhn8", 0, 0, (1, 10, 30)), ("kuhn8", 100, 0, (1, 10, 30)), ("kuhn8", 150, 3, (1, 10)),
+    ("icosphere001", 200, 0, (1, 10, 30)), ("kuhn12", 300, 5, (1, 10)), ("default", 0, 0, (1, 4)),
+    ("default", 700, 0, (1, 4)), ("bunny", 64, 2, (1, 20)),
+])
+def test_p1_tile_interleaved_order_bit_exact_vs_sequence_oracle(mesh, tile_vertices, partitions, frames, lanes, capi, po,
+                                                               meshgen, golden):
+    """PBD_ORDER_INTERLEAVED: a tile visit projects its edges and then its tets, so one iteration is
+    a permutation of [all edges, all tets] that the unmodified reference cannot express.  The
+    pinned C port replays the disclosed sequence (pbd_get_schedule_sequence) constraint by
+    constraint; positions, velocities, xStar and lambdas must be BIT-EXACT."""
+    x0, edges, tets = _mesh(mesh, meshgen, golden)
+    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_INTERLEAVED, tile_vertices=tile_vertices,
+                       partitions=partitions, lanes_per_tet=lanes)
+    body = capi.Body(capi.SolverParams.default(substeps=5), x0, edges, tets, device=0, options=opt)
+    assert body.info()["lanes_per_tet"] == lanes
+    ora = po.Oracle(po.Params.default(substeps=5), x0, edges, tets, kind="port")
+    ora.permute_constraints(*body.schedule_order())
+    seq = body.schedule_sequence()
+    assert np.array_equal(np.sort(seq), np.concatenate([np.arange(body.E, dtype=np.uint32),
+                                                        np.arange(body.T, dtype=np.uint32) | np.uint32(0x80000000)]))
+    done = 0
+    for fr in frames:
+        for _ in range(fr - done):
+            body.step(1.0 / 60.0)
+            ora.step_sequence(1.0 / 60.0, seq)
+        done = fr
+        _assert_state_equal(capi, po, body, ora, f"{mesh}/interleaved tv={tile_vertices} K={partitions} lanes={lanes} frame {fr}")
+    body.close()
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_p1_tile_strict_lanes_bit_exact(lanes, capi, po, meshgen, golden):
+    x0, edges, tets = _mesh("kuhn12", meshgen, golden)
+    body, ora = _same_order_pair(capi, po, dict(substeps=4), x0, edges, tets, "tile", tile_vertices=400, lanes_per_tet=lanes)
+    for _ in range(10):
+        body.step(1 / 60)
+    ora.step(1 / 60, 10)
+    _assert_state_equal(capi, po, body, ora, f"strict lanes={lanes}")
+    body.close()
+
+
+def test_p2_p3_interleaved_order_tolerance_and_residuals(capi, po, meshgen, golden):
+    """The interleaved order against the reference in its ORIGINAL order: same stated tolerance as
+    P2 (RMS/bbox diagonal <= 1e-4 after 10 frames) on every fixture mesh."""
+    for mesh in ("icosphere", "bunny", "icosphere001", "default", "kuhn6"):
+        x0, edges, tets = _mesh(mesh, meshgen, golden)
+        g = golden(f"ref_{mesh}.npz")
+        opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_INTERLEAVED)
+        with capi.Body(capi.SolverParams.default(substeps=10), x0, edges, tets, device=0, options=opt) as b:
+            diag = np.linalg.norm(x0.max(0) - x0.min(0))
+            b.step_async(1 / 60, 10)
+            b.sync()
+            rel = np.sqrt(np.mean(np.sum((b.read_positions().astype(np.float64) - g["pos_10"]) ** 2, 1))) / diag
+            assert rel <= 1e-4, f"{mesh}: rel RMS {rel:.3e}"
