@@ -179,10 +179,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--backend", default="auto", choices=["auto", "stream", "tile"])
-    ap.add_argument("--order", default="strict", choices=["strict", "interleaved"])
+    ap.add_argument("--order", default="interleaved", choices=["strict", "interleaved"],
+                    help="interleaved (default): a tile visit projects its edges then its tets, bit-exact vs the "
+                         "oracle's sequence sweep; strict: all edges then all tets per iteration, bit-exact vs the "
+                         "unmodified reference run on the permuted arrays")
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--tile-vertices", type=int, default=0)
-    ap.add_argument("--lanes", type=int, default=0, help="tile backend: lanes per tet (0 = auto, 1, 4)")
+    ap.add_argument("--lanes", type=int, default=0, help="tile backend: lanes per tet (0 = auto, 1, 2, 4)")
     ap.add_argument("--partitions", type=int, default=0, help="tile backend: shifted partitions (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
@@ -299,6 +302,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "V": V, "E": E, "T": T, "substeps_per_frame": S, "iterations": I,
                    "dt": DT, "backend": body.name(), "order_mode": args.order,
+                   "lanes_per_tet": info.get("lanes_per_tet"), "partitions": info.get("partitions"),
                    "parallelism": f"{world} independent bodies, one per GPU, no collective" if world > 1 else "1 GPU",
                    "l2": "not flushed" if flush is None else "flushed between timed frames (256 MiB memset, untimed)",
                    "working_set_bytes": info["device_bytes"]},
@@ -314,8 +318,8 @@ def main():
         "gpu_launches": args.steps * info["launches_per_frame"],
         "clocks": clocks,
         "init_ms": init_ms, "plan_ms": info["plan_ms"], "wall_ms_timed_region": wall_ms,
-        "schedule": {k: info[k] for k in ("edge_colors", "tet_colors", "edge_phases", "tet_phases", "tiles",
-                                          "launches_per_frame", "grid_blocks", "block_threads")},
+        "schedule": {k: info[k] for k in ("edge_colors", "tet_colors", "edge_phases", "tet_phases", "tiles", "partitions",
+                                          "lanes_per_tet", "launches_per_frame", "grid_blocks", "block_threads")},
         "sane": sane,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -20,7 +20,7 @@ namespace {
 thread_local std::string g_err;
 
 // shared memory the tile kernel keeps for itself (static variables, alignment slack)
-constexpr uint32_t kSmemReserve = 2048;
+constexpr uint32_t kSmemReserve = 8192;
 
 double wall_ms() {
   using namespace std::chrono;
@@ -111,7 +111,9 @@ namespace {
 
 bool build_plan(const MeshView& m, const pbd_options& o, int nSMs, uint32_t smemBytes, Plan& plan, std::string& err) {
   uint32_t backend = o.backend;
-  if (backend == PBD_BACKEND_AUTO) backend = PBD_BACKEND_STREAM;
+  // auto: the tile backend (one persistent kernel per frame); the stream backend (one launch per
+  // global colour) remains as the simple cross-check
+  if (backend == PBD_BACKEND_AUTO) backend = PBD_BACKEND_TILE;
   if (backend == PBD_BACKEND_STREAM) {
     if (o.order_mode != PBD_ORDER_STRICT) { err = "stream backend supports PBD_ORDER_STRICT only"; return false; }
     build_stream_plan(m, plan);

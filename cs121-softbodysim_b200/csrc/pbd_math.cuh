@@ -30,6 +30,15 @@ PBD_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz) {
   return fadd(fadd(fmul(ax, bx), fmul(ay, by)), fmul(az, bz));
 }
 
+// a / b for a finite b > 0, IEEE round-to-nearest like fdiv, but a zero numerator (a constraint
+// that is exactly satisfied: the whole body while it is in free fall) does not send the warp
+// through the division's slow path: +-0 / b = +-0 = a.
+PBD_DEV float fdiv_pos(float a, float b) {
+  const bool z = a == 0.0f;
+  const float q = fdiv(z ? 1.0f : a, b);
+  return z ? a : q;
+}
+
 // Edge-distance projection.  p0/p1 carry (x, y, z, invMass).  Returns false when the reference
 // `continue`s (no write).  lambda is updated in place.
 PBD_DEV bool project_edge(float4& p0, float4& p1, float rest, float& lambda, float alpha) {
@@ -90,6 +99,64 @@ PBD_DEV bool project_tet(float4& pa, float4& pb, float4& pc, float4& pd, float r
   pc.x = fadd(pc.x, fmul(gcx, sc)); pc.y = fadd(pc.y, fmul(gcy, sc)); pc.z = fadd(pc.z, fmul(gcz, sc));
   pd.x = fadd(pd.x, fmul(gdx, sd)); pd.y = fadd(pd.y, fmul(gdy, sd)); pd.z = fadd(pd.z, fmul(gdz, sd));
   return true;
+}
+
+// ---- branch-free forms for the shared-memory sweeps -------------------------------------------
+// Same operations in the same order as project_edge / project_tet, but the reference's early
+// `continue`s become one predicate that the caller uses to suppress the write-back: the dependent
+// chain of a colour step then has no divergence/reconvergence points and every operand load can
+// be issued up front.  When the predicate is false the computed values are garbage (possibly
+// NaN/inf) and are discarded, exactly as if the reference had skipped the constraint.
+PBD_DEV bool edge_delta(const float4 p0, const float4 p1, float rest, float lambda, float alpha, float4& q0,
+                        float4& q1, float& newLambda) {
+  const float w0 = p0.w, w1 = p1.w;
+  const float wSum = fadd(w0, w1);
+  const float dx = fsub(p0.x, p1.x), dy = fsub(p0.y, p1.y), dz = fsub(p0.z, p1.z);
+  const float len = __fsqrt_rn(dot3(dx, dy, dz, dx, dy, dz));
+  const bool ok = (wSum != 0.0f) && !(len < 1e-12f);
+  const float C = fsub(len, rest);
+  const float dl = fdiv_pos(fsub(-C, fmul(alpha, lambda)), fadd(wSum, alpha));   // wSum + alpha > 0 whenever ok
+  newLambda = fadd(lambda, dl);
+  const float inv = __frcp_rn(len);   // == 1.0f / len, both correctly rounded
+  const float cx = fmul(fmul(dx, inv), dl), cy = fmul(fmul(dy, inv), dl), cz = fmul(fmul(dz, inv), dl);
+  q0.x = fadd(p0.x, fmul(cx, w0)); q0.y = fadd(p0.y, fmul(cy, w0)); q0.z = fadd(p0.z, fmul(cz, w0)); q0.w = w0;
+  q1.x = fsub(p1.x, fmul(cx, w1)); q1.y = fsub(p1.y, fmul(cy, w1)); q1.z = fsub(p1.z, fmul(cz, w1)); q1.w = w1;
+  return ok;
+}
+
+PBD_DEV bool tet_delta(float4& pa, float4& pb, float4& pc, float4& pd, float rest, float lambda, float alpha,
+                       float& newLambda) {
+  const float k6 = 1.0f / 6.0f;
+  const float wa = pa.w, wb = pb.w, wc = pc.w, wd = pd.w;
+  const bool massive = fadd(fadd(fadd(wa, wb), wc), wd) != 0.0f;
+  const float dbx = fsub(pd.x, pb.x), dby = fsub(pd.y, pb.y), dbz = fsub(pd.z, pb.z);
+  const float cbx = fsub(pc.x, pb.x), cby = fsub(pc.y, pb.y), cbz = fsub(pc.z, pb.z);
+  const float cax = fsub(pc.x, pa.x), cay = fsub(pc.y, pa.y), caz = fsub(pc.z, pa.z);
+  const float dax = fsub(pd.x, pa.x), day = fsub(pd.y, pa.y), daz = fsub(pd.z, pa.z);
+  const float bax = fsub(pb.x, pa.x), bay = fsub(pb.y, pa.y), baz = fsub(pb.z, pa.z);
+  const float gax = fmul(cross_c(dby, cbz, dbz, cby), k6), gay = fmul(cross_c(dbz, cbx, dbx, cbz), k6),
+              gaz = fmul(cross_c(dbx, cby, dby, cbx), k6);
+  const float gbx = fmul(cross_c(cay, daz, caz, day), k6), gby = fmul(cross_c(caz, dax, cax, daz), k6),
+              gbz = fmul(cross_c(cax, day, cay, dax), k6);
+  const float gcx = fmul(cross_c(day, baz, daz, bay), k6), gcy = fmul(cross_c(daz, bax, dax, baz), k6),
+              gcz = fmul(cross_c(dax, bay, day, bax), k6);
+  const float nx = cross_c(bay, caz, baz, cay), ny = cross_c(baz, cax, bax, caz), nz = cross_c(bax, cay, bay, cax);
+  const float gdx = fmul(nx, k6), gdy = fmul(ny, k6), gdz = fmul(nz, k6);
+  const float wSum = fadd(fadd(fadd(fmul(wa, dot3(gax, gay, gaz, gax, gay, gaz)),
+                                    fmul(wb, dot3(gbx, gby, gbz, gbx, gby, gbz))),
+                               fmul(wc, dot3(gcx, gcy, gcz, gcx, gcy, gcz))),
+                          fmul(wd, dot3(gdx, gdy, gdz, gdx, gdy, gdz)));
+  const bool ok = massive && !(wSum < 1e-20f);
+  const float vol = fdiv(dot3(nx, ny, nz, dax, day, daz), 6.0f);
+  const float C = fsub(vol, rest);
+  const float dl = fdiv_pos(fsub(-C, fmul(alpha, lambda)), fadd(wSum, alpha));   // wSum + alpha > 0 whenever ok
+  newLambda = fadd(lambda, dl);
+  const float sa = fmul(wa, dl), sb = fmul(wb, dl), sc = fmul(wc, dl), sd = fmul(wd, dl);
+  pa.x = fadd(pa.x, fmul(gax, sa)); pa.y = fadd(pa.y, fmul(gay, sa)); pa.z = fadd(pa.z, fmul(gaz, sa));
+  pb.x = fadd(pb.x, fmul(gbx, sb)); pb.y = fadd(pb.y, fmul(gby, sb)); pb.z = fadd(pb.z, fmul(gbz, sb));
+  pc.x = fadd(pc.x, fmul(gcx, sc)); pc.y = fadd(pc.y, fmul(gcy, sc)); pc.z = fadd(pc.z, fmul(gcz, sc));
+  pd.x = fadd(pd.x, fmul(gdx, sd)); pd.y = fadd(pd.y, fmul(gdy, sd)); pd.z = fadd(pd.z, fmul(gdz, sd));
+  return ok;
 }
 
 // Per-frame scalars derived on the host in float exactly as the reference does.

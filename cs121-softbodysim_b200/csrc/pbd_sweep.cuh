@@ -1,0 +1,270 @@
+// pbd_sweep.cuh -- the shared-memory colour sweeps of the tile backend (device code only).
+//
+// A tile's RECORD BLOCK (built by pbd_tile.cu, layout sized by pbd_plan.h::tile_record_bytes) and
+// its vertices live in dynamic shared memory; these functions project the tile's edge colour
+// groups and then its tet colour groups on them.  Kept in a header so that tools/mb_sweep.cu can
+// time exactly the code the frame kernel runs.
+//
+// Reference lines restated: CProgram/src/Sim.cpp:104-129 (edge), :136-172 (tet), via pbd_math.cuh.
+#pragma once
+#include <cstdint>
+
+#include "pbd_math.cuh"
+
+namespace pbd {
+
+// The frame kernel calls the sweeps out of line: they then get a register allocation of their
+// own instead of sharing 128 registers with the kernel's schedule-walking state (which spilled
+// inside the colour loops).  One call per tile visit is noise next to a sweep.
+#ifndef PBD_SWEEP_INLINE
+#define PBD_SWEEP_INLINE __device__ __noinline__
+#endif
+
+// first 64 bytes of a tile's record block (shared memory); offsets in bytes from the block start
+struct TileHdr {
+  uint32_t vertCount, contiguous, vertBegin, nEdgeGroups;
+  uint32_t nTetGroups, nEdges, nTets, offVertIdx;
+  uint32_t offEdgeGroups, offTetGroups, offEdgeIdx, offEdgeRest;
+  uint32_t offTetIdx, offTetRest, offEdgeLam, offTetLam;
+};
+static_assert(sizeof(TileHdr) == 64, "TileHdr is the 64-byte block header");
+
+// ---------------------------------------------------------------- sweeps (shared memory only)
+//
+// Everything a colour step touches lives in shared memory: `rec` / `svOff` are byte offsets into
+// the dynamic shared array, so every access below is an LDS/STS.  The record of a thread's
+// constraint in the NEXT colour group (indices, rest value, lambda: never written by another
+// thread) is fetched before the block barrier; after the barrier the dependent chain is
+// LDS.128 vertices -> arithmetic -> STS.128 -> barrier.
+
+PBD_SWEEP_INLINE void sweep_edges(const TileHdr& h, uint32_t rec, uint32_t svOff, float alpha, long long* ft) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t n = h.nEdgeGroups;
+  if (n == 0) return;
+  const uint2* groups = reinterpret_cast<const uint2*>(smem + rec + h.offEdgeGroups);
+  const uint32_t* idx = reinterpret_cast<const uint32_t*>(smem + rec + h.offEdgeIdx);
+  const float* rest = reinterpret_cast<const float*>(smem + rec + h.offEdgeRest);
+  float* lam = reinterpret_cast<float*>(smem + rec + h.offEdgeLam);
+  float4* sv = reinterpret_cast<float4*>(smem + svOff);
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  auto project = [&](uint32_t e, uint32_t id, float r, float l) {
+    const uint32_t a = id & 0xffffu, b = id >> 16;
+    const float4 p0 = sv[a], p1 = sv[b];
+    float4 q0, q1;
+    float nl;
+    if (edge_delta(p0, p1, r, l, alpha, q0, q1, nl)) {
+      sv[a] = q0;
+      sv[b] = q1;
+      lam[e] = nl;
+    }
+  };
+  uint2 gd = groups[0];
+  uint32_t e = gd.x + tid, id = 0;
+  float r = 0.0f, l = 0.0f;
+  bool have = tid < gd.y;
+  if (have) { id = idx[e]; r = rest[e]; l = lam[e]; }
+  for (uint32_t g = 0; g < n; ++g) {
+    const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 0u);
+    if (have) project(e, id, r, l);
+    for (uint32_t i = tid + nth; i < gd.y; i += nth) {   // colour groups larger than the block
+      const uint32_t e2 = gd.x + i;
+      project(e2, idx[e2], rest[e2], lam[e2]);
+    }
+    e = gn.x + tid;
+    have = tid < gn.y;
+    if (have) { id = idx[e]; r = rest[e]; l = lam[e]; }
+    __syncthreads();
+    if (ft && g < 40) { ft[16 + g] = clock64(); ft[56 + g] = gd.y; }
+    gd = gn;
+  }
+}
+
+// LANES == 1: one thread per tet.
+// LANES == 4: one tet per 4 adjacent lanes, lane `role` owns vertex `role` (a,b,c,d).  All four
+// gradients have the form cross(x - o, y - o)/6 (Sim.cpp:146-149):
+//   ga: o=b x=d y=c | gb: o=a x=c y=d | gc: o=a x=d y=b | gd: o=a x=b y=c
+// so every lane runs the same instructions on role-selected operands; the reduction terms are
+// exchanged with quad shuffles and summed in the reference's order, which keeps the result
+// bit-identical while shortening the dependent instruction stream of a colour step.
+template <int LANES>
+PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff, float alpha, long long* ft) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t n = h.nTetGroups;
+  if (n == 0) return;
+  const uint2* groups = reinterpret_cast<const uint2*>(smem + rec + h.offTetGroups);
+  const uint2* idx = reinterpret_cast<const uint2*>(smem + rec + h.offTetIdx);
+  const float* rest = reinterpret_cast<const float*>(smem + rec + h.offTetRest);
+  float* lam = reinterpret_cast<float*>(smem + rec + h.offTetLam);
+  float4* sv = reinterpret_cast<float4*>(smem + svOff);
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  if (LANES == 1) {
+    auto project = [&](uint32_t t, uint2 id, float r, float l) {
+      const uint32_t a = id.x & 0xffffu, b = id.x >> 16, c = id.y & 0xffffu, d = id.y >> 16;
+      float4 pa = sv[a], pb = sv[b], pc = sv[c], pd = sv[d];
+      float nl;
+      if (tet_delta(pa, pb, pc, pd, r, l, alpha, nl)) {
+        sv[a] = pa; sv[b] = pb; sv[c] = pc; sv[d] = pd;
+        lam[t] = nl;
+      }
+    };
+    uint2 gd = groups[0];
+    uint32_t t = gd.x + tid;
+    uint2 id = make_uint2(0u, 0u);
+    float r = 0.0f, l = 0.0f;
+    bool have = tid < gd.y;
+    if (have) { id = idx[t]; r = rest[t]; l = lam[t]; }
+    for (uint32_t g = 0; g < n; ++g) {
+      const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 0u);
+      if (have) project(t, id, r, l);
+      for (uint32_t i = tid + nth; i < gd.y; i += nth) {
+        const uint32_t t2 = gd.x + i;
+        project(t2, idx[t2], rest[t2], lam[t2]);
+      }
+      t = gn.x + tid;
+      have = tid < gn.y;
+      if (have) { id = idx[t]; r = rest[t]; l = lam[t]; }
+      __syncthreads();
+      if (ft && g < 40) { ft[16 + g] = clock64(); ft[56 + g] = gd.y; }
+      gd = gn;
+    }
+  } else if (LANES == 2) {
+    // Two adjacent lanes per tet.  Lane A (even) owns vertices a, b and computes ga, gb; lane B
+    // (odd) owns c, d and computes gc, gd.  The lanes load the four vertices in the orders
+    //   A: (V0,V1,V2,V3) = (a,b,c,d)      B: (V0,V1,V2,V3) = (c,a,b,d)
+    // so that   g1 = cross(V3-V1, V2-V1)/6   is ga on A and gc on B      (Sim.cpp:146,148)
+    // and       g2 = cross(V2-o2, y2-o2)/6   with (o2,y2) = (V0,V3) on A -> gb, (V1,V0) on B -> gd.
+    // B's g2 cross is cross(pb-pa, pc-pa), the volume normal; its V3-V1 is pd-pa.  The four
+    // w|g|^2 terms are exchanged with one shuffle pair and summed in the reference's order on
+    // both lanes, so both derive the identical delta-lambda.
+    const uint32_t half = tid & 1u, lane = tid & 31u;
+    const uint32_t pairs = nth >> 1, pair = tid >> 1;
+    const unsigned m = 0xffffffffu;
+    const bool isB = half != 0u;
+    auto project = [&](uint32_t t, uint2 id, float r, float l0, bool live) {
+      const uint32_t ia = id.x & 0xffffu, ib = id.x >> 16, ic = id.y & 0xffffu, idd = id.y >> 16;
+      const uint32_t i0 = isB ? ic : ia, i1 = isB ? ia : ib, i2 = isB ? ib : ic, i3 = idd;
+      const float4 V0 = sv[i0], V1 = sv[i1], V2 = sv[i2], V3 = sv[i3];
+      const float wa = isB ? V1.w : V0.w, wb = isB ? V2.w : V1.w, wc = isB ? V0.w : V2.w, wd = V3.w;
+      const bool massive = fadd(fadd(fadd(wa, wb), wc), wd) != 0.0f;
+      const float k6 = 1.0f / 6.0f;
+      // g1
+      const float ux = fsub(V3.x, V1.x), uy = fsub(V3.y, V1.y), uz = fsub(V3.z, V1.z);
+      const float vx = fsub(V2.x, V1.x), vy = fsub(V2.y, V1.y), vz = fsub(V2.z, V1.z);
+      const float g1x = fmul(cross_c(uy, vz, uz, vy), k6), g1y = fmul(cross_c(uz, vx, ux, vz), k6),
+                  g1z = fmul(cross_c(ux, vy, uy, vx), k6);
+      // g2
+      const float ox = isB ? V1.x : V0.x, oy = isB ? V1.y : V0.y, oz = isB ? V1.z : V0.z;
+      const float yx = isB ? V0.x : V3.x, yy = isB ? V0.y : V3.y, yz = isB ? V0.z : V3.z;
+      const float px = fsub(V2.x, ox), py = fsub(V2.y, oy), pz = fsub(V2.z, oz);
+      const float qx = fsub(yx, ox), qy = fsub(yy, oy), qz = fsub(yz, oz);
+      const float nx = cross_c(py, qz, pz, qy), ny = cross_c(pz, qx, px, qz), nz = cross_c(px, qy, py, qx);
+      const float g2x = fmul(nx, k6), g2y = fmul(ny, k6), g2z = fmul(nz, k6);
+      // own vertices: u1 = V0, u2 = V1 (A) / V3 (B)
+      const uint32_t iu2 = isB ? i3 : i1;
+      float4 u1 = V0, u2;
+      u2.x = isB ? V3.x : V1.x; u2.y = isB ? V3.y : V1.y; u2.z = isB ? V3.z : V1.z; u2.w = isB ? V3.w : V1.w;
+      const float t1 = fmul(u1.w, dot3(g1x, g1y, g1z, g1x, g1y, g1z));
+      const float t2 = fmul(u2.w, dot3(g2x, g2y, g2z, g2x, g2y, g2z));
+      const float o1 = __shfl_xor_sync(m, t1, 1), o2 = __shfl_xor_sync(m, t2, 1);
+      // ((ta + tb) + tc) + td
+      const float sab = isB ? fadd(o1, o2) : fadd(t1, t2);
+      const float wSum = fadd(fadd(sab, isB ? t1 : o1), isB ? t2 : o2);
+      // volume numerator dot(cross(pb-pa, pc-pa), pd-pa): lane B's (n, V3-V1)
+      const float vnLocal = dot3(nx, ny, nz, ux, uy, uz);
+      const float vol = fdiv(__shfl_sync(m, vnLocal, lane | 1u), 6.0f);
+      const float C = fsub(vol, r);
+      const float dl = fdiv_pos(fsub(-C, fmul(alpha, l0)), fadd(wSum, alpha));
+      const float s1 = fmul(u1.w, dl), s2 = fmul(u2.w, dl);
+      u1.x = fadd(u1.x, fmul(g1x, s1)); u1.y = fadd(u1.y, fmul(g1y, s1)); u1.z = fadd(u1.z, fmul(g1z, s1));
+      u2.x = fadd(u2.x, fmul(g2x, s2)); u2.y = fadd(u2.y, fmul(g2y, s2)); u2.z = fadd(u2.z, fmul(g2z, s2));
+      if (live && massive && !(wSum < 1e-20f)) {
+        sv[i0] = u1;
+        sv[iu2] = u2;
+        if (!isB) lam[t] = fadd(l0, dl);
+      }
+    };
+    uint2 gd = groups[0];
+    bool live = pair < gd.y;
+    uint32_t t = gd.x + (live ? pair : gd.y - 1u);
+    uint2 id = idx[t];
+    float r = rest[t], l = lam[t];
+    for (uint32_t g = 0; g < n; ++g) {
+      const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 1u);
+      if (((tid >> 5) << 4) < gd.y) project(t, id, r, l, live);                // warp-uniform: idle warps skip the step
+      for (uint32_t i0 = pairs + ((tid >> 5) << 4); i0 < gd.y; i0 += pairs) {   // warp-uniform trip count
+        const uint32_t i = i0 + (lane >> 1);
+        const bool lv = i < gd.y;
+        const uint32_t t2 = gd.x + (lv ? i : gd.y - 1u);
+        project(t2, idx[t2], rest[t2], lam[t2], lv);
+      }
+      live = pair < gn.y && g + 1 < n;
+      t = gn.x + ((pair < gn.y) ? pair : gn.y - 1u);
+      if (g + 1 < n) { id = idx[t]; r = rest[t]; l = lam[t]; }
+      __syncthreads();
+      if (ft && g < 40) { ft[16 + g] = clock64(); ft[56 + g] = gd.y; }
+      gd = gn;
+    }
+  } else {
+    const uint32_t role = tid & 3u, lane = tid & 31u, qbase = lane & ~3u;
+    const uint32_t fo = (0x00000001u >> (role * 8u)) & 3u;        // {1,0,0,0}
+    const uint32_t fx = (0x01030203u >> (role * 8u)) & 3u;        // {3,2,3,1}
+    const uint32_t fy = (0x02010302u >> (role * 8u)) & 3u;        // {2,3,1,2}
+    const uint32_t quads = nth >> 2, quad = tid >> 2;
+    const unsigned m = 0xffffffffu;
+    // `live` is quad-uniform; idle quads run the same instructions on the group's last tet and
+    // write nothing, so every lane of a warp takes part in the shuffles
+    auto project = [&](uint32_t t, uint2 id, float r, float l0, bool live) {
+      auto pick = [&](uint32_t f) -> uint32_t { return (((f & 2u) ? id.y : id.x) >> ((f & 1u) * 16u)) & 0xffffu; };
+      const uint32_t iown = pick(role);
+      float4 own = sv[iown];
+      const float4 o = sv[pick(fo)], x = sv[pick(fx)], y = sv[pick(fy)];
+      const float wa = __shfl_sync(m, own.w, qbase), wb = __shfl_sync(m, own.w, qbase + 1),
+                  wc = __shfl_sync(m, own.w, qbase + 2), wd = __shfl_sync(m, own.w, qbase + 3);
+      const bool massive = fadd(fadd(fadd(wa, wb), wc), wd) != 0.0f;   // quad-uniform
+      const float k6 = 1.0f / 6.0f;
+      const float ux = fsub(x.x, o.x), uy = fsub(x.y, o.y), uz = fsub(x.z, o.z);
+      const float vx = fsub(y.x, o.x), vy = fsub(y.y, o.y), vz = fsub(y.z, o.z);
+      const float nx = cross_c(uy, vz, uz, vy), ny = cross_c(uz, vx, ux, vz), nz = cross_c(ux, vy, uy, vx);
+      const float gx = fmul(nx, k6), gy = fmul(ny, k6), gz = fmul(nz, k6);
+      const float tt = fmul(own.w, dot3(gx, gy, gz, gx, gy, gz));
+      const float ta = __shfl_sync(m, tt, qbase), tb = __shfl_sync(m, tt, qbase + 1), tc = __shfl_sync(m, tt, qbase + 2),
+                  td = __shfl_sync(m, tt, qbase + 3);
+      const float wSum = fadd(fadd(fadd(ta, tb), tc), td);
+      // role 3 holds n = cross(pb-pa, pc-pa) and own - o = pd - pa: the volume numerator
+      const float vn = dot3(nx, ny, nz, fsub(own.x, o.x), fsub(own.y, o.y), fsub(own.z, o.z));
+      const float vol = fdiv(__shfl_sync(m, vn, qbase + 3), 6.0f);
+      const float C = fsub(vol, r);
+      const float dl = fdiv_pos(fsub(-C, fmul(alpha, l0)), fadd(wSum, alpha));
+      const float sc = fmul(own.w, dl);
+      own.x = fadd(own.x, fmul(gx, sc)); own.y = fadd(own.y, fmul(gy, sc)); own.z = fadd(own.z, fmul(gz, sc));
+      if (live && massive && !(wSum < 1e-20f)) {
+        sv[iown] = own;
+        if (role == 0) lam[t] = fadd(l0, dl);
+      }
+    };
+    uint2 gd = groups[0];
+    bool live = quad < gd.y;
+    uint32_t t = gd.x + (live ? quad : gd.y - 1u);
+    uint2 id = idx[t];
+    float r = rest[t], l = lam[t];
+    for (uint32_t g = 0; g < n; ++g) {
+      const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 1u);
+      if (((tid >> 5) << 3) < gd.y) project(t, id, r, l, live);   // warp-uniform: idle warps skip the step
+      // colour groups larger than a block's worth of quads: warp-uniform trip count
+      for (uint32_t i0 = quads + ((tid >> 5) << 3); i0 < gd.y; i0 += quads) {
+        const uint32_t i = i0 + (lane >> 2);
+        const bool lv = i < gd.y;
+        const uint32_t t2 = gd.x + (lv ? i : gd.y - 1u);
+        project(t2, idx[t2], rest[t2], lam[t2], lv);
+      }
+      live = quad < gn.y && g + 1 < n;
+      t = gn.x + ((quad < gn.y) ? quad : gn.y - 1u);
+      if (g + 1 < n) { id = idx[t]; r = rest[t]; l = lam[t]; }
+      __syncthreads();
+      if (ft && g < 40) { ft[16 + g] = clock64(); ft[56 + g] = gd.y; }
+      gd = gn;
+    }
+  }
+}
+
+}  // namespace pbd

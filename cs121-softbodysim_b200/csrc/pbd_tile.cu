@@ -33,19 +33,11 @@
 #include <vector>
 
 #include "pbd_body.h"
+#include "pbd_sweep.cuh"
 
 namespace pbd {
 
 namespace {
-
-// first 64 bytes of a tile's record block (shared memory); offsets in bytes from the block start
-struct TileHdr {
-  uint32_t vertCount, contiguous, vertBegin, nEdgeGroups;
-  uint32_t nTetGroups, nEdges, nTets, offVertIdx;
-  uint32_t offEdgeGroups, offTetGroups, offEdgeIdx, offEdgeRest;
-  uint32_t offTetIdx, offTetRest, offEdgeLam, offTetLam;
-};
-static_assert(sizeof(TileHdr) == 64, "TileHdr is the 64-byte block header");
 
 // what the copy-issuing thread needs per tile (global memory)
 struct TileCopy {
@@ -148,19 +140,31 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
 
 // ---------------------------------------------------------------- vertex stages
 
-// Vertex stage applied while a phase-0 tile is loaded.  p arrives as (xStar, w) from HBM/L2.
-__device__ __forceinline__ float4 load_transform(const TileParams& P, const StepConsts& k, uint32_t s, int mode,
-                                                 bool clampFirst) {
-  float4 p = __ldcg(P.pos + s);
+// Vertex stage applied while a phase-0 tile is loaded, split into its loads and its arithmetic +
+// stores so that a thread can have the loads of several vertices in flight before the first store
+// (the compiler must assume that stores to prev/vel alias later loads).
+struct VertexIn {
+  float4 p, x, v;   // (xStar, w) | committed position | velocity
+};
+__device__ __forceinline__ VertexIn load_vertex(const TileParams& P, uint32_t s, int mode) {
+  VertexIn in;
+  in.p = __ldcg(P.pos + s);
+  in.x = in.v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mode == LOAD_PREDICT || mode == LOAD_COMMIT_PREDICT) in.x = __ldcg(P.prev + s);
+  if (mode == LOAD_PREDICT) in.v = __ldcg(P.vel + s);
+  return in;
+}
+__device__ __forceinline__ float4 finish_vertex(const TileParams& P, const StepConsts& k, uint32_t s, int mode,
+                                                bool clampFirst, VertexIn in) {
+  float4 p = in.p;
   if (mode == LOAD_GROUND) {
     ground_vertex(p, k);
   } else if (mode == LOAD_PREDICT) {
-    const float4 x = __ldcg(P.prev + s);
-    float4 v = __ldcg(P.vel + s);
-    p = predict_vertex(x, v, p.w, k);
+    float4 v = in.v;
+    p = predict_vertex(in.x, v, p.w, k);
     __stcg(P.vel + s, v);
   } else if (mode == LOAD_COMMIT_PREDICT) {
-    float4 x = __ldcg(P.prev + s), v;
+    float4 x = in.x, v;
     if (clampFirst) ground_vertex(p, k);
     commit_vertex(p, x, v, k);
     v.w = 0.0f;
@@ -169,6 +173,10 @@ __device__ __forceinline__ float4 load_transform(const TileParams& P, const Step
     __stcg(P.vel + s, v);
   }
   return p;
+}
+__device__ __forceinline__ float4 load_transform(const TileParams& P, const StepConsts& k, uint32_t s, int mode,
+                                                 bool clampFirst) {
+  return finish_vertex(P, k, s, mode, clampFirst, load_vertex(P, s, mode));
 }
 
 // vertex-only pass over the phase-0 partition (no constraints): used when there is nothing to
@@ -194,115 +202,16 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
   }
 }
 
-// ---------------------------------------------------------------- sweeps (shared memory only)
-
-__device__ __forceinline__ void sweep_edges(const TileHdr& h, unsigned char* rec, float4* sv, float alpha) {
-  const uint2* groups = reinterpret_cast<const uint2*>(rec + h.offEdgeGroups);
-  const uint32_t* idx = reinterpret_cast<const uint32_t*>(rec + h.offEdgeIdx);
-  const float* rest = reinterpret_cast<const float*>(rec + h.offEdgeRest);
-  float* lam = reinterpret_cast<float*>(rec + h.offEdgeLam);
-  for (uint32_t g = 0; g < h.nEdgeGroups; ++g) {
-    const uint2 gd = groups[g];
-    for (uint32_t i = threadIdx.x; i < gd.y; i += blockDim.x) {
-      const uint32_t e = gd.x + i;
-      const uint32_t id = idx[e];
-      const uint32_t a = id & 0xffffu, b = id >> 16;
-      float4 p0 = sv[a], p1 = sv[b];
-      float l = lam[e];
-      if (project_edge(p0, p1, rest[e], l, alpha)) {
-        sv[a] = p0;
-        sv[b] = p1;
-        lam[e] = l;
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// LANES == 1: one thread per tet (project_tet).
-// LANES == 4: one tet per 4 adjacent lanes, lane `role` owns vertex `role` (a,b,c,d).  All four
-// gradients have the form cross(x - o, y - o)/6 (Sim.cpp:146-149):
-//   ga: o=b x=d y=c | gb: o=a x=c y=d | gc: o=a x=d y=b | gd: o=a x=b y=c
-// so every lane runs the same instructions on role-selected operands; the reduction terms are
-// exchanged with quad shuffles and summed in the reference's order, which keeps the result
-// bit-identical while shortening the dependent instruction stream of a colour step ~3x.
-template <int LANES>
-__device__ __forceinline__ void sweep_tets(const TileHdr& h, unsigned char* rec, float4* sv, float alpha) {
-  const uint2* groups = reinterpret_cast<const uint2*>(rec + h.offTetGroups);
-  const uint2* idx = reinterpret_cast<const uint2*>(rec + h.offTetIdx);
-  const float* rest = reinterpret_cast<const float*>(rec + h.offTetRest);
-  float* lam = reinterpret_cast<float*>(rec + h.offTetLam);
-  for (uint32_t g = 0; g < h.nTetGroups; ++g) {
-    const uint2 gd = groups[g];
-    if (LANES == 1) {
-      for (uint32_t i = threadIdx.x; i < gd.y; i += blockDim.x) {
-        const uint32_t t = gd.x + i;
-        const uint2 id = idx[t];
-        const uint32_t a = id.x & 0xffffu, b = id.x >> 16, c = id.y & 0xffffu, d = id.y >> 16;
-        float4 pa = sv[a], pb = sv[b], pc = sv[c], pd = sv[d];
-        float l = lam[t];
-        if (project_tet(pa, pb, pc, pd, rest[t], l, alpha)) {
-          sv[a] = pa; sv[b] = pb; sv[c] = pc; sv[d] = pd;
-          lam[t] = l;
-        }
-      }
-    } else {
-      const uint32_t role = threadIdx.x & 3u, lane = threadIdx.x & 31u, qbase = lane & ~3u;
-      const uint32_t fo = (0x00000001u >> (role * 8u)) & 3u;        // {1,0,0,0}
-      const uint32_t fx = (0x01030203u >> (role * 8u)) & 3u;        // {3,2,3,1}
-      const uint32_t fy = (0x02010302u >> (role * 8u)) & 3u;        // {2,3,1,2}
-      const uint32_t quads = blockDim.x >> 2;
-      // warp-uniform trip count: every lane of a warp takes part in the shuffles
-      for (uint32_t i0 = (threadIdx.x >> 5) << 3; i0 < gd.y; i0 += quads) {
-        const uint32_t i = i0 + (lane >> 2);
-        const bool live = i < gd.y;
-        const uint32_t t = gd.x + (live ? i : gd.y - 1u);
-        const uint2 id = idx[t];
-        auto pick = [&](uint32_t f) -> uint32_t { return (((f & 2u) ? id.y : id.x) >> ((f & 1u) * 16u)) & 0xffffu; };
-        const uint32_t iown = pick(role);
-        float4 own = sv[iown];
-        const float4 o = sv[pick(fo)], x = sv[pick(fx)], y = sv[pick(fy)];
-        const float r = rest[t], l0 = lam[t];
-        const unsigned m = 0xffffffffu;
-        const float wa = __shfl_sync(m, own.w, qbase), wb = __shfl_sync(m, own.w, qbase + 1),
-                    wc = __shfl_sync(m, own.w, qbase + 2), wd = __shfl_sync(m, own.w, qbase + 3);
-        const bool massive = fadd(fadd(fadd(wa, wb), wc), wd) != 0.0f;   // quad-uniform
-        const float k6 = 1.0f / 6.0f;
-        const float ux = fsub(x.x, o.x), uy = fsub(x.y, o.y), uz = fsub(x.z, o.z);
-        const float vx = fsub(y.x, o.x), vy = fsub(y.y, o.y), vz = fsub(y.z, o.z);
-        const float nx = cross_c(uy, vz, uz, vy), ny = cross_c(uz, vx, ux, vz), nz = cross_c(ux, vy, uy, vx);
-        const float gx = fmul(nx, k6), gy = fmul(ny, k6), gz = fmul(nz, k6);
-        const float tt = fmul(own.w, dot3(gx, gy, gz, gx, gy, gz));
-        const float ta = __shfl_sync(m, tt, qbase), tb = __shfl_sync(m, tt, qbase + 1), tc = __shfl_sync(m, tt, qbase + 2),
-                    td = __shfl_sync(m, tt, qbase + 3);
-        const float wSum = fadd(fadd(fadd(ta, tb), tc), td);
-        // role 3 holds n = cross(pb-pa, pc-pa) and own - o = pd - pa: the volume numerator
-        const float vn = dot3(nx, ny, nz, fsub(own.x, o.x), fsub(own.y, o.y), fsub(own.z, o.z));
-        const float vol = fdiv(__shfl_sync(m, vn, qbase + 3), 6.0f);
-        if (live && massive && !(wSum < 1e-20f)) {
-          const float C = fsub(vol, r);
-          const float dl = fdiv(fsub(-C, fmul(alpha, l0)), fadd(wSum, alpha));
-          const float sc = fmul(own.w, dl);
-          own.x = fadd(own.x, fmul(gx, sc)); own.y = fadd(own.y, fmul(gy, sc)); own.z = fadd(own.z, fmul(gz, sc));
-          sv[iown] = own;
-          if (role == 0) lam[t] = fadd(l0, dl);
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // ---------------------------------------------------------------- the frame kernel
 
 template <int LANES>
 __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar[2];
-  __shared__ uint32_t itemTile[kMaxItems];
+  __shared__ TileCopy itemCopy[kMaxItems];   // copy descriptors of this CTA's tiles: no global latency when prefetching
   __shared__ uint32_t nItemsS;
-  unsigned char* const recBuf[2] = {smem, smem + P.recStride};
-  float4* const sv = reinterpret_cast<float4*>(smem + 2 * (size_t)P.recStride);
+  const uint32_t svOff = 2u * P.recStride;
+  float4* const sv = reinterpret_cast<float4*>(smem + svOff);
 
   const StepConsts k = *P.consts;
   const uint32_t tid = threadIdx.x, nth = blockDim.x;
@@ -322,7 +231,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
     for (uint32_t ph = 0; ph < P.nPhases; ++ph) {
       const PhaseDesc pd = P.phases[ph];
       for (uint32_t t = blockIdx.x; t < pd.tileCount; t += gridDim.x)
-        if (n < kMaxItems) itemTile[n++] = pd.tileBegin + t;
+        if (n < kMaxItems) itemCopy[n++] = P.copies[pd.tileBegin + t];
     }
     nItemsS = n;
     mbar_init(&mbar[0], 1);
@@ -334,24 +243,22 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   const uint32_t nItems = nItemsS;
   const uint32_t totalItems = nItems * P.iterations * P.substeps;
 
-  // fetch the record block of tile `t` into buffer `b` (thread 0 only)
-  auto fetch = [&](uint32_t t, uint32_t b) -> TileCopy {
-    const TileCopy c = P.copies[t];
-    unsigned char* dst = recBuf[b];
+  // fetch the record block of this CTA's item `ji` into buffer `b` (thread 0 only)
+  auto fetch = [&](uint32_t ji, uint32_t b) {
+    const TileCopy c = itemCopy[ji];
+    unsigned char* dst = smem + b * P.recStride;
     mbar_expect_tx(&mbar[b], c.staticBytes + c.edgeLamBytes + c.tetLamBytes);
     bulk_load(dst, P.blob + c.blobOff, c.staticBytes, &mbar[b]);
     if (c.edgeLamBytes) bulk_load(dst + c.staticBytes, P.edgeLam + c.edgeDevBegin, c.edgeLamBytes, &mbar[b]);
     if (c.tetLamBytes) bulk_load(dst + c.staticBytes + c.edgeLamBytes, P.tetLam + c.tetDevBegin, c.tetLamBytes, &mbar[b]);
-    return c;
   };
 
-  TileCopy curCopy{}, nextCopy{};   // thread 0 only: lambda ranges of the current / prefetched tile
-  if (tid == 0 && nItems) curCopy = fetch(itemTile[0], 0);
+  if (tid == 0 && nItems) fetch(0, 0);
 
   unsigned epoch = 0;
   uint32_t item = 0;      // items processed so far by this CTA
   uint32_t buf = 0;
-  uint32_t parity[2] = {0, 0};
+  uint32_t parityBits = 0;   // bit b: phase parity of mbar[b]
   bool needWait = true;
   uint32_t j = 0;         // position in itemTile
 
@@ -361,16 +268,17 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
         const PhaseDesc pd = P.phases[ph];
         const int mode = ph != 0 ? LOAD_PLAIN : it != 0 ? LOAD_GROUND : sub != 0 ? LOAD_COMMIT_PREDICT : LOAD_PREDICT;
         const bool tr = P.trace && sub == 0 && it + 1 == P.iterations && tid == 0;
-        long long* ft = (P.ftrace && tr && blockIdx.x == 0) ? P.ftrace + 128 * ph : nullptr;
+        long long* ft = (P.ftrace && tr && blockIdx.x == 0) ? P.ftrace + 256 * ph : nullptr;
         if (tr) P.trace[2 * ((size_t)ph * gridDim.x + blockIdx.x)] = globaltimer_ns();
         for (uint32_t t = blockIdx.x; t < pd.tileCount; t += gridDim.x) {
           if (ft) ft[0] = clock64();
           // ---- record block
           if (needWait) {
-            while (!mbar_try_wait(&mbar[buf], parity[buf])) {}
-            parity[buf] ^= 1u;
+            while (!mbar_try_wait(&mbar[buf], (parityBits >> buf) & 1u)) {}
+            parityBits ^= 1u << buf;
           }
-          unsigned char* rec = recBuf[buf];
+          const uint32_t recOff = buf * P.recStride;
+          unsigned char* rec = smem + recOff;
           const TileHdr h = *reinterpret_cast<const TileHdr*>(rec);
           if (ft) ft[1] = clock64();
           // ---- prefetch the next tile's block into the other buffer
@@ -378,33 +286,57 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           const bool hasNext = item + 1 < totalItems;
           if (tid == 0 && hasNext && nItems > 1) {
             bulk_wait_all();   // the lambda write-back that last read the other buffer (and its global writes) is complete
-            nextCopy = fetch(itemTile[jn], buf ^ 1u);
+            fetch(jn, buf ^ 1u);
           }
-          // ---- vertices L2 -> shared memory
+          // ---- vertices L2 -> shared memory (all of a thread's loads are issued before the first use)
           if (h.contiguous) {
-            for (uint32_t i = tid; i < h.vertCount; i += nth) sv[i] = load_transform(P, k, h.vertBegin + i, mode, true);
+            for (uint32_t base = 0; base < h.vertCount; base += 3u * nth) {
+              VertexIn in[3];
+#pragma unroll
+              for (int u = 0; u < 3; ++u) {
+                const uint32_t i = base + u * nth + tid;
+                if (i < h.vertCount) in[u] = load_vertex(P, h.vertBegin + i, mode);
+              }
+#pragma unroll
+              for (int u = 0; u < 3; ++u) {
+                const uint32_t i = base + u * nth + tid;
+                if (i < h.vertCount) sv[i] = finish_vertex(P, k, h.vertBegin + i, mode, true, in[u]);
+              }
+            }
           } else {
-            const uint32_t* vidx = reinterpret_cast<const uint32_t*>(rec + h.offVertIdx);
-            for (uint32_t i = tid; i < h.vertCount; i += nth) sv[i] = __ldcg(P.pos + vidx[i]);
+            const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
+            for (uint32_t base = 0; base < h.vertCount; base += 4u * nth) {
+              float4 v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t i = base + u * nth + tid;
+                if (i < h.vertCount) v[u] = __ldcg(P.pos + vidx[i]);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t i = base + u * nth + tid;
+                if (i < h.vertCount) sv[i] = v[u];
+              }
+            }
           }
           __syncthreads();
           if (ft) ft[2] = clock64();
           // ---- sweeps
-          sweep_edges(h, rec, sv, k.alphaEdge);
+          sweep_edges(h, recOff, svOff, k.alphaEdge, ft);
           if (ft) ft[3] = clock64();
-          sweep_tets<LANES>(h, rec, sv, k.alphaTet);
+          sweep_tets<LANES>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr);
           if (ft) ft[4] = clock64();
           // ---- write back
           if (h.contiguous) {
             for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + h.vertBegin + i, sv[i]);
           } else {
-            const uint32_t* vidx = reinterpret_cast<const uint32_t*>(rec + h.offVertIdx);
+            const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
             for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + vidx[i], sv[i]);
           }
           fence_async_smem();   // lambdas written by the sweeps -> visible to the bulk store
           __syncthreads();      // also: sv and rec are free for the next tile
           if (tid == 0) {
-            const TileCopy c = curCopy;
+            const TileCopy c = itemCopy[j];
             if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
             if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
             bulk_commit();
@@ -415,7 +347,6 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             needWait = false;
           } else {
             buf ^= 1u;
-            curCopy = nextCopy;
           }
           j = jn;
           ++item;
@@ -445,8 +376,7 @@ class TileBackend final : public Backend {
     block_ = plan.blockThreads ? std::min(plan.blockThreads, 512u) : 512u;
     nPhases_ = (uint32_t)plan.phases.size();
     nTile0_ = (uint32_t)plan.tile0Begin.size() - 1;
-    lanes_ = opts_.lanes_per_tet == 1 ? 1u : opts_.lanes_per_tet == 4 ? 4u : 4u;
-    if (lanes_ == 4 && block_ % 32) return cudaErrorInvalidValue;
+    lanes_ = opts_.lanes_per_tet == 2 ? 2u : opts_.lanes_per_tet == 4 ? 4u : 1u;   // auto: one thread per tet (fastest measured)
 
     // rest values are already on the device at the plan's device indices (pbd_capi.cu)
     std::vector<float> eRest(plan.edgeDevCount), tRest(plan.tetDevCount);
@@ -515,6 +445,28 @@ class TileBackend final : public Backend {
       c.tetDevBegin = t.tetDevBegin; c.tetLamBytes = 4u * pad4(t.tetCount);
       c.pad = 0;
     }
+    if (const char* dumpPath = getenv("PBD_DUMP_TILE")) {
+      // tools/mb_sweep.cu input: one tile's record block + its vertices (debug aid)
+      size_t ti = plan.phases.size() > 1 ? plan.phases[1].tileBegin : 0;
+      if (const char* e = getenv("PBD_DUMP_TILE_INDEX")) ti = (size_t)atoi(e);
+      if (ti < plan.tiles.size()) {
+        const Tile& t = plan.tiles[ti];
+        const TileCopy& c = copies[ti];
+        std::vector<float4> all(d.V), vv(t.vertCount);
+        cudaMemcpy(all.data(), d.pos, sizeof(float4) * d.V, cudaMemcpyDeviceToHost);
+        for (uint32_t i = 0; i < t.vertCount; ++i) vv[i] = all[t.contiguous ? t.vertBegin + i : plan.tileVerts[t.vertBegin + i]];
+        const uint32_t lamBytes = c.edgeLamBytes + c.tetLamBytes;
+        const uint32_t head[6] = {0x54494c45u, c.staticBytes + lamBytes, c.staticBytes, t.vertCount, t.edgeCount, t.tetCount};
+        if (FILE* f = fopen(dumpPath, "wb")) {
+          fwrite(head, sizeof(head), 1, f);
+          fwrite(blob.data() + c.blobOff, 1, c.staticBytes, f);
+          std::vector<unsigned char> z(lamBytes, 0);
+          fwrite(z.data(), 1, lamBytes, f);
+          fwrite(vv.data(), sizeof(float4), vv.size(), f);
+          fclose(f);
+        }
+      }
+    }
     recStride_ = (recMax + 127u) & ~127u;
     smemBytes_ = 2 * (size_t)recStride_ + sizeof(float4) * (size_t)std::max(plan.tileVertexCapacity, 1u);
 
@@ -542,8 +494,8 @@ class TileBackend final : public Backend {
       traceN_ = 2 * (size_t)(nPhases_ + 1) * 4096;
       if ((err = cudaMalloc((void**)&trace_, sizeof(unsigned long long) * traceN_)) != cudaSuccess) return err;
       cudaMemset(trace_, 0, sizeof(unsigned long long) * traceN_);
-      if ((err = cudaMalloc((void**)&ftrace_, sizeof(long long) * 128 * (nPhases_ + 1))) != cudaSuccess) return err;
-      cudaMemset(ftrace_, 0, sizeof(long long) * 128 * (nPhases_ + 1));
+      if ((err = cudaMalloc((void**)&ftrace_, sizeof(long long) * 256 * (nPhases_ + 1))) != cudaSuccess) return err;
+      cudaMemset(ftrace_, 0, sizeof(long long) * 256 * (nPhases_ + 1));
     }
 
     const void* fn = kernel();
@@ -594,12 +546,19 @@ class TileBackend final : public Backend {
               prevEnd ? (double)(s0 - prevEnd) * 1e-3 : 0.0);
       prevEnd = aMax;
     }
-    std::vector<long long> f(128 * (size_t)nPhases_);
+    std::vector<long long> f(256 * (size_t)nPhases_);
     cudaMemcpy(f.data(), ftrace_, sizeof(long long) * f.size(), cudaMemcpyDeviceToHost);
     for (uint32_t ph = 0; ph < nPhases_; ++ph) {
-      const long long* q = &f[128 * (size_t)ph];
+      const long long* q = &f[256 * (size_t)ph];
       fprintf(stderr, "[pbd-ftrace] phase %u CTA0: verts %lld edges %lld tets %lld | groups %lld+%lld | wait rec %lld cyc | vertex load %lld | edge sweep %lld | tet sweep %lld | store %lld\n",
               ph, q[8], q[9], q[10], q[6], q[7], q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4]);
+      fprintf(stderr, "[pbd-steps] phase %u edges (cycles/size):", ph);
+      long long prev = q[2];
+      for (int g = 0; g < 20 && g < q[6]; ++g) { fprintf(stderr, " %lld/%lld", q[16 + g] - prev, q[56 + g]); prev = q[16 + g]; }
+      fprintf(stderr, " | tets:");
+      prev = q[3];
+      for (int g = 0; g < 40 && g < q[7]; ++g) { fprintf(stderr, " %lld/%lld", q[36 + g] - prev, q[76 + g]); prev = q[36 + g]; }
+      fprintf(stderr, "\n");
     }
   }
   uint32_t launches_per_frame(const FrameShape&) const override { return 1; }
@@ -612,7 +571,8 @@ class TileBackend final : public Backend {
 
  private:
   const void* kernel() const {
-    return lanes_ == 1 ? (const void*)tile_frame_kernel<1> : (const void*)tile_frame_kernel<4>;
+    return lanes_ == 1 ? (const void*)tile_frame_kernel<1>
+           : lanes_ == 2 ? (const void*)tile_frame_kernel<2> : (const void*)tile_frame_kernel<4>;
   }
   pbd_options opts_;
   int device_;

@@ -49,13 +49,17 @@ double now_ms() {
 // ------------------------------------------------------------------ shifted k-d partitions
 
 // Multi-way k-d split in rank space.  Level L sorts the current vertex set along the L-th longest
-// axis of the body and cuts it into parts that receive equal shares of the tiles; `offset` (a
-// fraction of one part) rotates the cuts cyclically, so the last part wraps around to the first.
+// axis of the body frame and cuts it into parts that receive equal shares of the tiles; `offset`
+// (a fraction of one part) rotates the cuts cyclically, so the last part wraps around to the first.
+// Every cut is then snapped to the widest coordinate gap nearby: on lattice-like meshes the cuts
+// fall BETWEEN vertex planes (and the shifted partitions' cuts between other planes), on
+// unstructured meshes the snap is a no-op in effect.
 struct Partitioner {
-  const float* x = nullptr;
+  const float* x = nullptr;         // 3V body-frame coordinates
   int axis[3] = {0, 1, 2};
   double ext[3] = {1, 1, 1};
   double offset = 0.0;
+  uint32_t grid[3] = {0, 0, 0};     // parts per level when the tile count is a product m0*m1*m2 (0: derive)
   std::vector<uint32_t> idx;        // permutation being partitioned
   std::vector<uint32_t> tileBegin;  // leaf ranges in idx
   uint32_t* tileOf = nullptr;       // per caller vertex
@@ -75,26 +79,119 @@ struct Partitioner {
     if (level == 2) want = nTiles;
     else if (level == 1) want = std::sqrt((double)nTiles * ext[1] / ext[2]);
     else want = std::cbrt((double)nTiles * ext[0] * ext[0] / (ext[1] * ext[2]));
-    uint32_t parts = (uint32_t)std::llround(want);
+    uint32_t parts = grid[level] ? grid[level] : (uint32_t)std::llround(want);
     parts = std::max(1u, std::min(parts, std::min(nTiles, n)));
     if (parts == 1 && level < 2) { split(lo, hi, nTiles, level + 1); return; }
     const int ax = axis[level];
+    auto coord = [&](uint32_t i) { return x[3 * (size_t)idx[lo + i] + ax]; };
     std::sort(idx.begin() + lo, idx.begin() + hi, [&](uint32_t a, uint32_t b) {
       const float ca = x[3 * (size_t)a + ax], cb = x[3 * (size_t)b + ax];
       return ca < cb || (ca == cb && a < b);   // total order -> the split is unique
     });
+    // boundaries in sorted-rank space (cyclic), snapped to the widest gap within +-window
     const uint32_t shift = (uint32_t)((offset * n) / parts) % n;
-    if (shift) std::rotate(idx.begin() + lo, idx.begin() + lo + shift, idx.begin() + hi);
+    const uint32_t window = n / parts / 8;
+    std::vector<uint32_t> cut(parts), tiles(parts);
     uint32_t cum = 0;
     for (uint32_t j = 0; j < parts; ++j) {
-      const uint32_t tj = nTiles / parts + (j < nTiles % parts ? 1u : 0u);
-      const uint32_t b = lo + (uint32_t)(((uint64_t)n * cum) / nTiles);
-      const uint32_t e = lo + (uint32_t)(((uint64_t)n * (cum + tj)) / nTiles);
-      cum += tj;
-      split(b, e, tj, level + 1);
+      tiles[j] = nTiles / parts + (j < nTiles % parts ? 1u : 0u);
+      uint32_t b = (shift + (uint32_t)(((uint64_t)n * cum) / nTiles)) % n;
+      cum += tiles[j];
+      if (window && b != 0) {
+        const uint32_t from = b > window ? b - window : 1u, to = std::min(n - 1, b + window);
+        float best = coord(b) - coord(b - 1);
+        uint32_t bestR = b;
+        for (uint32_t r = from; r <= to; ++r) {
+          const float gap = coord(r) - coord(r - 1);
+          const uint32_t dr = r > b ? r - b : b - r, db = bestR > b ? bestR - b : b - bestR;
+          if (gap > best * 1.0001f || (gap >= best && dr < db)) { best = gap; bestR = r; }
+        }
+        b = bestR;
+      }
+      cut[j] = b;
+    }
+    // parts are the cyclic ranges [cut[j], cut[j+1]); rotate so that part 0 starts the array
+    for (uint32_t j = 1; j < parts; ++j)   // keep the cuts strictly increasing in cyclic order
+      if (((cut[j] + n - cut[0]) % n) <= ((cut[j - 1] + n - cut[0]) % n)) cut[j] = (cut[j - 1] + 1) % n;
+    const uint32_t c0 = cut[0];
+    if (c0) std::rotate(idx.begin() + lo, idx.begin() + lo + c0, idx.begin() + hi);
+    for (uint32_t j = 0; j < parts; ++j) {
+      const uint32_t b = (cut[j] + n - c0) % n;
+      const uint32_t e = j + 1 < parts ? (cut[j + 1] + n - c0) % n : n;
+      if (e > b) split(lo + b, lo + e, tiles[j], level + 1);
     }
   }
 };
+
+// Body frame: the rotation that minimises the volume of the axis-aligned bounding box (searched
+// over Euler angles on the extreme points of the body).  For box-like bodies the k-d cuts then
+// run parallel to the faces, so the cuts of different slabs line up and the shifted partitions
+// stay a fixed distance apart.  Returns row-major R (frame coordinates = R * x); identity unless
+// the box shrinks by more than 2 %.
+void body_frame(const float* x, uint32_t V, double R[9]) {
+  for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (V < 8) return;
+  // extreme points along 96 fixed directions (Fibonacci sphere)
+  std::vector<uint32_t> ext;
+  const int D = 96;
+  for (int d = 0; d < D; ++d) {
+    const double z = 1.0 - (2.0 * d + 1.0) / D, r = std::sqrt(std::max(0.0, 1.0 - z * z)), ph = d * 2.399963229728653;
+    const double dx = r * std::cos(ph), dy = r * std::sin(ph), dz = z;
+    uint32_t lo = 0, hi = 0;
+    double vlo = INFINITY, vhi = -INFINITY;
+    for (uint32_t v = 0; v < V; ++v) {
+      const double t = dx * x[3 * (size_t)v] + dy * x[3 * (size_t)v + 1] + dz * x[3 * (size_t)v + 2];
+      if (t < vlo) { vlo = t; lo = v; }
+      if (t > vhi) { vhi = t; hi = v; }
+    }
+    ext.push_back(lo);
+    ext.push_back(hi);
+  }
+  std::sort(ext.begin(), ext.end());
+  ext.erase(std::unique(ext.begin(), ext.end()), ext.end());
+  auto rot = [](double a, double b, double c, double M[9]) {   // Rz(c) * Ry(b) * Rx(a)
+    const double ca = std::cos(a), sa = std::sin(a), cb = std::cos(b), sb = std::sin(b), cc = std::cos(c), sc = std::sin(c);
+    M[0] = cc * cb; M[1] = cc * sb * sa - sc * ca; M[2] = cc * sb * ca + sc * sa;
+    M[3] = sc * cb; M[4] = sc * sb * sa + cc * ca; M[5] = sc * sb * ca - cc * sa;
+    M[6] = -sb;     M[7] = cb * sa;                M[8] = cb * ca;
+  };
+  auto volume = [&](const double M[9]) {
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t v : ext)
+      for (int i = 0; i < 3; ++i) {
+        const double t = M[3 * i] * x[3 * (size_t)v] + M[3 * i + 1] * x[3 * (size_t)v + 1] + M[3 * i + 2] * x[3 * (size_t)v + 2];
+        mn[i] = std::min(mn[i], t);
+        mx[i] = std::max(mx[i], t);
+      }
+    return (mx[0] - mn[0]) * (mx[1] - mn[1]) * (mx[2] - mn[2]);
+  };
+  double I[9];
+  rot(0, 0, 0, I);
+  const double v0 = volume(I);
+  if (!(v0 > 0.0) || !std::isfinite(v0)) return;
+  const double H = 1.5707963267948966;
+  double best[3] = {0, 0, 0}, bestV = v0, M[9];
+  const int G = 15;
+  for (int i = 0; i < G; ++i)
+    for (int j = 0; j < G; ++j)
+      for (int k = 0; k < G; ++k) {
+        const double a = H * i / G, b = H * j / G - H / 2, c = H * k / G;
+        rot(a, b, c, M);
+        const double v = volume(M);
+        if (v < bestV) { bestV = v; best[0] = a; best[1] = b; best[2] = c; }
+      }
+  for (double step = H / G / 2; step > 1e-5; step *= 0.5)
+    for (int pass = 0; pass < 2; ++pass)
+      for (int q = 0; q < 3; ++q)
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+          double t[3] = {best[0], best[1], best[2]};
+          t[q] += sgn * step;
+          rot(t[0], t[1], t[2], M);
+          const double v = volume(M);
+          if (v < bestV) { bestV = v; best[q] = t[q]; }
+        }
+  if (bestV < 0.98 * v0) rot(best[0], best[1], best[2], R);
+}
 
 // ------------------------------------------------------------------ residual re-partitioning
 
@@ -255,15 +352,121 @@ struct TileBuild {
 };
 
 // colour the constraints of one tile locally and sort them by (colour, id)
+// Try to empty the highest colour classes: move each of their constraints to a lower colour that
+// is free at all its vertices, or that is blocked by a single constraint which can itself move
+// to another free lower colour.  `ids` are tile-local vertex indices, arity per constraint.
+uint32_t reduce_colours(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nVerts, std::vector<uint32_t>& col,
+                        uint32_t nColours) {
+  if (nColours <= 1 || nColours > 64) return nColours;   // 64-bit masks are enough for tiles; otherwise keep greedy
+  std::vector<uint64_t> used(nVerts, 0);                 // colours present at a vertex
+  // owner[v * nColours + c] = constraint of colour c at vertex v
+  std::vector<uint32_t> owner((size_t)nVerts * nColours, NONE);
+  for (uint32_t k = 0; k < n; ++k)
+    for (uint32_t j = 0; j < arity; ++j) {
+      const uint32_t v = ids[(size_t)k * arity + j];
+      used[v] |= 1ull << col[k];
+      owner[(size_t)v * nColours + col[k]] = k;
+    }
+  auto mask_of = [&](uint32_t k) {
+    uint64_t mk = 0;
+    for (uint32_t j = 0; j < arity; ++j) mk |= used[ids[(size_t)k * arity + j]];
+    return mk;
+  };
+  auto recolour = [&](uint32_t k, uint32_t c) {
+    for (uint32_t j = 0; j < arity; ++j) {
+      const uint32_t v = ids[(size_t)k * arity + j];
+      // a constraint may list a vertex twice: clear/set is idempotent
+      used[v] &= ~(1ull << col[k]);
+      owner[(size_t)v * nColours + col[k]] = NONE;
+    }
+    col[k] = c;
+    for (uint32_t j = 0; j < arity; ++j) {
+      const uint32_t v = ids[(size_t)k * arity + j];
+      used[v] |= 1ull << c;
+      owner[(size_t)v * nColours + c] = k;
+    }
+  };
+  std::vector<std::vector<uint32_t>> byColour(nColours);
+  for (uint32_t k = 0; k < n; ++k) byColour[col[k]].push_back(k);
+  uint32_t top = nColours;
+  while (top > 1) {
+    const uint32_t hc = top - 1;
+    const uint64_t lower = (hc >= 64 ? ~0ull : ((1ull << hc) - 1));
+    bool emptied = true;
+    std::vector<uint32_t> members;
+    for (uint32_t k = 0; k < n; ++k)
+      if (col[k] == hc) members.push_back(k);
+    std::vector<std::pair<uint32_t, uint32_t>> undo;   // (constraint, previous colour)
+    for (uint32_t k : members) {
+      const uint64_t freeMask = ~mask_of(k) & lower;
+      if (freeMask) {
+        undo.push_back({k, col[k]});
+        recolour(k, (uint32_t)__builtin_ctzll(freeMask));
+        continue;
+      }
+      // one-step swap: a lower colour c blocked by exactly one constraint b that can move elsewhere
+      bool moved = false;
+      for (uint32_t c = 0; c < hc && !moved; ++c) {
+        uint32_t blocker = NONE;
+        bool single = true;
+        for (uint32_t j = 0; j < arity && single; ++j) {
+          const uint32_t o = owner[(size_t)ids[(size_t)k * arity + j] * nColours + c];
+          if (o == NONE || o == k) continue;
+          if (blocker == NONE) blocker = o; else if (blocker != o) single = false;
+        }
+        if (!single || blocker == NONE) continue;
+        // colours free for the blocker once k has left hc (k still occupies hc at its vertices: exclude hc anyway)
+        const uint64_t fb = ~mask_of(blocker) & lower & ~(1ull << c);
+        if (!fb) continue;
+        undo.push_back({blocker, col[blocker]});
+        recolour(blocker, (uint32_t)__builtin_ctzll(fb));
+        if (~mask_of(k) & (1ull << c)) {
+          undo.push_back({k, col[k]});
+          recolour(k, c);
+          moved = true;
+        }
+      }
+      if (!moved) { emptied = false; break; }
+    }
+    if (!emptied) {
+      for (size_t i = undo.size(); i-- > 0;) recolour(undo[i].first, undo[i].second);
+      break;
+    }
+    --top;
+  }
+  return top;
+}
+
+// colour the constraints of one tile locally and sort them by (colour, id)
 void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vector<uint32_t>& localOf,
                  std::vector<uint32_t>& scratch) {
   const uint32_t n = (uint32_t)tl.cons.size();
   std::sort(tl.cons.begin(), tl.cons.end());
+  // visiting order: most constrained first (largest vertex degree inside the tile), then id
+  std::vector<uint32_t> deg(nLocal, 0);
+  for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t j = 0; j < cs.arity; ++j) deg[localOf[cs.at(tl.cons[i])[j]]]++;
+  std::vector<uint32_t> key(n), visit(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t mx = 0, sum = 0;
+    for (uint32_t j = 0; j < cs.arity; ++j) {
+      const uint32_t d = deg[localOf[cs.at(tl.cons[i])[j]]];
+      mx = std::max(mx, d);
+      sum += d;
+    }
+    key[i] = (std::min(mx, 0xfffu) << 20) | std::min(sum, 0xfffffu);
+  }
+  std::iota(visit.begin(), visit.end(), 0u);
+  std::stable_sort(visit.begin(), visit.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
   scratch.resize((size_t)n * cs.arity);
   for (uint32_t i = 0; i < n; ++i)
-    for (uint32_t j = 0; j < cs.arity; ++j) scratch[(size_t)i * cs.arity + j] = localOf[cs.at(tl.cons[i])[j]];
-  std::vector<uint32_t> col;
-  tl.nColours = greedy_colour(scratch.data(), n, cs.arity, nLocal, col);
+    for (uint32_t j = 0; j < cs.arity; ++j) scratch[(size_t)i * cs.arity + j] = localOf[cs.at(tl.cons[visit[i]])[j]];
+  std::vector<uint32_t> colV;
+  uint32_t nc = greedy_colour(scratch.data(), n, cs.arity, nLocal, colV);
+  nc = reduce_colours(scratch.data(), n, cs.arity, nLocal, colV, nc);
+  std::vector<uint32_t> col(n);
+  for (uint32_t i = 0; i < n; ++i) col[visit[i]] = colV[i];
+  tl.nColours = nc;
   std::vector<uint32_t> order(n);
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return col[a] < col[b]; });
@@ -271,6 +474,45 @@ void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vecto
   for (uint32_t i = 0; i < n; ++i) { c2[i] = tl.cons[order[i]]; k2[i] = col[order[i]]; }
   tl.cons.swap(c2);
   tl.colour.swap(k2);
+}
+
+// Order the constraints of one colour group so that the shared-memory gathers of a warp do not
+// collide: a 16-byte vertex load is served per quarter-warp (8 lanes), conflict-free when the 8
+// tile-local vertex indices of each role differ modulo 8.  Greedy: fill one quarter-warp at a
+// time with the first remaining constraints whose indices are still free in every role.  The
+// order inside a colour group never changes the result (its constraints share no vertex).
+void bank_order(const CSet& cs, const std::vector<uint32_t>& localOf, uint32_t* cons, uint32_t n) {
+  if (n <= 1) return;
+  std::vector<uint32_t> rest(cons, cons + n), out;
+  out.reserve(n);
+  std::vector<uint8_t> taken(n, 0);
+  uint32_t firstFree = 0, left = n;
+  while (left) {
+    uint8_t used[4] = {0, 0, 0, 0};
+    uint32_t filled = 0;
+    for (uint32_t i = firstFree; i < n && filled < 8; ++i) {
+      if (taken[i]) continue;
+      const uint32_t* id = cs.at(rest[i]);
+      bool ok = true;
+      for (uint32_t r = 0; r < cs.arity && ok; ++r) ok = !(used[r] >> (localOf[id[r]] & 7u) & 1u);
+      if (!ok) continue;
+      for (uint32_t r = 0; r < cs.arity; ++r) used[r] |= (uint8_t)(1u << (localOf[id[r]] & 7u));
+      taken[i] = 1;
+      out.push_back(rest[i]);
+      ++filled;
+      --left;
+    }
+    // nothing compatible is left for the open lanes of this quarter-warp: fill them in order
+    for (uint32_t i = firstFree; i < n && filled < 8 && left; ++i) {
+      if (taken[i]) continue;
+      taken[i] = 1;
+      out.push_back(rest[i]);
+      ++filled;
+      --left;
+    }
+    while (firstFree < n && taken[firstFree]) ++firstFree;
+  }
+  std::copy(out.begin(), out.end(), cons);
 }
 
 // Finish a tile: vertex list (gathered tiles: the slots its constraints touch), local numbering,
@@ -291,8 +533,17 @@ void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& local
     nLocal = (uint32_t)tb.verts.size();
     for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.verts[i]] = i;
   }
-  for (int ty = 0; ty < 2; ++ty)
-    if (!tb.ty[ty].cons.empty()) colour_list(sets[ty], tb.ty[ty], nLocal, localOf, scratch);
+  for (int ty = 0; ty < 2; ++ty) {
+    TypeList& L = tb.ty[ty];
+    if (L.cons.empty()) continue;
+    colour_list(sets[ty], L, nLocal, localOf, scratch);
+    for (size_t i = 0; i < L.cons.size();) {
+      size_t j = i;
+      while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
+      bank_order(sets[ty], localOf, &L.cons[i], (uint32_t)(j - i));
+      i = j;
+    }
+  }
 }
 
 uint32_t tile_bytes(const TileBuild& tb) {
@@ -372,14 +623,23 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   plan.blockThreads = blockThreads;
   if (opts.partitions > kMaxPartitions) { err = "partitions must be <= 8"; return false; }
 
-  // body extents -> axis order for the k-d levels
+  // body frame, extents -> axis order for the k-d levels
   Partitioner base;
-  base.x = m.x0;
+  std::vector<float> xf((size_t)m.V * 3);
+  {
+    double R[9];
+    body_frame(m.x0, m.V, R);
+    for (uint32_t v = 0; v < m.V; ++v)
+      for (int i = 0; i < 3; ++i)
+        xf[3 * (size_t)v + i] = (float)(R[3 * i] * m.x0[3 * (size_t)v] + R[3 * i + 1] * m.x0[3 * (size_t)v + 1] +
+                                        R[3 * i + 2] * m.x0[3 * (size_t)v + 2]);
+  }
+  base.x = xf.data();
   {
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t v = 0; v < m.V; ++v)
       for (int a = 0; a < 3; ++a) {
-        const float c = m.x0[3 * (size_t)v + a];
+        const float c = xf[3 * (size_t)v + a];
         mn[a] = std::min(mn[a], c);
         mx[a] = std::max(mx[a], c);
       }
@@ -406,6 +666,32 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     if (attempt > 24) { err = "could not fit the tiles into shared memory"; return false; }
     const uint32_t K = K1 <= 1 ? 1u : (opts.partitions ? opts.partitions : 4u);
 
+    // A regular m0 x m1 x m2 arrangement keeps the cuts of all slabs / columns aligned, which is
+    // what makes the shifted partitions cover every constraint of a box-like body.  Take the
+    // largest product <= K1 whose tiles are not too elongated (when the caller fixed the tile
+    // size, or the body is tiny, keep K1 and split unevenly instead).
+    base.grid[0] = base.grid[1] = base.grid[2] = 0;
+    uint32_t tilesWanted = K1;
+    if (!opts.tile_vertices && K1 >= 8) {
+      uint32_t bestProd = 0;
+      double bestAspect = 0.0;
+      for (uint32_t a = 1; a <= K1; ++a)
+        for (uint32_t b = 1; a * b <= K1; ++b) {
+          const uint32_t c = K1 / (a * b);
+          if (c == 0) continue;
+          const double d0 = base.ext[0] / a, d1 = base.ext[1] / b, d2 = base.ext[2] / c;
+          const double aspect = std::max({d0, d1, d2}) / std::min({d0, d1, d2});
+          if (aspect > 1.75) continue;
+          const uint32_t prod = a * b * c;
+          if (prod > bestProd || (prod == bestProd && aspect < bestAspect)) {
+            bestProd = prod; bestAspect = aspect;
+            base.grid[0] = a; base.grid[1] = b; base.grid[2] = c;
+          }
+        }
+      if (bestProd * 10 >= K1 * 8) tilesWanted = bestProd;   // give up at most 20 % of the SMs for regularity
+      else base.grid[0] = base.grid[1] = base.grid[2] = 0;
+    }
+
     // ---- partitions (per caller vertex), P_0 also defines the slot numbering
     std::vector<std::vector<uint32_t>> tileOfV(K, std::vector<uint32_t>(m.V, 0));
     std::vector<uint32_t> tile0Begin, slotToVertex;
@@ -416,7 +702,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       pt.idx.resize(m.V);
       std::iota(pt.idx.begin(), pt.idx.end(), 0u);
       pt.tileOf = tileOfV[p].data();
-      if (m.V) pt.split(0, m.V, K1, 0); else pt.tileBegin.push_back(0);
+      if (m.V) pt.split(0, m.V, tilesWanted, 0); else pt.tileBegin.push_back(0);
       nTilesMax = std::max(nTilesMax, (uint32_t)pt.tileBegin.size());
       if (p == 0) {
         tile0Begin = pt.tileBegin;
@@ -445,7 +731,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     for (int ty = 0; ty < 2; ++ty) {
       const CSet& cs = sets[ty];
       std::fill(load.begin(), load.end(), (uint16_t)0);
-      std::vector<uint8_t> mask(cs.n, 0);
+      std::vector<uint8_t> mask(cs.n, 0), phaseOf(cs.n, 0);
       std::vector<uint32_t> bucket[kMaxPartitions + 1];
       for (uint32_t k = 0; k < cs.n; ++k) {
         const uint32_t* id = cs.at(k);
@@ -481,8 +767,35 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
             if (mxl < bestMax || (mxl == bestMax && sum < bestSum)) { bestP = p; bestMax = mxl; bestSum = sum; }
           }
           for (uint32_t j = 0; j < cs.arity; ++j) load[(size_t)id[j] * K + bestP]++;
-          mainPh[bestP][tileOfS[bestP][id[0]]].ty[ty].cons.push_back(k);
+          phaseOf[k] = (uint8_t)bestP;
         }
+      // local search: move a constraint to another admissible phase when that lowers the larger
+      // of the two peak loads involved (a few sweeps; deterministic)
+      for (int sweep = 0; sweep < 6; ++sweep) {
+        uint32_t moves = 0;
+        for (uint32_t k = 0; k < cs.n; ++k) {
+          if (mask[k] == 0 || (mask[k] & (mask[k] - 1)) == 0) continue;   // residual or forced
+          const uint32_t* id = cs.at(k);
+          const uint32_t p0 = phaseOf[k];
+          uint32_t cur = 0;
+          for (uint32_t j = 0; j < cs.arity; ++j) cur = std::max<uint32_t>(cur, load[(size_t)id[j] * K + p0]);
+          uint32_t bestP = p0, bestMax = cur;
+          for (uint32_t p = 0; p < K; ++p) {
+            if (p == p0 || !(mask[k] >> p & 1)) continue;
+            uint32_t mxl = 0;
+            for (uint32_t j = 0; j < cs.arity; ++j) mxl = std::max<uint32_t>(mxl, load[(size_t)id[j] * K + p] + 1u);
+            if (mxl < bestMax) { bestMax = mxl; bestP = p; }
+          }
+          if (bestP != p0) {
+            for (uint32_t j = 0; j < cs.arity; ++j) { load[(size_t)id[j] * K + p0]--; load[(size_t)id[j] * K + bestP]++; }
+            phaseOf[k] = (uint8_t)bestP;
+            ++moves;
+          }
+        }
+        if (!moves) break;
+      }
+      for (uint32_t k = 0; k < cs.n; ++k)
+        if (mask[k]) mainPh[phaseOf[k]][tileOfS[phaseOf[k]][cs.at(k)[0]]].ty[ty].cons.push_back(k);
       if (getenv("PBD_PLAN_DEBUG")) {
         // forced load: constraints with a single admissible phase
         std::vector<uint16_t> forced((size_t)m.V * K, 0);

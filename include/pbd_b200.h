@@ -100,7 +100,7 @@ typedef struct pbd_options {
   uint32_t block_threads;  /* 0 = auto                                                           */
   uint32_t max_phases;     /* reserved (ignored)                                                 */
   uint32_t partitions;     /* tile backend: shifted vertex partitions per sweep, 0 = auto (4)    */
-  uint32_t lanes_per_tet;  /* tile backend: 1 or 4 lanes cooperate on one tet, 0 = auto          */
+  uint32_t lanes_per_tet;  /* tile backend: 1, 2 or 4 lanes cooperate on one tet, 0 = auto (1)   */
   uint32_t reserved[7];
 } pbd_options;
 

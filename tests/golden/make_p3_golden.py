@@ -2,10 +2,10 @@
 """P3 golden: how the REFERENCE's own 1000-frame residuals on BASELINE config 1 vary with the
 constraint order.  Trajectories are chaotic after contact, so "no worse than the
 reference" is judged against the reference's own spread: the unmodified reference
-(oracle/_ref) is run on the original order and on 3 seeded random permutations of the edge and
+(oracle/_ref) is run on the original order and on 11 seeded random permutations of the edge and
 tet arrays; residuals are averaged over frames 800..1000 (every 10th frame).
 
-Run in the build container:  python tests/golden/make_p3_golden.py   (~2 min on 4 cores)
+Run in the build container:  python tests/golden/make_p3_golden.py   (~5 min on 6 cores)
 Writes tests/golden/ref_config1_p3_window.npz.
 """
 import importlib
@@ -44,8 +44,8 @@ def run(seed):
 
 
 if __name__ == "__main__":
-    with ProcessPoolExecutor(4) as ex:
-        res = list(ex.map(run, [0, 1, 2, 3]))
+    with ProcessPoolExecutor(6) as ex:
+        res = list(ex.map(run, list(range(12))))
     res = np.stack(res)                      # [order, frame, metric]
     np.savez_compressed(os.path.join(HERE, "ref_config1_p3_window.npz"), window=np.array(WINDOW),
                         keys=np.array(KEYS), residuals=res)
