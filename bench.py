@@ -59,6 +59,17 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload: str, backend: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the frame kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json); None if never captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(f"{workload}:{backend}")
+    except Exception:
+        return None
+
+
 def make_workload(name, mg):
     import numpy as np
     w = WORKLOADS[name]
@@ -309,7 +320,7 @@ def main():
         "tet_constraints_per_s": value * T * I,
         "substeps_per_s_per_gpu": value / world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": ncu_traffic(args.workload, body.name()), "peak_source": peak_src,
                      "kernel": "whole frame = %d launches of %s" % (info["launches_per_frame"], body.name()),
                      "algorithmic_bytes_per_substep": bytes_sub, "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": world * args.steps * S / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 52,
