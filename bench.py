@@ -48,6 +48,9 @@ WORKLOADS = {
     "config1": dict(asset="default", substeps=10, iterations=6,
                     desc="BASELINE configs[0]: default Assets/SoftBody tet mesh (V=8613 E=41488 T=26070), 10 substeps x 6 iterations"),
     "small": dict(kuhn=10, substeps=10, iterations=6, desc="one 6k-tet body (config-4 body), smoke-sized"),
+    "batch4096": dict(kuhn=10, bodies=4096, substeps=10, iterations=6,
+                      desc="BASELINE configs[3]: batch of 4096 independent 6,000-tet bodies (Kuhn n=10, V=1331 E=7930 "
+                           "T=6000 each, per-body rotation), 10 substeps x 6 iterations; bodies sharded across the GPUs"),
 }
 
 
@@ -182,6 +185,119 @@ def run_reference_arm(args):
     return 0
 
 
+def run_batch(args):
+    """--workload batch4096 (BASELINE configs[3]): 4096 independent 6k-tet bodies, sharded across the
+    ranks (bodies b with b % world == rank), one kernel per frame per GPU, no collective on the data
+    path.  Total work is fixed -> "scaling": "strong".  A substep here = one substep of ALL bodies."""
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if dist:
+        dist.barrier()
+    pkg = ge.package()
+    capi, mg = pkg.capi, pkg.meshgen
+    w = WORKLOADS[args.workload]
+    nb, S, I = w["bodies"], w["substeps"], w["iterations"]
+    local_xyz, tets, edges = mg.kuhn_grid(w["kuhn"], rot=np.eye(3), lowest_y=None)
+    mine = list(range(rank, nb, world))
+    bodies = []
+    for b in mine:       # deterministic per-body orientation and drop height: trajectories differ
+        rot = mg.rotation_zx(7.0 * (b % 47), 3.0 * (b % 29))
+        bodies.append((mg.place_body(local_xyz, rot=rot, lowest_y=0.25 + 0.001 * (b % 13)), edges, tets))
+    V, E, T = len(local_xyz), len(edges), len(tets)
+    t0 = time.perf_counter()
+    batch = capi.Batch(capi.SolverParams.default(substeps=S, iterations=I), bodies, device=local)
+    init_ms = (time.perf_counter() - t0) * 1e3
+    info = batch.info()
+    host_pos = torch.empty(3 * V * len(mine), dtype=torch.float32).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        batch.step_async(DT, 1)
+        batch.sync()
+    sampler = ClockSampler(local)
+    sync_all()
+    sampler.start()
+    dev_ms = []
+    for _ in range(args.steps):                      # working set (~0.9 GB per GPU at N=1) >> L2: no flush needed
+        batch.step_async(DT, 1)
+        dev_ms.append(batch.sync())
+    sync_all()
+    total_ms = sum(dev_ms)
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.step(DT)
+        batch.read_positions(out_ptr=host_pos.data_ptr())
+    e2e_s = time.perf_counter() - e0
+    clocks = sampler.stop()
+    if dist:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    pos = host_pos.numpy().reshape(-1, 3)
+    sane = bool(np.isfinite(pos).all() and pos[:, 1].min() >= -1e-5)
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+    frame_ms = total_ms / args.steps
+    value = args.steps * S / (total_ms * 1e-3)                      # substeps of the WHOLE batch per second
+    bytes_sub = nb * (104 * V + I * (20 * E + 28 * T + 84 * V))
+    achieved = bytes_sub * S / (frame_ms * 1e-3) / 1e9
+    peak, peak_src = load_peaks()
+    line = {
+        "metric": METRIC, "value": value, "unit": "batch-" + UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "bodies": nb, "bodies_per_gpu": len(mine), "V": V, "E": E, "T": T,
+                   "substeps_per_frame": S, "iterations": I, "dt": DT, "backend": "b200-batch",
+                   "order_mode": "strict", "parallelism": f"{world} GPU(s), bodies sharded, no collective",
+                   "l2": "not flushed: per-GPU working set %.2f GB >> L2" % (info["device_bytes"] / 1e9)},
+        "body_substeps_per_s": value * nb, "tet_constraints_per_s": value * nb * T * I,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                     "frac": achieved / (peak * world), "traffic": ncu_traffic(args.workload, "b200-batch"),
+                     "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
+                     "kernel": "batch_frame_kernel, 1 launch per frame per GPU",
+                     "algorithmic_bytes_per_substep": bytes_sub},
+        "e2e": {"value": args.steps * S / e2e_s, "unit": "batch-" + UNIT, "h2d_bytes_per_step": 52,
+                "d2h_bytes_per_step": 12 * V * len(mine), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "pbd_batch_step + pbd_batch_read_positions -> pinned host buffer"},
+        "gpu_launches": args.steps * world, "clocks": clocks, "init_ms": init_ms, "plan_ms": info["plan_ms"],
+        "schedule": {k: info[k] for k in ("edge_colors", "tet_colors", "tiles", "grid_blocks", "block_threads")},
+        "sane": sane,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_run(bodies[0][0], edges, tets, w, S, 8, 1, threads=0)   # 8 frames of ONE body
+        per_body = r["substeps"] / r["seconds"]
+        line["cpu_baseline"] = {"value": per_body / nb, "unit": "batch-" + UNIT, "cores": 1, "kind": r["kind"],
+                                "sample": f"8 frames x {S} substeps of ONE body on 1 of {os.cpu_count()} host cores "
+                                          f"({per_body:.1f} body-substeps/s), divided by {nb} bodies"}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    batch.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,6 +319,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    if args.workload == "batch4096" and args.impl != "reference":
+        return run_batch(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 

@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "pbd_plan_create", "pbd_plan_get_info", "pbd_plan_get_order", "pbd_plan_get_sequence",
     "pbd_plan_get_edge_slots", "pbd_plan_get_tet_slots", "pbd_plan_destroy",
     "pbd_batch_create", "pbd_batch_step", "pbd_batch_step_async", "pbd_batch_sync",
-    "pbd_batch_read_positions", "pbd_batch_get_info", "pbd_batch_destroy",
+    "pbd_batch_read_positions", "pbd_batch_get_info", "pbd_batch_get_schedule_order", "pbd_batch_destroy",
 ]
 
 
@@ -162,6 +162,7 @@ def lib() -> C.CDLL:
     L.pbd_batch_sync.argtypes = [vp, C.POINTER(C.c_double)]
     L.pbd_batch_read_positions.argtypes = [vp, vp, C.POINTER(C.c_double)]
     L.pbd_batch_get_info.argtypes = [vp, C.POINTER(Info)]
+    L.pbd_batch_get_schedule_order.argtypes = [vp, vp, vp]
     L.pbd_batch_destroy.argtypes = [vp]
     L.pbd_batch_destroy.restype = None
     _lib = L
@@ -266,6 +267,82 @@ class Body:
         out = np.zeros(shape, dtype=np.float32)
         _check(lib().pbd_get_array(self.h, what, out.ctypes.data_as(C.c_void_p)))
         return out
+
+
+class Batch:
+    """Many independent bodies stepped by one kernel per frame (pbd_batch_*; BASELINE config 4).
+    ``bodies`` is a list of ``(x0 [V,3], edges [E,2], tets [T,4])`` with body-local indices."""
+
+    def __init__(self, params: SolverParams, bodies, device: int = -1, options: Options | None = None):
+        L = lib()
+        xs = [np.ascontiguousarray(b[0], dtype=np.float32).reshape(-1, 3) for b in bodies]
+        es = [np.ascontiguousarray(b[1], dtype=np.uint32).reshape(-1, 2) for b in bodies]
+        ts = [np.ascontiguousarray(b[2], dtype=np.uint32).reshape(-1, 4) for b in bodies]
+        self.n = len(bodies)
+        self.v_off = np.concatenate([[0], np.cumsum([len(x) for x in xs])]).astype(np.uint64)
+        self.e_off = np.concatenate([[0], np.cumsum([len(e) for e in es])]).astype(np.uint64)
+        self.t_off = np.concatenate([[0], np.cumsum([len(t) for t in ts])]).astype(np.uint64)
+        x0 = np.concatenate(xs) if xs else np.zeros((0, 3), np.float32)
+        e = np.concatenate(es) if es else np.zeros((0, 2), np.uint32)
+        t = np.concatenate(ts) if ts else np.zeros((0, 4), np.uint32)
+        self.V, self.E, self.T = int(self.v_off[-1]), int(self.e_off[-1]), int(self.t_off[-1])
+        self.params = params.copy()
+        st = C.c_int(0)
+        self.h = L.pbd_batch_create(C.byref(self.params), self.n, _ptr(self.v_off), _ptr(self.e_off), _ptr(self.t_off),
+                                    _ptr(x0), _ptr(e), _ptr(t), device,
+                                    C.byref(options) if options is not None else None, C.byref(st))
+        if not self.h:
+            raise PBDError(st.value, L.pbd_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pbd_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def step(self, dt: float, stats: StepStats | None = None):
+        _check(lib().pbd_batch_step(self.h, C.c_float(dt), C.byref(stats) if stats is not None else None))
+
+    def step_async(self, dt: float, frames: int = 1):
+        _check(lib().pbd_batch_step_async(self.h, C.c_float(dt), frames))
+
+    def sync(self) -> float:
+        ms = C.c_double(0.0)
+        _check(lib().pbd_batch_sync(self.h, C.byref(ms)))
+        return ms.value
+
+    def read_positions(self, out: np.ndarray | None = None, out_ptr: int | None = None):
+        """Committed positions of all bodies, concatenated in body order, float32 [sum V, 3]."""
+        if out_ptr is not None:
+            _check(lib().pbd_batch_read_positions(self.h, C.c_void_p(out_ptr), None))
+            return None
+        if out is None:
+            out = np.empty((self.V, 3), dtype=np.float32)
+        _check(lib().pbd_batch_read_positions(self.h, out.ctypes.data_as(C.c_void_p), None))
+        return out
+
+    def body_positions(self, b: int, pos: np.ndarray) -> np.ndarray:
+        return pos[int(self.v_off[b]):int(self.v_off[b + 1])]
+
+    def schedule_order(self, b: int | None = None):
+        eo = np.empty(self.E, dtype=np.uint32)
+        to = np.empty(self.T, dtype=np.uint32)
+        _check(lib().pbd_batch_get_schedule_order(self.h, _ptr(eo), _ptr(to)))
+        if b is None:
+            return eo, to
+        return (eo[int(self.e_off[b]):int(self.e_off[b + 1])], to[int(self.t_off[b]):int(self.t_off[b + 1])])
+
+    def info(self) -> dict:
+        i = Info()
+        _check(lib().pbd_batch_get_info(self.h, C.byref(i)))
+        return i.as_dict()
 
 
 class Plan:

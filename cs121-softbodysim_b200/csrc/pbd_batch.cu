@@ -1,15 +1,438 @@
-// pbd_batch.cu -- batch-of-bodies entry points (placeholder).
+// pbd_batch.cu -- many independent soft bodies (BASELINE.json config 4: 4096 x 5k-tet bodies).
+//
+// The reference runs one body per PBDServer process (CProgram/src/main.cpp:69-98); a batch is
+// that path N times.  Bodies never interact, so nothing here synchronises across CTAs: ONE kernel
+// per frame, each CTA takes whole bodies.  A body's record block (tile-local u16 indices, rest
+// values, colour-group table, lambdas -- the same block format the tile backend uses, one "tile"
+// = the whole body) is fetched with TMA bulk copies and its vertices are loaded ONCE; all
+// substeps x iterations of the frame then run out of shared memory (pbd_sweep.cuh) with block
+// barriers only, and positions / velocities / lambdas go back to HBM once per frame.
+//
+//   for body in my bodies:                                   SerialStepper::step, Sim.cpp:280-305
+//     bulk-load record block; load xStar|w, x, v; predict     Sim.cpp:178-185
+//     for substep: for iteration: [ground clamp of the previous iteration] edges; tets
+//                  ground + commit (+ predict of the next substep) in shared memory      :187-222
+//     store x, v, xStar; bulk-store lambdas
+//
+// Bodies must fit one SM's shared memory (16 B/vertex + 20 B/edge + 28 B/tet, ~213 KB for the
+// 6k-tet body of config 4); larger bodies belong to pbd_create.  Order of projection per body:
+// all edges colour by colour, then all tets colour by colour (PBD_ORDER_STRICT), disclosed by
+// pbd_batch_get_schedule_order -- the unmodified reference run on the permuted arrays matches bit
+// for bit (tests/test_parity_gpu.py).
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
 #include "pbd_body.h"
+#include "pbd_device.cuh"
+#include "pbd_sweep.cuh"
+
+using namespace pbd;
+
+namespace {
+
+double wall_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct BodyDesc {
+  unsigned long long blobOff;
+  uint32_t staticBytes;
+  uint32_t edgeDevBegin, edgeLamBytes;
+  uint32_t tetDevBegin, tetLamBytes;
+  uint32_t pad;
+};
+
+struct BatchParams {
+  float4* pos;
+  float4* prev;
+  float4* vel;
+  const unsigned char* blob;
+  const BodyDesc* bodies;
+  float* edgeLam;
+  float* tetLam;
+  const StepConsts* consts;
+  uint32_t nBodies, substeps, iterations;
+  uint32_t recStride;
+};
+
+__global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const uint32_t svOff = P.recStride;
+  float4* const sv = reinterpret_cast<float4*>(smem + svOff);
+  const StepConsts k = *P.consts;
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  const bool clamp = P.iterations > 0;   // the reference clamps once per iteration (Sim.cpp:296)
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  for (uint32_t b = blockIdx.x; b < P.nBodies; b += gridDim.x) {
+    const BodyDesc c = P.bodies[b];
+    if (tid == 0) {
+      mbar_expect_tx(&mbar, c.staticBytes + c.edgeLamBytes + c.tetLamBytes);
+      bulk_load(smem, P.blob + c.blobOff, c.staticBytes, &mbar);
+      if (c.edgeLamBytes) bulk_load(smem + c.staticBytes, P.edgeLam + c.edgeDevBegin, c.edgeLamBytes, &mbar);
+      if (c.tetLamBytes) bulk_load(smem + c.staticBytes + c.edgeLamBytes, P.tetLam + c.tetDevBegin, c.tetLamBytes, &mbar);
+    }
+    while (!mbar_try_wait(&mbar, parity)) {}
+    parity ^= 1u;
+    const TileHdr h = *reinterpret_cast<const TileHdr*>(smem);
+    // predict of the first substep while the vertices are loaded
+    for (uint32_t i = tid; i < h.vertCount; i += nth) sv[i] = load_transform(P, k, h.vertBegin + i, LOAD_PREDICT, false);
+    __syncthreads();
+    for (uint32_t sub = 0; sub < P.substeps; ++sub) {
+      for (uint32_t it = 0; it < P.iterations; ++it) {
+        if (it != 0) {   // ground clamp that closes the previous iteration
+          for (uint32_t i = tid; i < h.vertCount; i += nth) { float4 p = sv[i]; ground_vertex(p, k); sv[i] = p; }
+          __syncthreads();
+        }
+        sweep_edges(h, 0, svOff, k.alphaEdge, nullptr);
+        sweep_tets<1>(h, 0, svOff, k.alphaTet, nullptr);
+      }
+      const bool last = sub + 1 == P.substeps;
+      for (uint32_t i = tid; i < h.vertCount; i += nth) {
+        const uint32_t s = h.vertBegin + i;
+        float4 p = sv[i], x = __ldcg(P.prev + s), v;
+        if (clamp) ground_vertex(p, k);
+        commit_vertex(p, x, v, k);
+        v.w = 0.0f;
+        if (last) {
+          __stcg(P.pos + s, p);
+        } else {
+          p = predict_vertex(x, v, p.w, k);
+          sv[i] = p;
+        }
+        __stcg(P.prev + s, x);
+        __stcg(P.vel + s, v);
+      }
+      __syncthreads();
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, smem + h.offEdgeLam, c.edgeLamBytes);
+      if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, smem + h.offTetLam, c.tetLamBytes);
+      bulk_commit();
+      bulk_wait_read();   // the buffer is overwritten by the next body
+    }
+    __syncthreads();
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
+template <class T>
+cudaError_t upload_vec(T** dst, const std::vector<T>& src, uint64_t& bytes) {
+  cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * src.size() + 256);
+  if (e != cudaSuccess) return e;
+  bytes += sizeof(T) * src.size();
+  if (!src.empty()) e = cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice);
+  return e;
+}
+
+}  // namespace
+
+struct pbd_batch {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  pbd_params params{};
+  uint32_t nBodies = 0;
+  uint64_t Vtot = 0, Etot = 0, Ttot = 0;
+  DeviceArrays d;                     // pos/prev/vel/packed/consts over the concatenated vertices
+  unsigned char* blob = nullptr;
+  BodyDesc* bodies = nullptr;
+  uint32_t recStride = 128, grid = 1, maxVerts = 0;
+  size_t smemBytes = 0;
+  uint32_t edgeColorsMax = 0, tetColorsMax = 0;
+  std::vector<uint32_t> edgeOrder, tetOrder;   // per body, body-local constraint indices, concatenated
+  uint64_t bytes = 0;
+  double planMs = 0.0, uploadMs = 0.0;
+  bool pending = false;
+
+  ~pbd_batch() {
+    cudaFree(d.pos); cudaFree(d.prev); cudaFree(d.vel); cudaFree(d.edgeLam); cudaFree(d.tetLam);
+    cudaFree(d.packed); cudaFree(d.consts); cudaFree(blob); cudaFree(bodies);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int bfail(int code, const std::string& msg, int* status = nullptr) {
+  set_last_error(msg);
+  if (status) *status = code;
+  return code;
+}
+
+#define BCU(call)                                                                             \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) return bfail(PBD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct Coloured {
+  std::vector<uint32_t> eOrder, eCounts, tOrder, tCounts;
+};
+
+}  // namespace
+
 extern "C" {
-pbd_batch* pbd_batch_create(const pbd_params*, uint32_t, const uint64_t*, const uint64_t*, const uint64_t*, const float*,
-                            const uint32_t*, const uint32_t*, int, const pbd_options*, int* status) {
-  if (status) *status = PBD_ERR_UNSUPPORTED;
-  return nullptr;
+
+pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const uint64_t* vOff, const uint64_t* eOff,
+                            const uint64_t* tOff, const float* x0, const uint32_t* edgeIds, const uint32_t* tetIds,
+                            int device, const pbd_options* opts, int* status) {
+  (void)opts;
+  if (status) *status = PBD_OK;
+  if (!params || !vOff || !eOff || !tOff) { bfail(PBD_ERR_INVALID, "null argument", status); return nullptr; }
+  const uint64_t Vtot = vOff[nBodies], Etot = eOff[nBodies], Ttot = tOff[nBodies];
+  if (Vtot > 0xfffffff0ull || Etot > 0xfffffff0ull || Ttot > 0xfffffff0ull) { bfail(PBD_ERR_INVALID, "batch too large", status); return nullptr; }
+  if ((Vtot && !x0) || (Etot && !edgeIds) || (Ttot && !tetIds)) { bfail(PBD_ERR_INVALID, "null array", status); return nullptr; }
+  for (uint32_t b = 0; b < nBodies; ++b) {
+    if (vOff[b + 1] < vOff[b] || eOff[b + 1] < eOff[b] || tOff[b + 1] < tOff[b]) { bfail(PBD_ERR_INVALID, "offsets must be non-decreasing", status); return nullptr; }
+    const uint64_t Vb = vOff[b + 1] - vOff[b];
+    if (Vb > 65535) { bfail(PBD_ERR_UNSUPPORTED, "a batch body has more than 65535 vertices: use pbd_create for it", status); return nullptr; }
+    for (uint64_t i = 2 * eOff[b]; i < 2 * eOff[b + 1]; ++i)
+      if (edgeIds[i] >= Vb) { bfail(PBD_ERR_INDEX, "edge index out of range in body " + std::to_string(b), status); return nullptr; }
+    for (uint64_t i = 4 * tOff[b]; i < 4 * tOff[b + 1]; ++i)
+      if (tetIds[i] >= Vb) { bfail(PBD_ERR_INDEX, "tet index out of range in body " + std::to_string(b), status); return nullptr; }
+  }
+  int nDev = 0;
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
+    cudaGetLastError();
+    bfail(PBD_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)", status);
+    return nullptr;
+  }
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= nDev) { bfail(PBD_ERR_INVALID, "device ordinal out of range", status); return nullptr; }
+  cudaError_t ce;
+  auto cbail = [&](cudaError_t e, const char* what) {
+    bfail(e == cudaErrorMemoryAllocation ? PBD_ERR_OOM : PBD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e), status);
+    return nullptr;
+  };
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return cbail(ce, "cudaSetDevice");
+  cudaDeviceProp prop{};
+  if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cbail(ce, "cudaGetDeviceProperties");
+  const size_t smemLimit = prop.sharedMemPerBlockOptin > 1024 ? prop.sharedMemPerBlockOptin - 1024 : 0;
+
+  std::unique_ptr<pbd_batch> B(new pbd_batch());
+  B->device = device;
+  B->params = *params;
+  B->nBodies = nBodies;
+  B->Vtot = Vtot; B->Etot = Etot; B->Ttot = Ttot;
+
+  // ---- host: per-body derived state (reference init helpers, caller's order) + colouring
+  const double tPlan = wall_ms();
+  std::vector<float4> pos(Vtot), prev(Vtot);
+  std::vector<unsigned char> blob;
+  std::vector<BodyDesc> descs(nBodies);
+  B->edgeOrder.resize(Etot);
+  B->tetOrder.resize(Ttot);
+  std::map<std::string, std::shared_ptr<Coloured>> cache;   // bodies that share a topology share a colouring
+  uint32_t eDev = 0, tDev = 0, recMax = 64;
+  for (uint32_t b = 0; b < nBodies; ++b) {
+    const uint32_t Vb = (uint32_t)(vOff[b + 1] - vOff[b]), Eb = (uint32_t)(eOff[b + 1] - eOff[b]), Tb = (uint32_t)(tOff[b + 1] - tOff[b]);
+    MeshView m{Vb, Eb, Tb, x0 + 3 * vOff[b], edgeIds + 2 * eOff[b], tetIds + 4 * tOff[b]};
+    std::vector<float> w, eRest, tRest;
+    host_inverse_mass(m, nullptr, 0, w);
+    host_rest_state(m, eRest, tRest);
+    for (uint32_t v = 0; v < Vb; ++v) {
+      const float* q = m.x0 + 3 * (size_t)v;
+      pos[vOff[b] + v] = make_float4(q[0], q[1], q[2], w[v]);
+      prev[vOff[b] + v] = make_float4(q[0], q[1], q[2], 0.0f);
+    }
+    std::string key(reinterpret_cast<const char*>(&Vb), 4);
+    key.append(reinterpret_cast<const char*>(m.edges), sizeof(uint32_t) * 2 * (size_t)Eb);
+    key.append(reinterpret_cast<const char*>(m.tets), sizeof(uint32_t) * 4 * (size_t)Tb);
+    std::shared_ptr<Coloured>& col = cache[key];
+    if (!col) {
+      col = std::make_shared<Coloured>();
+      colour_and_order(m.edges, Eb, 2, Vb, col->eOrder, col->eCounts);
+      colour_and_order(m.tets, Tb, 4, Vb, col->tOrder, col->tCounts);
+    }
+    std::copy(col->eOrder.begin(), col->eOrder.end(), B->edgeOrder.begin() + eOff[b]);
+    std::copy(col->tOrder.begin(), col->tOrder.end(), B->tetOrder.begin() + tOff[b]);
+    const uint32_t nEG = (uint32_t)col->eCounts.size(), nTG = (uint32_t)col->tCounts.size();
+    B->edgeColorsMax = std::max(B->edgeColorsMax, nEG);
+    B->tetColorsMax = std::max(B->tetColorsMax, nTG);
+    B->maxVerts = std::max(B->maxVerts, Vb);
+
+    TileHdr h{};
+    h.vertCount = Vb; h.contiguous = 1; h.vertBegin = (uint32_t)vOff[b];
+    h.nEdgeGroups = nEG; h.nTetGroups = nTG; h.nEdges = Eb; h.nTets = Tb;
+    uint32_t off = 64;
+    h.offVertIdx = off;
+    h.offEdgeGroups = off; off += 8u * (pad4(nEG * 2) / 2);
+    h.offTetGroups = off; off += 8u * (pad4(nTG * 2) / 2);
+    h.offEdgeIdx = off; off += 4u * pad4(Eb);
+    h.offEdgeRest = off; off += 4u * pad4(Eb);
+    h.offTetIdx = off; off += 8u * (pad4(Tb * 2) / 2);
+    h.offTetRest = off; off += 4u * pad4(Tb);
+    const uint32_t staticBytes = off;
+    h.offEdgeLam = off; off += 4u * pad4(Eb);
+    h.offTetLam = off; off += 4u * pad4(Tb);
+    recMax = std::max(recMax, off);
+    if ((size_t)((off + 127u) & ~127u) + 16ull * Vb > smemLimit) {
+      bfail(PBD_ERR_UNSUPPORTED, "body " + std::to_string(b) + " does not fit one SM's shared memory: use pbd_create for it", status);
+      return nullptr;
+    }
+    const size_t base = blob.size();
+    blob.resize(base + staticBytes, 0);
+    unsigned char* p = blob.data() + base;
+    memcpy(p, &h, sizeof(h));
+    uint32_t* eg = reinterpret_cast<uint32_t*>(p + h.offEdgeGroups);
+    for (uint32_t g = 0, at = 0; g < nEG; ++g) { eg[2 * g] = at; eg[2 * g + 1] = col->eCounts[g]; at += col->eCounts[g]; }
+    uint32_t* tg = reinterpret_cast<uint32_t*>(p + h.offTetGroups);
+    for (uint32_t g = 0, at = 0; g < nTG; ++g) { tg[2 * g] = at; tg[2 * g + 1] = col->tCounts[g]; at += col->tCounts[g]; }
+    uint32_t* ei = reinterpret_cast<uint32_t*>(p + h.offEdgeIdx);
+    float* er = reinterpret_cast<float*>(p + h.offEdgeRest);
+    for (uint32_t q = 0; q < Eb; ++q) {
+      const uint32_t e = col->eOrder[q];
+      ei[q] = m.edges[2 * (size_t)e] | (m.edges[2 * (size_t)e + 1] << 16);
+      er[q] = eRest[e];
+    }
+    uint32_t* ti = reinterpret_cast<uint32_t*>(p + h.offTetIdx);
+    float* tr = reinterpret_cast<float*>(p + h.offTetRest);
+    for (uint32_t q = 0; q < Tb; ++q) {
+      const uint32_t* id = m.tets + 4 * (size_t)col->tOrder[q];
+      ti[2 * q] = id[0] | (id[1] << 16);
+      ti[2 * q + 1] = id[2] | (id[3] << 16);
+      tr[q] = tRest[col->tOrder[q]];
+    }
+    BodyDesc& c = descs[b];
+    c.blobOff = base; c.staticBytes = staticBytes;
+    c.edgeDevBegin = eDev; c.edgeLamBytes = 4u * pad4(Eb); eDev += pad4(Eb);
+    c.tetDevBegin = tDev; c.tetLamBytes = 4u * pad4(Tb); tDev += pad4(Tb);
+    c.pad = 0;
+  }
+  B->planMs = wall_ms() - tPlan;
+  B->recStride = (recMax + 127u) & ~127u;
+  B->smemBytes = (size_t)B->recStride + 16ull * std::max(B->maxVerts, 1u);
+
+  // ---- device
+  const double tUp = wall_ms();
+  DeviceArrays& d = B->d;
+  d.V = (uint32_t)Vtot; d.E = (uint32_t)Etot; d.T = (uint32_t)Ttot;
+  if ((ce = cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking)) != cudaSuccess) return cbail(ce, "cudaStreamCreate");
+  if ((ce = cudaEventCreate(&B->ev0)) != cudaSuccess || (ce = cudaEventCreate(&B->ev1)) != cudaSuccess) return cbail(ce, "cudaEventCreate");
+  if ((ce = upload_vec(&d.pos, pos, B->bytes)) != cudaSuccess) return cbail(ce, "upload pos");
+  if ((ce = upload_vec(&d.prev, prev, B->bytes)) != cudaSuccess) return cbail(ce, "upload prev");
+  if ((ce = cudaMalloc((void**)&d.vel, sizeof(float4) * (Vtot + 1))) != cudaSuccess) return cbail(ce, "cudaMalloc vel");
+  if ((ce = cudaMemset(d.vel, 0, sizeof(float4) * (Vtot + 1))) != cudaSuccess) return cbail(ce, "memset vel");
+  if ((ce = cudaMalloc((void**)&d.edgeLam, sizeof(float) * ((size_t)eDev + 4))) != cudaSuccess) return cbail(ce, "cudaMalloc edgeLam");
+  if ((ce = cudaMalloc((void**)&d.tetLam, sizeof(float) * ((size_t)tDev + 4))) != cudaSuccess) return cbail(ce, "cudaMalloc tetLam");
+  if ((ce = cudaMemset(d.edgeLam, 0, sizeof(float) * ((size_t)eDev + 4))) != cudaSuccess) return cbail(ce, "memset edgeLam");
+  if ((ce = cudaMemset(d.tetLam, 0, sizeof(float) * ((size_t)tDev + 4))) != cudaSuccess) return cbail(ce, "memset tetLam");
+  if ((ce = cudaMalloc((void**)&d.packed, sizeof(float) * (3 * Vtot + 1))) != cudaSuccess) return cbail(ce, "cudaMalloc packed");
+  if ((ce = cudaMalloc((void**)&d.consts, sizeof(StepConsts))) != cudaSuccess) return cbail(ce, "cudaMalloc consts");
+  B->bytes += sizeof(float4) * Vtot + sizeof(float) * ((size_t)eDev + tDev + 3 * Vtot);
+  if ((ce = upload_vec(&B->blob, blob, B->bytes)) != cudaSuccess) return cbail(ce, "upload blob");
+  if ((ce = upload_vec(&B->bodies, descs, B->bytes)) != cudaSuccess) return cbail(ce, "upload bodies");
+  if ((ce = cudaFuncSetAttribute(batch_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smemBytes)) != cudaSuccess) return cbail(ce, "cudaFuncSetAttribute");
+  int perSM = 0;
+  if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, batch_frame_kernel, 512, B->smemBytes)) != cudaSuccess) return cbail(ce, "occupancy");
+  if (perSM < 1) { bfail(PBD_ERR_UNSUPPORTED, "batch kernel does not fit on an SM", status); return nullptr; }
+  B->grid = std::max(1u, std::min(nBodies, (uint32_t)(perSM * prop.multiProcessorCount)));
+  if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return cbail(ce, "cudaDeviceSynchronize");
+  B->uploadMs = wall_ms() - tUp;
+  return B.release();
 }
-int pbd_batch_step(pbd_batch*, float, pbd_step_stats*) { return PBD_ERR_UNSUPPORTED; }
-int pbd_batch_step_async(pbd_batch*, float, uint32_t) { return PBD_ERR_UNSUPPORTED; }
-int pbd_batch_sync(pbd_batch*, double*) { return PBD_ERR_UNSUPPORTED; }
-int pbd_batch_read_positions(pbd_batch*, float*, double*) { return PBD_ERR_UNSUPPORTED; }
-int pbd_batch_get_info(const pbd_batch*, pbd_info*) { return PBD_ERR_UNSUPPORTED; }
-void pbd_batch_destroy(pbd_batch*) {}
+
+int pbd_batch_step_async(pbd_batch* b, float dt, uint32_t frames) {
+  if (!b) return bfail(PBD_ERR_INVALID, "batch is null");
+  BCU(cudaSetDevice(b->device));
+  const StepConsts k = make_consts(b->params, dt);
+  BCU(cudaMemcpyAsync(b->d.consts, &k, sizeof(k), cudaMemcpyHostToDevice, b->stream));
+  BatchParams P{};
+  P.pos = b->d.pos; P.prev = b->d.prev; P.vel = b->d.vel; P.blob = b->blob; P.bodies = b->bodies;
+  P.edgeLam = b->d.edgeLam; P.tetLam = b->d.tetLam; P.consts = b->d.consts;
+  P.nBodies = b->nBodies; P.substeps = b->params.substeps > 1u ? b->params.substeps : 1u; P.iterations = b->params.iterations;
+  P.recStride = b->recStride;
+  BCU(cudaEventRecord(b->ev0, b->stream));
+  for (uint32_t f = 0; f < frames; ++f) {
+    if (b->nBodies) batch_frame_kernel<<<b->grid, 512, b->smemBytes, b->stream>>>(P);
+    BCU(cudaGetLastError());
+  }
+  BCU(cudaEventRecord(b->ev1, b->stream));
+  b->pending = true;
+  return PBD_OK;
 }
+
+int pbd_batch_sync(pbd_batch* b, double* device_ms) {
+  if (!b) return bfail(PBD_ERR_INVALID, "batch is null");
+  BCU(cudaSetDevice(b->device));
+  BCU(cudaStreamSynchronize(b->stream));
+  if (device_ms) {
+    float ms = 0.f;
+    if (b->pending) BCU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    *device_ms = ms;
+  }
+  b->pending = false;
+  return PBD_OK;
+}
+
+int pbd_batch_step(pbd_batch* b, float dt, pbd_step_stats* stats) {
+  const double t0 = wall_ms();
+  int rc = pbd_batch_step_async(b, dt, 1);
+  if (rc != PBD_OK) return rc;
+  double ms = 0.0;
+  rc = pbd_batch_sync(b, &ms);
+  if (rc != PBD_OK) return rc;
+  if (stats) { stats->solveMs += ms; stats->totalMs += wall_ms() - t0; }
+  return PBD_OK;
+}
+
+int pbd_batch_read_positions(pbd_batch* b, float* out, double* packMs) {
+  if (!b || !out) return bfail(PBD_ERR_INVALID, "null argument");
+  const double t0 = wall_ms();
+  BCU(cudaSetDevice(b->device));
+  BCU(launch_pack(b->d, b->stream));
+  if (b->Vtot) BCU(cudaMemcpyAsync(out, b->d.packed, sizeof(float) * 3 * b->Vtot, cudaMemcpyDeviceToHost, b->stream));
+  BCU(cudaStreamSynchronize(b->stream));
+  if (packMs) *packMs += wall_ms() - t0;
+  return PBD_OK;
+}
+
+int pbd_batch_get_schedule_order(const pbd_batch* b, uint32_t* edgeOrder, uint32_t* tetOrder) {
+  if (!b) return bfail(PBD_ERR_INVALID, "batch is null");
+  if (edgeOrder && b->Etot) memcpy(edgeOrder, b->edgeOrder.data(), sizeof(uint32_t) * b->Etot);
+  if (tetOrder && b->Ttot) memcpy(tetOrder, b->tetOrder.data(), sizeof(uint32_t) * b->Ttot);
+  return PBD_OK;
+}
+
+int pbd_batch_get_info(const pbd_batch* b, pbd_info* out) {
+  if (!b || !out) return bfail(PBD_ERR_INVALID, "null argument");
+  memset(out, 0, sizeof(*out));
+  out->V = (uint32_t)b->Vtot; out->E = (uint32_t)b->Etot; out->T = (uint32_t)b->Ttot;
+  out->backend = PBD_BACKEND_TILE;
+  out->edge_colors = b->edgeColorsMax; out->tet_colors = b->tetColorsMax;
+  out->edge_phases = b->Etot ? 1 : 0; out->tet_phases = b->Ttot ? 1 : 0;
+  out->tiles = b->nBodies;
+  out->launches_per_frame = 1;
+  out->grid_blocks = b->grid; out->block_threads = 512;
+  out->partitions = 1; out->lanes_per_tet = 1;
+  out->device_bytes = b->bytes;
+  out->algorithmic_bytes_per_substep = algorithmic_bytes_per_substep((uint32_t)b->Vtot, (uint32_t)b->Etot, (uint32_t)b->Ttot, b->params.iterations);
+  out->plan_ms = b->planMs;
+  out->upload_ms = b->uploadMs;
+  return PBD_OK;
+}
+
+void pbd_batch_destroy(pbd_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  delete b;
+}
+
+}  // extern "C"

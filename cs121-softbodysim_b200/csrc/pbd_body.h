@@ -64,4 +64,7 @@ cudaError_t launch_pack(const DeviceArrays& d, cudaStream_t s);
 
 StepConsts make_consts(const pbd_params& p, float dt);
 
+// message returned by pbd_last_error() on this thread (pbd_capi.cu)
+void set_last_error(const std::string& msg);
+
 }  // namespace pbd

@@ -74,6 +74,10 @@ void free_arrays(DeviceArrays& d) {
 
 }  // namespace
 
+namespace pbd {
+void set_last_error(const std::string& msg) { g_err = msg; }
+}  // namespace pbd
+
 struct pbd_plan {
   Plan plan;
   pbd_options opts;

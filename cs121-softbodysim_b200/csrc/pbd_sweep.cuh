@@ -17,7 +17,7 @@ namespace pbd {
 // own instead of sharing 128 registers with the kernel's schedule-walking state (which spilled
 // inside the colour loops).  One call per tile visit is noise next to a sweep.
 #ifndef PBD_SWEEP_INLINE
-#define PBD_SWEEP_INLINE __device__ __noinline__
+#define PBD_SWEEP_INLINE static __device__ __noinline__
 #endif
 
 // first 64 bytes of a tile's record block (shared memory); offsets in bytes from the block start

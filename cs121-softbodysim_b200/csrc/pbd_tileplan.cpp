@@ -607,6 +607,28 @@ void build_residual_phases(const CSet sets[2], int ty, std::vector<uint32_t> res
 
 }  // namespace
 
+void colour_and_order(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nVerts, std::vector<uint32_t>& order,
+                      std::vector<uint32_t>& counts) {
+  order.clear();
+  counts.clear();
+  if (n == 0) return;
+  const CSet cs{ids, n, arity};
+  std::vector<uint32_t> localOf(nVerts), scratch;
+  std::iota(localOf.begin(), localOf.end(), 0u);
+  TypeList L;
+  L.cons.resize(n);
+  std::iota(L.cons.begin(), L.cons.end(), 0u);
+  colour_list(cs, L, nVerts, localOf, scratch);
+  for (size_t i = 0; i < L.cons.size();) {
+    size_t j = i;
+    while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
+    bank_order(cs, localOf, &L.cons[i], (uint32_t)(j - i));
+    counts.push_back((uint32_t)(j - i));
+    i = j;
+  }
+  order = L.cons;
+}
+
 bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, uint32_t smemBytes, Plan& plan,
                      std::string& err) {
   const double t0 = now_ms();

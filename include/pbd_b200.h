@@ -195,7 +195,10 @@ void pbd_plan_destroy(pbd_plan* p);
 /* ---- batch of independent bodies (BASELINE.json config 4) ----------------------------- */
 
 /* Bodies are concatenated: body b owns vertices [vOff[b], vOff[b+1]), edges [eOff[b], eOff[b+1]),
- * tets [tOff[b], tOff[b+1]); edge/tet indices are LOCAL to the body.  All bodies share params. */
+ * tets [tOff[b], tOff[b+1]); edge/tet indices are LOCAL to the body.  All bodies share params.
+ * One kernel per frame, each CTA steps whole bodies out of shared memory (csrc/pbd_batch.cu), so a
+ * body must fit one SM (16 B/vertex + 20 B/edge + 28 B/tet <= ~220 KB, < 65536 vertices);
+ * otherwise PBD_ERR_UNSUPPORTED -- use pbd_create for such a body. */
 pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const uint64_t* vOff,
                             const uint64_t* eOff, const uint64_t* tOff, const float* x0,
                             const uint32_t* edgeIds, const uint32_t* tetIds, int device,
@@ -205,6 +208,9 @@ int pbd_batch_step_async(pbd_batch* b, float dt, uint32_t frames);
 int pbd_batch_sync(pbd_batch* b, double* device_ms);
 int pbd_batch_read_positions(pbd_batch* b, float* out, double* packMs); /* 3*vOff[nBodies] floats */
 int pbd_batch_get_info(const pbd_batch* b, pbd_info* out);
+/* per body: edges colour by colour, then tets colour by colour; entries are BODY-LOCAL constraint
+ * indices, concatenated in body order (eOff / tOff positions).  Either pointer may be NULL. */
+int pbd_batch_get_schedule_order(const pbd_batch* b, uint32_t* edgeOrder, uint32_t* tetOrder);
 void pbd_batch_destroy(pbd_batch* b);
 
 #ifdef __cplusplus

@@ -314,3 +314,62 @@ def test_p2_p3_interleaved_order_tolerance_and_residuals(capi, po, meshgen, gold
             b.sync()
             rel = np.sqrt(np.mean(np.sum((b.read_positions().astype(np.float64) - g["pos_10"]) ** 2, 1))) / diag
             assert rel <= 1e-4, f"{mesh}: rel RMS {rel:.3e}"
+
+
+def test_batch_bodies_bit_exact_vs_reference_per_body(capi, po, meshgen, golden):
+    """pbd_batch_*: independent bodies of different shapes in one batch.  Every body must match the
+    reference run on that body alone with its constraints permuted into the disclosed per-body
+    order -- positions BIT-EXACT after 1, 10 and 40 frames -- and bodies must not influence each other."""
+    rots = [meshgen.rotation_zx(20.0, 10.0), meshgen.rotation_zx(-35.0, 50.0), meshgen.rotation_zx(80.0, 5.0)]
+    bodies = []
+    for n, r in ((4, rots[0]), (5, rots[1]), (4, rots[2]), (6, rots[0])):
+        x0, tets, edges = meshgen.kuhn_grid(n, rot=r)
+        bodies.append((x0, edges, tets))
+    m = golden("mesh_icosphere.npz")
+    bodies.append((meshgen.place_body(m["vertices"], lowest_y=0.5), m["edges"], m["tets"]))
+    x0, tets, edges = meshgen.kuhn_grid(3)
+    bodies.append((x0, np.zeros((0, 2), np.uint32), tets))            # tets only
+    bodies.append((x0, edges, np.zeros((0, 4), np.uint32)))            # edges only (all w = 0 -> static)
+    prm = dict(substeps=5)
+    batch = capi.Batch(capi.SolverParams.default(**prm), bodies, device=0)
+    oracles = []
+    for b, (x, e, t) in enumerate(bodies):
+        ora = po.Oracle(po.Params.default(**prm), x, e, t, kind=_oracle_kind(po))
+        ora.permute_constraints(*batch.schedule_order(b))
+        oracles.append(ora)
+    done = 0
+    for fr in (1, 10, 40):
+        batch.step_async(1 / 60, fr - done)
+        batch.sync()
+        pos = batch.read_positions()
+        for b, ora in enumerate(oracles):
+            ora.step(1 / 60, fr - done)
+            assert np.array_equal(batch.body_positions(b, pos), ora.positions()), f"body {b} frame {fr}"
+        done = fr
+    info = batch.info()
+    assert info["tiles"] == len(bodies) and info["launches_per_frame"] == 1
+    batch.close()
+
+
+def test_batch_many_identical_bodies_and_limits(capi, po, meshgen):
+    """More bodies than SMs (every CTA steps several), identical topology (shared colouring), and
+    the documented limit: a body that does not fit one SM is refused, not mis-stepped."""
+    x0, tets, edges = meshgen.kuhn_grid(4)
+    n = 333
+    bodies = [(x0 + np.float32(0.01 * (b % 7)) * np.array([0, 1, 0], np.float32), edges, tets) for b in range(n)]
+    with capi.Batch(capi.SolverParams.default(substeps=3), bodies, device=0) as batch:
+        batch.step_async(1 / 60, 12)
+        batch.sync()
+        pos = batch.read_positions()
+        for b in (0, 1, 147, 148, 332):
+            ora = po.Oracle(po.Params.default(substeps=3), bodies[b][0], edges, tets, kind="port")
+            ora.permute_constraints(*batch.schedule_order(b))
+            ora.step(1 / 60, 12)
+            assert np.array_equal(batch.body_positions(b, pos), ora.positions()), f"body {b}"
+    xb, tb, eb = meshgen.kuhn_grid(14)                                  # 16k tets: > 227 KB of records
+    with pytest.raises(capi.PBDError) as e:
+        capi.Batch(capi.SolverParams.default(), [(xb, eb, tb)], device=0)
+    assert e.value.code == capi.PBD_ERR_UNSUPPORTED
+    with capi.Batch(capi.SolverParams.default(), [], device=0) as empty:
+        empty.step(1 / 60)
+        assert empty.read_positions().shape == (0, 3)
