@@ -314,6 +314,7 @@ def main():
     ap.add_argument("--tile-vertices", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="tile backend: lanes per tet (0 = auto, 1, 2, 4)")
     ap.add_argument("--partitions", type=int, default=0, help="tile backend: shifted partitions (0 = auto)")
+    ap.add_argument("--tiles-per-sm", type=int, default=0, help="tile backend: resident tiles (CTAs) per SM (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
     args = ap.parse_args()
@@ -354,7 +355,7 @@ def main():
     opt = capi.Options(backend={"auto": 0, "stream": 1, "tile": 2}[args.backend],
                        order_mode=1 if args.order == "interleaved" else 0,
                        block_threads=args.block_threads, tile_vertices=args.tile_vertices,
-                       lanes_per_tet=args.lanes, partitions=args.partitions)
+                       lanes_per_tet=args.lanes, partitions=args.partitions, tiles_per_sm=args.tiles_per_sm)
 
     t0 = time.perf_counter()
     stepper = capi.CudaStepper(device=local, options=opt)

@@ -88,7 +88,7 @@ class Options(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("backend", C.c_uint32), ("order_mode", C.c_uint32),
                 ("flags", C.c_uint32), ("tile_vertices", C.c_uint32), ("block_threads", C.c_uint32),
                 ("max_phases", C.c_uint32), ("partitions", C.c_uint32), ("lanes_per_tet", C.c_uint32),
-                ("reserved", C.c_uint32 * 7)]
+                ("tiles_per_sm", C.c_uint32), ("reserved", C.c_uint32 * 6)]
 
     def __init__(self, **kw):
         super().__init__()

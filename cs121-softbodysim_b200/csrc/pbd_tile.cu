@@ -71,6 +71,7 @@ struct TileParams {
   long long* ftrace;            // debug: clock64 stamps of CTA 0, 128 per phase
   uint32_t nTile0, nPhases, substeps, iterations;
   uint32_t recStride;           // bytes of one record buffer
+  uint32_t stagger;             // cycles by which every second CTA of an SM delays its sweeps (tiles_per_sm >= 2)
 };
 
 
@@ -148,6 +149,17 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   __syncthreads();
   const uint32_t nItems = nItemsS;
   const uint32_t totalItems = nItems * P.iterations * P.substeps;
+  // CTAs that share an SM start every phase in lockstep (same barrier, similar tiles) and would
+  // hit the shared-memory pipe and the FP32 pipe at the same moments; delaying every second one by
+  // about half a colour step lets one CTA's gathers overlap the other's arithmetic.
+  __shared__ uint32_t staggerS;
+  if (tid == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    staggerS = (P.stagger && (atomicAdd(P.barrier + 16 + (smid & 255u), 1u) & 1u)) ? P.stagger : 0u;
+  }
+  __syncthreads();
+  const uint32_t stagger = staggerS;
 
   // fetch the record block of this CTA's item `ji` into buffer `b` (thread 0 only)
   auto fetch = [&](uint32_t ji, uint32_t b) {
@@ -228,6 +240,10 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           __syncthreads();
           if (ft) ft[2] = clock64();
           // ---- sweeps
+          if (stagger) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < (long long)stagger) {}
+          }
           sweep_edges(h, recOff, svOff, k.alphaEdge, ft);
           if (ft) ft[3] = clock64();
           sweep_tets<LANES>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr);
@@ -395,7 +411,8 @@ class TileBackend final : public Backend {
     if ((err = up(&copies_, copies)) != cudaSuccess) return err;
     if ((err = up(&phases_, pd)) != cudaSuccess) return err;
     if ((err = up(&tile0Begin_, plan.tile0Begin)) != cudaSuccess) return err;
-    if ((err = cudaMalloc((void**)&barrier_, 256)) != cudaSuccess) return err;
+    if ((err = cudaMalloc((void**)&barrier_, 2048)) != cudaSuccess) return err;
+    stagger_ = getenv("PBD_TILE_STAGGER") ? (uint32_t)atoi(getenv("PBD_TILE_STAGGER")) : 0u;
     if (getenv("PBD_TILE_TRACE")) {
       traceN_ = 2 * (size_t)(nPhases_ + 1) * 4096;
       if ((err = cudaMalloc((void**)&trace_, sizeof(unsigned long long) * traceN_)) != cudaSuccess) return err;
@@ -411,7 +428,8 @@ class TileBackend final : public Backend {
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, device_);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_);
     if (!coop || perSM < 1) return cudaErrorCooperativeLaunchTooLarge;
-    grid_ = std::max(1u, std::min(maxTilesPerPhase_, (uint32_t)nSM));   // one CTA per SM: a tile owns the SM's shared memory
+    const uint32_t wantPerSm = std::max(1u, std::min(opts_.tiles_per_sm ? opts_.tiles_per_sm : 1u, (uint32_t)perSM));
+    grid_ = std::max(1u, std::min(maxTilesPerPhase_, wantPerSm * (uint32_t)nSM));
     // every CTA's per-iteration tile list must fit the kernel's item table
     uint64_t items = 0;
     for (const PhaseDesc& p : pd) items += (p.tileCount + grid_ - 1) / grid_;
@@ -427,7 +445,8 @@ class TileBackend final : public Backend {
     P.trace = trace_; P.ftrace = ftrace_;
     P.nTile0 = nTile0_; P.nPhases = nPhases_; P.substeps = f.substeps; P.iterations = f.iterations;
     P.recStride = recStride_;
-    cudaError_t err = cudaMemsetAsync(barrier_, 0, sizeof(unsigned), s);
+    P.stagger = stagger_;
+    cudaError_t err = cudaMemsetAsync(barrier_, 0, 2048, s);
     if (err != cudaSuccess) return err;
     void* args[] = {&P};
     return cudaLaunchCooperativeKernel(kernel(), dim3(grid_), dim3(block_), args, smemBytes_, s);
@@ -490,6 +509,7 @@ class TileBackend final : public Backend {
   unsigned long long* trace_ = nullptr;
   long long* ftrace_ = nullptr;
   size_t traceN_ = 0;
+  uint32_t stagger_ = 0;
   uint32_t block_ = 512, grid_ = 1, nPhases_ = 0, nTile0_ = 0, maxTilesPerPhase_ = 0, lanes_ = 4, recStride_ = 128;
   size_t smemBytes_ = 0;
   uint64_t bytes_ = 0;

@@ -439,7 +439,7 @@ uint32_t reduce_colours(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_
 
 // colour the constraints of one tile locally and sort them by (colour, id)
 void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vector<uint32_t>& localOf,
-                 std::vector<uint32_t>& scratch) {
+                 std::vector<uint32_t>& scratch, int maxIter = 48, uint32_t goal = 0, uint32_t seed = 0x9e3779b9u) {
   const uint32_t n = (uint32_t)tl.cons.size();
   std::sort(tl.cons.begin(), tl.cons.end());
   // visiting order: most constrained first (largest vertex degree inside the tile), then id
@@ -464,6 +464,49 @@ void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vecto
   std::vector<uint32_t> colV;
   uint32_t nc = greedy_colour(scratch.data(), n, cs.arity, nLocal, colV);
   nc = reduce_colours(scratch.data(), n, cs.arity, nLocal, colV, nc);
+  // Iterated greedy (Culberson): re-run first-fit with the constraints grouped by their current
+  // colour class and the classes permuted -- never needs more colours than before, often fewer --
+  // alternating with the recolouring pass, until the vertex-degree lower bound is met or the
+  // colour count stops improving.  Deterministic (fixed LCG for the shuffles).
+  uint32_t maxDeg = 0;
+  for (uint32_t v = 0; v < nLocal; ++v) maxDeg = std::max(maxDeg, deg[v]);
+  {
+    std::vector<uint32_t> ids2((size_t)n * cs.arity), perm(n), col2, classOrder, classStart;
+    uint32_t lcg = seed, stale = 0;
+    const uint32_t stop = std::max(maxDeg, goal);
+    const uint32_t staleMax = maxIter > 48 ? (uint32_t)maxIter : 12u;
+    for (int iter = 0; iter < maxIter && nc > stop && stale < staleMax; ++iter) {
+      classOrder.resize(nc);
+      std::iota(classOrder.begin(), classOrder.end(), 0u);
+      std::vector<uint32_t> size(nc, 0);
+      for (uint32_t i = 0; i < n; ++i) size[colV[i]]++;
+      switch (iter % 4) {
+        case 0: std::reverse(classOrder.begin(), classOrder.end()); break;
+        case 1: std::stable_sort(classOrder.begin(), classOrder.end(), [&](uint32_t a, uint32_t b) { return size[a] > size[b]; }); break;
+        case 2: std::stable_sort(classOrder.begin(), classOrder.end(), [&](uint32_t a, uint32_t b) { return size[a] < size[b]; }); break;
+        default:
+          for (uint32_t i = nc; i > 1; --i) {
+            lcg = lcg * 1664525u + 1013904223u;
+            std::swap(classOrder[i - 1], classOrder[(lcg >> 8) % i]);
+          }
+      }
+      std::vector<uint32_t> rank(nc);
+      for (uint32_t c = 0; c < nc; ++c) rank[classOrder[c]] = c;
+      std::iota(perm.begin(), perm.end(), 0u);
+      std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return rank[colV[a]] < rank[colV[b]]; });
+      for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t j = 0; j < cs.arity; ++j) ids2[(size_t)i * cs.arity + j] = scratch[(size_t)perm[i] * cs.arity + j];
+      uint32_t nc2 = greedy_colour(ids2.data(), n, cs.arity, nLocal, col2);
+      nc2 = reduce_colours(ids2.data(), n, cs.arity, nLocal, col2, nc2);
+      if (nc2 <= nc) {
+        stale = nc2 < nc ? 0 : stale + 1;
+        nc = nc2;
+        for (uint32_t i = 0; i < n; ++i) colV[perm[i]] = col2[i];
+      } else {
+        ++stale;
+      }
+    }
+  }
   std::vector<uint32_t> col(n);
   for (uint32_t i = 0; i < n; ++i) col[visit[i]] = colV[i];
   tl.nColours = nc;
@@ -640,7 +683,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   plan.orderMode = opts.order_mode;
   if (opts.order_mode != PBD_ORDER_STRICT && opts.order_mode != PBD_ORDER_INTERLEAVED) { err = "unknown order_mode"; return false; }
   const bool fused = opts.order_mode == PBD_ORDER_INTERLEAVED;
-  const uint32_t blockThreads = opts.block_threads ? opts.block_threads : 512;
+  const uint32_t blockThreads = opts.block_threads ? opts.block_threads : (opts.tiles_per_sm >= 2 ? 256u : 512u);
   if (blockThreads % 32 || blockThreads > 1024) { err = "block_threads must be a multiple of 32, <= 1024"; return false; }
   plan.blockThreads = blockThreads;
   if (opts.partitions > kMaxPartitions) { err = "partitions must be <= 8"; return false; }
@@ -679,8 +722,9 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   if (opts.tile_vertices) {
     K1 = std::max(1u, (m.V + opts.tile_vertices - 1) / opts.tile_vertices);
   } else {
-    const uint32_t minTile = 1024;   // below this a tile is all interface: use fewer SMs instead
-    K1 = std::max(1u, std::min(nSMs, m.V / minTile));
+    const uint32_t perSm = opts.tiles_per_sm ? opts.tiles_per_sm : 1u;
+    const uint32_t minTile = 1024 / perSm;   // below this a tile is all interface: use fewer SMs instead
+    K1 = std::max(1u, std::min(nSMs * perSm, m.V / std::max(1u, minTile)));
   }
 
   std::vector<uint32_t> localOf(m.V, NONE), scratch;
@@ -845,6 +889,43 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
         const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
         if (nv > 65535u || tile_bytes(tb) > smemBytes) fits = false;
       }
+    // second colouring pass: a phase lasts as long as its slowest tile, so tiles that ended above
+    // what most tiles of their phase reached get a longer search
+    if (fits)
+      for (uint32_t p = 0; p < K; ++p)
+        for (int ty = 0; ty < 2; ++ty) {
+          std::vector<uint32_t> ncs;
+          for (auto& tb : mainPh[p])
+            if (!tb.ty[ty].cons.empty()) ncs.push_back(tb.ty[ty].nColours);
+          if (ncs.size() < 4) continue;
+          std::sort(ncs.begin(), ncs.end());
+          const uint32_t goal = ncs[ncs.size() / 4];   // lower quartile
+          for (uint32_t t = 0; t < mainPh[p].size(); ++t) {
+            TileBuild& tb = mainPh[p][t];
+            TypeList& L = tb.ty[ty];
+            if (L.cons.empty() || L.nColours <= goal) continue;
+            uint32_t nLocal;
+            if (tb.contiguous) {
+              nLocal = tb.rangeCount;
+              for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.rangeBegin + i] = i;
+            } else {
+              nLocal = (uint32_t)tb.verts.size();
+              for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.verts[i]] = i;
+            }
+            for (uint32_t attempt2 = 0; attempt2 < 4 && L.nColours > goal; ++attempt2) {
+              TypeList trial;
+              trial.cons = L.cons;
+              colour_list(sets[ty], trial, nLocal, localOf, scratch, 160, goal, 0x85ebca6bu * (attempt2 + 1));
+              if (trial.nColours < L.nColours) L = std::move(trial);
+            }
+            for (size_t i = 0; i < L.cons.size();) {
+              size_t j = i;
+              while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
+              bank_order(sets[ty], localOf, &L.cons[i], (uint32_t)(j - i));
+              i = j;
+            }
+          }
+        }
     if (!fits) {
       uint32_t next = K1 + (K1 + 1) / 2;
       if (next > nSMs) next = ((next + nSMs - 1) / nSMs) * nSMs;   // whole waves

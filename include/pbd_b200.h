@@ -101,7 +101,8 @@ typedef struct pbd_options {
   uint32_t max_phases;     /* reserved (ignored)                                                 */
   uint32_t partitions;     /* tile backend: shifted vertex partitions per sweep, 0 = auto (4)    */
   uint32_t lanes_per_tet;  /* tile backend: 1, 2 or 4 lanes cooperate on one tet, 0 = auto (1)   */
-  uint32_t reserved[7];
+  uint32_t tiles_per_sm;   /* tile backend: tiles (CTAs) resident per SM, 0 = auto               */
+  uint32_t reserved[6];
 } pbd_options;
 
 typedef struct pbd_info {
