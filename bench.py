@@ -167,21 +167,26 @@ def run_reference_arm(args):
     sample = 2 if len(tets) > 200000 else w["substeps"]
     r = cpu_reference_run(x0, edges, tets, w, sample, args.steps, args.warmup, threads=ncpu)
     val = r["substeps"] / r["seconds"]
+    unit = UNIT
+    if "bodies" in w:
+        # batch workload: the reference steps ONE body per process; a substep of the whole batch costs
+        # `bodies` body-substeps on one core (bodies are independent, so P cores would give P x this)
+        val, unit = val / w["bodies"], "batch-" + UNIT
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "iterations": w["iterations"], "substeps_per_frame": w["substeps"],
                    "step": f"{sample} substeps of the full mesh (bounded sample of one {w['substeps']}-substep frame)"},
         "tet_constraints_per_s": val * len(tets) * w["iterations"],
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": r["kind"],
+        "cpu_baseline": {"value": val, "unit": unit, "cores": 1, "kind": r["kind"],
                          "threads_offered": ncpu,
                          "sample": f"{args.steps} x {sample} substeps after {args.warmup} warm-up steps; "
                                    f"ParallelStepper(threads={ncpu}) -- its constraint sweeps are serial "
                                    "(Sim.cpp:334-337), so the hot loop uses 1 core"},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -213,7 +218,7 @@ def run_batch(args):
     w = WORKLOADS[args.workload]
     nb, S, I = w["bodies"], w["substeps"], w["iterations"]
     local_xyz, tets, edges = mg.kuhn_grid(w["kuhn"], rot=np.eye(3), lowest_y=None)
-    mine = list(range(rank, nb, world))
+    mine = pkg.shard.body_slice(nb, world, rank)
     bodies = []
     for b in mine:       # deterministic per-body orientation and drop height: trajectories differ
         rot = mg.rotation_zx(7.0 * (b % 47), 3.0 * (b % 29))
@@ -249,10 +254,8 @@ def run_batch(args):
         batch.read_positions(out_ptr=host_pos.data_ptr())
     e2e_s = time.perf_counter() - e0
     clocks = sampler.stop()
-    if dist:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    total_ms, e2e_s = pkg.shard.reduce_max([total_ms, e2e_s], dist, "cuda")
+    assert sum(pkg.shard.gather_counts(len(mine), dist, "cuda")) == nb
     pos = host_pos.numpy().reshape(-1, 3)
     sane = bool(np.isfinite(pos).all() and pos[:, 1].min() >= -1e-5)
     if rank != 0:
@@ -291,14 +294,38 @@ def run_batch(args):
         line["cpu_baseline"] = {"value": per_body / nb, "unit": "batch-" + UNIT, "cores": 1, "kind": r["kind"],
                                 "sample": f"8 frames x {S} substeps of ONE body on 1 of {os.cpu_count()} host cores "
                                           f"({per_body:.1f} body-substeps/s), divided by {nb} bodies"}
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
     batch.close()
     return 0
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there)
+    must not interleave: everything written to fd 1 from here on goes to stderr, and emit() writes the
+    result line to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -461,7 +488,7 @@ def main():
                                 "sample": f"{frames} x {sample} substeps (same mesh, same substep dt) after 1 warm-up; "
                                           f"SerialStepper on 1 of {os.cpu_count()} host cores",
                                 "solve_fraction": r["stats"]["solveMs"] / max(r["stats"]["totalMs"], 1e-9)}
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
     stepper.close()

@@ -10,6 +10,7 @@ Contents (only what the hot path needs):
   capi.py    ctypes binding of that C ABI + the host-side mirror of the reference's
              ``IStepper`` / ``PBDState`` / ``SolverParams`` / ``perf::StepStats``
   meshgen.py deterministic inputs (Kuhn tet grids, edge builder, placement)
+  shard.py   which bodies a rank owns + the max-over-ranks timing reduction (multi-GPU batches)
   build.py   the nvcc command line (``-gencode arch=compute_100a,code=sm_100a -lineinfo``)
 
 There is no CPU fallback: every solver call goes through ``libpbd_b200.so`` and raises if
@@ -22,7 +23,7 @@ __all__ = ["meshgen"]
 
 def __getattr__(name):
     # capi/build are imported lazily so that meshgen stays usable before the library is built
-    if name in ("capi", "build"):
+    if name in ("capi", "build", "shard"):
         import importlib
 
         return importlib.import_module(f"{__name__}.{name}")

@@ -25,12 +25,14 @@
 //   PBD_ORDER_INTERLEAVED  a tile visit projects its edges and then its tets (K phases per
 //                          iteration instead of 2K); checked against the oracle's sequence sweep.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "pbd_plan.h"
 
@@ -875,20 +877,37 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       }
     }
 
-    // ---- finish the main tiles
+    // ---- finish the main tiles (independent of each other: spread over host threads; the result
+    // does not depend on the thread count)
     bool fits = true;
-    for (uint32_t p = 0; p < K && fits; ++p)
-      for (uint32_t t = 0; t < mainPh[p].size() && fits; ++t) {
-        TileBuild& tb = mainPh[p][t];
-        if (p == 0 && t < nTile0) {
-          tb.contiguous = true;
-          tb.rangeBegin = tile0Begin[t];
-          tb.rangeCount = tile0Begin[t + 1] - tile0Begin[t];
+    for (uint32_t t = 0; t < nTile0 && t < mainPh[0].size(); ++t) {
+      TileBuild& tb = mainPh[0][t];
+      tb.contiguous = true;
+      tb.rangeBegin = tile0Begin[t];
+      tb.rangeCount = tile0Begin[t + 1] - tile0Begin[t];
+    }
+    {
+      std::vector<TileBuild*> work;
+      for (uint32_t p = 0; p < K; ++p)
+        for (auto& tb : mainPh[p]) work.push_back(&tb);
+      std::atomic<size_t> next{0};
+      std::atomic<bool> ok{true};
+      auto worker = [&](std::vector<uint32_t>& lo, std::vector<uint32_t>& sc) {
+        for (size_t i; (i = next.fetch_add(1)) < work.size();) {
+          TileBuild& tb = *work[i];
+          finish_tile(sets, tb, lo, sc);
+          const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
+          if (nv > 65535u || tile_bytes(tb) > smemBytes) ok = false;
         }
-        finish_tile(sets, tb, localOf, scratch);
-        const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
-        if (nv > 65535u || tile_bytes(tb) > smemBytes) fits = false;
-      }
+      };
+      const unsigned nThreads = (m.T + m.E < 200000u) ? 1u : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+      std::vector<std::thread> pool;
+      std::vector<std::vector<uint32_t>> los(nThreads > 1 ? nThreads - 1 : 0, std::vector<uint32_t>(m.V, NONE)), scs(los.size());
+      for (size_t i = 0; i < los.size(); ++i) pool.emplace_back(worker, std::ref(los[i]), std::ref(scs[i]));
+      worker(localOf, scratch);
+      for (auto& th : pool) th.join();
+      fits = ok;
+    }
     // second colouring pass: a phase lasts as long as its slowest tile, so tiles that ended above
     // what most tiles of their phase reached get a longer search
     if (fits)
