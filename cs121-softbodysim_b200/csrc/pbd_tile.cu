@@ -192,7 +192,10 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           if (ft) ft[0] = clock64();
           // ---- record block
           if (needWait) {
-            while (!mbar_try_wait(&mbar[buf], (parityBits >> buf) & 1u)) {}
+            // one thread waits on the mbarrier, the block barrier releases the rest (16 warps
+            // polling the same mbarrier serialise: ~45 cycles each)
+            if (tid == 0) while (!mbar_try_wait(&mbar[buf], (parityBits >> buf) & 1u)) {}
+            __syncthreads();
             parityBits ^= 1u << buf;
           }
           const uint32_t recOff = buf * P.recStride;
