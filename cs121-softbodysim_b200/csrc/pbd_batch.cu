@@ -268,9 +268,9 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
     B->maxVerts = std::max(B->maxVerts, Vb);
 
     TileHdr h{};
-    h.vertCount = Vb; h.contiguous = 1; h.vertBegin = (uint32_t)vOff[b];
+    h.vertCount = Vb; h.flags = 1; h.vertBegin = (uint32_t)vOff[b];
     h.nEdgeGroups = nEG; h.nTetGroups = nTG; h.nEdges = Eb; h.nTets = Tb;
-    uint32_t off = 64;
+    uint32_t off = 64 + 4u * kMaxPreds;
     h.offVertIdx = off;
     h.offEdgeGroups = off; off += 8u * (pad4(nEG * 2) / 2);
     h.offTetGroups = off; off += 8u * (pad4(nTG * 2) / 2);

@@ -115,13 +115,15 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
 
 // Shared-memory record block of one tile (built by pbd_tile.cu, sized here so the planner can keep
 // every tile within the SM's capacity).  Sections, each padded to 16 bytes:
-//   header 64 B | gathered vertex slots u32[nVertGather] | edge groups uint2[] | tet groups uint2[]
+//   header 64 B | predecessor tiles u32[kMaxPreds] | gathered vertex slots u32[nVertGather]
+//   | edge groups uint2[] | tet groups uint2[]
 //   | edge idx u32[nE] | edge rest f32[nE] | tet idx uint2[nT] | tet rest f32[nT]
 //   | edge lambda f32[nE] | tet lambda f32[nT]            (the last two come from the lambda arrays)
 inline uint32_t pad4(uint32_t n) { return (n + 3u) & ~3u; }
+constexpr uint32_t kMaxPreds = 32;   // tiles of the previous phase a tile can depend on (point-to-point sync)
 inline uint32_t tile_static_bytes(uint32_t nVertGather, uint32_t nEdgeGroups, uint32_t nTetGroups, uint32_t nE,
                                   uint32_t nT) {
-  return 64u + 4u * pad4(nVertGather) + 8u * (pad4(nEdgeGroups * 2) / 2) + 8u * (pad4(nTetGroups * 2) / 2) +
+  return 64u + 4u * kMaxPreds + 4u * pad4(nVertGather) + 8u * (pad4(nEdgeGroups * 2) / 2) + 8u * (pad4(nTetGroups * 2) / 2) +
          8u * pad4(nE) + 8u * (pad4(nT * 2) / 2) + 4u * pad4(nT);
 }
 inline uint32_t tile_record_bytes(uint32_t nVertGather, uint32_t nEdgeGroups, uint32_t nTetGroups, uint32_t nE,

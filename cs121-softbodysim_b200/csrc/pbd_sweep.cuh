@@ -22,7 +22,7 @@ namespace pbd {
 
 // first 64 bytes of a tile's record block (shared memory); offsets in bytes from the block start
 struct TileHdr {
-  uint32_t vertCount, contiguous, vertBegin, nEdgeGroups;
+  uint32_t vertCount, flags, vertBegin, nEdgeGroups;   // flags: bit 0 = contiguous slot range, bits 8..15 = predecessor count
   uint32_t nTetGroups, nEdges, nTets, offVertIdx;
   uint32_t offEdgeGroups, offTetGroups, offEdgeIdx, offEdgeRest;
   uint32_t offTetIdx, offTetRest, offEdgeLam, offTetLam;

@@ -67,6 +67,7 @@ struct TileParams {
   const uint32_t* tile0Begin;   // nTile0 + 1
   const StepConsts* consts;
   unsigned* barrier;
+  unsigned* done;               // per tile: completed visits this frame (point-to-point sync), or null: grid barrier per phase
   unsigned long long* trace;    // debug: [phase][cta][2] globaltimer ns of (start, arrive), substep 0, last iteration
   long long* ftrace;            // debug: clock64 stamps of CTA 0, 128 per phase
   uint32_t nTile0, nPhases, substeps, iterations;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar[2];
   __shared__ TileCopy itemCopy[kMaxItems];   // copy descriptors of this CTA's tiles: no global latency when prefetching
+  __shared__ uint32_t itemTile[kMaxItems];
   __shared__ uint32_t nItemsS;
   const uint32_t svOff = 2u * P.recStride;
   float4* const sv = reinterpret_cast<float4*>(smem + svOff);
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
     for (uint32_t ph = 0; ph < P.nPhases; ++ph) {
       const PhaseDesc pd = P.phases[ph];
       for (uint32_t t = blockIdx.x; t < pd.tileCount; t += gridDim.x)
-        if (n < kMaxItems) itemCopy[n++] = P.copies[pd.tileBegin + t];
+        if (n < kMaxItems) { itemTile[n] = pd.tileBegin + t; itemCopy[n++] = P.copies[pd.tileBegin + t]; }
     }
     nItemsS = n;
     mbar_init(&mbar[0], 1);
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           const uint32_t recOff = buf * P.recStride;
           unsigned char* rec = smem + recOff;
           const TileHdr h = *reinterpret_cast<const TileHdr*>(rec);
+          const bool contiguous = (h.flags & 1u) != 0u;
           if (ft) ft[1] = clock64();
           // ---- prefetch the next tile's block into the other buffer
           const uint32_t jn = (j + 1 == nItems) ? 0u : j + 1;
@@ -210,7 +213,18 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             fetch(jn, buf ^ 1u);
           }
           // ---- vertices L2 -> shared memory (all of a thread's loads are issued before the first use)
-          if (h.contiguous) {
+          // ---- point-to-point sync: wait until the tiles that last wrote my vertices have stored them
+          if (P.done) {
+            const uint32_t np = (h.flags >> 8) & 0xffu;
+            if (tid < np) {
+              const uint32_t e = reinterpret_cast<const uint32_t*>(rec + 64)[tid];
+              const uint32_t need = sub * P.iterations + it + (e >> 31);   // bit 31: written earlier in THIS iteration
+              const unsigned* f = P.done + (e & 0x7fffffffu);
+              while (ld_acquire(f) < need) {}
+            }
+            __syncthreads();
+          }
+          if (contiguous) {
             for (uint32_t base = 0; base < h.vertCount; base += 3u * nth) {
               VertexIn in[3];
 #pragma unroll
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           sweep_tets<LANES>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr);
           if (ft) ft[4] = clock64();
           // ---- write back
-          if (h.contiguous) {
+          if (contiguous) {
             for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + h.vertBegin + i, sv[i]);
           } else {
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
@@ -266,6 +280,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
             bulk_commit();
             if (nItems == 1) bulk_wait_read();   // the block stays resident and is swept again next iteration
+            if (P.done) st_release(P.done + itemTile[j], sub * P.iterations + it + 1u);   // my vertices are in L2
           }
           if (nItems == 1) {
             __syncthreads();
@@ -278,11 +293,12 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           if (ft) { ft[5] = clock64(); ft[6] = h.nEdgeGroups; ft[7] = h.nTetGroups; ft[8] = h.vertCount; ft[9] = h.nEdges; ft[10] = h.nTets; }
         }
         if (tr) P.trace[2 * ((size_t)ph * gridDim.x + blockIdx.x) + 1] = globaltimer_ns();
-        grid_barrier(P.barrier, epoch);
+        if (!P.done) grid_barrier(P.barrier, epoch);
       }
     }
   }
   if (tid == 0) bulk_wait_all();
+  if (P.done) grid_barrier(P.barrier, epoch);   // the final commit reads every vertex's last value
   vertex_pass(P, k, LOAD_PLAIN, clamp, true);
 }
 
@@ -290,6 +306,7 @@ class TileBackend final : public Backend {
  public:
   TileBackend(const pbd_options& o, int device) : opts_(o), device_(device) {}
   ~TileBackend() override {
+    cudaFree(done_);
     cudaFree(blob_); cudaFree(copies_); cudaFree(phases_); cudaFree(tile0Begin_); cudaFree(barrier_);
     cudaFree(trace_); cudaFree(ftrace_);
   }
@@ -308,6 +325,33 @@ class TileBackend final : public Backend {
     if (plan.edgeDevCount && (err = cudaMemcpy(eRest.data(), d.edgeRest, sizeof(float) * plan.edgeDevCount, cudaMemcpyDeviceToHost)) != cudaSuccess) return err;
     if (plan.tetDevCount && (err = cudaMemcpy(tRest.data(), d.tetRest, sizeof(float) * plan.tetDevCount, cudaMemcpyDeviceToHost)) != cudaSuccess) return err;
 
+    // ---- point-to-point dependencies: for every tile, the tiles that last wrote one of its vertices
+    // (bit 31 set: earlier in the same iteration; clear: in the previous iteration)
+    std::vector<std::vector<uint32_t>> preds(plan.tiles.size());
+    bool flagsOk = !getenv("PBD_TILE_GRIDSYNC");
+    {
+      std::vector<uint32_t> lastTile(plan.V, 0xffffffffu), lastPhase(plan.V, 0);
+      auto for_verts = [&](const Tile& t, auto&& fn) {
+        for (uint32_t i = 0; i < t.vertCount; ++i) fn(t.contiguous ? t.vertBegin + i : plan.tileVerts[t.vertBegin + i]);
+      };
+      for (int pass = 0; pass < 2; ++pass)
+        for (size_t ph = 0; ph < plan.phases.size(); ++ph)
+          for (uint32_t ti = plan.phases[ph].tileBegin; ti < plan.phases[ph].tileBegin + plan.phases[ph].tileCount; ++ti) {
+            const Tile& t = plan.tiles[ti];
+            if (pass == 1) {
+              std::vector<uint32_t>& pr = preds[ti];
+              for_verts(t, [&](uint32_t s) {
+                if (lastTile[s] != 0xffffffffu && lastTile[s] != ti) pr.push_back(lastTile[s] | (lastPhase[s] < ph ? 0x80000000u : 0u));
+              });
+              std::sort(pr.begin(), pr.end());
+              pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
+              if (pr.size() > kMaxPreds) flagsOk = false;
+            }
+            for_verts(t, [&](uint32_t s) { lastTile[s] = ti; lastPhase[s] = (uint32_t)ph; });
+          }
+    }
+    useFlags_ = flagsOk && plan.tiles.size() < 0x7fffffffull;
+
     // ---- record blocks
     std::vector<TileCopy> copies(plan.tiles.size());
     std::vector<unsigned char> blob;
@@ -316,9 +360,10 @@ class TileBackend final : public Backend {
       const Tile& t = plan.tiles[ti];
       const uint32_t nVG = t.contiguous ? 0u : t.vertCount;
       TileHdr h{};
-      h.vertCount = t.vertCount; h.contiguous = t.contiguous; h.vertBegin = t.contiguous ? t.vertBegin : 0u;
+      const uint32_t nPred = useFlags_ ? (uint32_t)preds[ti].size() : 0u;
+      h.vertCount = t.vertCount; h.flags = (t.contiguous ? 1u : 0u) | (nPred << 8); h.vertBegin = t.contiguous ? t.vertBegin : 0u;
       h.nEdgeGroups = t.edgeGroupCount; h.nTetGroups = t.tetGroupCount; h.nEdges = t.edgeCount; h.nTets = t.tetCount;
-      uint32_t off = 64;
+      uint32_t off = 64 + 4u * kMaxPreds;
       h.offVertIdx = off; off += 4u * pad4(nVG);
       h.offEdgeGroups = off; off += 8u * (pad4(t.edgeGroupCount * 2) / 2);
       h.offTetGroups = off; off += 8u * (pad4(t.tetGroupCount * 2) / 2);
@@ -336,6 +381,7 @@ class TileBackend final : public Backend {
       blob.resize(base + staticBytes, 0);
       unsigned char* b = blob.data() + base;
       memcpy(b, &h, sizeof(h));
+      if (nPred) memcpy(b + 64, preds[ti].data(), 4u * nPred);
       if (nVG) memcpy(b + h.offVertIdx, &plan.tileVerts[t.vertBegin], 4u * nVG);
       uint32_t* eg = reinterpret_cast<uint32_t*>(b + h.offEdgeGroups);
       for (uint32_t g = 0; g < t.edgeGroupCount; ++g) {
@@ -415,6 +461,8 @@ class TileBackend final : public Backend {
     if ((err = up(&phases_, pd)) != cudaSuccess) return err;
     if ((err = up(&tile0Begin_, plan.tile0Begin)) != cudaSuccess) return err;
     if ((err = cudaMalloc((void**)&barrier_, 2048)) != cudaSuccess) return err;
+    doneBytes_ = sizeof(unsigned) * (plan.tiles.size() + 1);
+    if (useFlags_ && (err = cudaMalloc((void**)&done_, doneBytes_)) != cudaSuccess) return err;
     stagger_ = getenv("PBD_TILE_STAGGER") ? (uint32_t)atoi(getenv("PBD_TILE_STAGGER")) : 0u;
     if (getenv("PBD_TILE_TRACE")) {
       traceN_ = 2 * (size_t)(nPhases_ + 1) * 4096;
@@ -449,7 +497,9 @@ class TileBackend final : public Backend {
     P.nTile0 = nTile0_; P.nPhases = nPhases_; P.substeps = f.substeps; P.iterations = f.iterations;
     P.recStride = recStride_;
     P.stagger = stagger_;
+    P.done = useFlags_ ? done_ : nullptr;
     cudaError_t err = cudaMemsetAsync(barrier_, 0, 2048, s);
+    if (err == cudaSuccess && useFlags_) err = cudaMemsetAsync(done_, 0, doneBytes_, s);
     if (err != cudaSuccess) return err;
     void* args[] = {&P};
     return cudaLaunchCooperativeKernel(kernel(), dim3(grid_), dim3(block_), args, smemBytes_, s);
@@ -513,6 +563,9 @@ class TileBackend final : public Backend {
   long long* ftrace_ = nullptr;
   size_t traceN_ = 0;
   uint32_t stagger_ = 0;
+  unsigned* done_ = nullptr;
+  size_t doneBytes_ = 0;
+  bool useFlags_ = false;
   uint32_t block_ = 512, grid_ = 1, nPhases_ = 0, nTile0_ = 0, maxTilesPerPhase_ = 0, lanes_ = 4, recStride_ = 128;
   size_t smemBytes_ = 0;
   uint64_t bytes_ = 0;
