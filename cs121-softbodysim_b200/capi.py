@@ -28,7 +28,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpbd_b200.so")
+# PBD_B200_LIB: load another build of the same ABI (A/B timing of kernel variants on one box)
+LIB_PATH = os.environ.get("PBD_B200_LIB") or os.path.join(HERE, "libpbd_b200.so")
 
 PBD_OK, PBD_ERR_INVALID, PBD_ERR_INDEX, PBD_ERR_NO_DEVICE, PBD_ERR_CUDA, PBD_ERR_OOM, PBD_ERR_UNSUPPORTED = range(7)
 BACKEND_AUTO, BACKEND_STREAM, BACKEND_TILE = 0, 1, 2
