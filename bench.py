@@ -48,6 +48,11 @@ WORKLOADS = {
     "config1": dict(asset="default", substeps=10, iterations=6,
                     desc="BASELINE configs[0]: default Assets/SoftBody tet mesh (V=8613 E=41488 T=26070), 10 substeps x 6 iterations"),
     "small": dict(kuhn=10, substeps=10, iterations=6, desc="one 6k-tet body (config-4 body), smoke-sized"),
+    "big8m": dict(kuhn=112, substeps=10, iterations=6,
+                  desc="scaling probe: 8.4M-tet Kuhn cube n=112 (V=1442897 E=9947504 T=8429568), 10 substeps x 6 iterations, 1 GPU"),
+    "big32m": dict(kuhn=175, substeps=10, iterations=6,
+                   desc="BASELINE configs[4] mesh on ONE GPU: 32M-tet Kuhn cube n=175 (V=5451776 E=37791775 T=32156250), "
+                        "10 substeps x 6 iterations (no domain decomposition)"),
     "batch4096": dict(kuhn=10, bodies=4096, substeps=10, iterations=6,
                       desc="BASELINE configs[3]: batch of 4096 independent 6,000-tet bodies (Kuhn n=10, V=1331 E=7930 "
                            "T=6000 each, per-body rotation), 10 substeps x 6 iterations; bodies sharded across the GPUs"),
@@ -345,6 +350,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
     args = ap.parse_args()
+    if args.backend == "stream":
+        args.order = "strict"          # the per-colour stream backend only has the reference's edges-then-tets order
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.workload == "batch4096" and args.impl != "reference":

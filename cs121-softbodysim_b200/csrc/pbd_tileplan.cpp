@@ -739,6 +739,13 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     const uint32_t perSm = opts.tiles_per_sm ? opts.tiles_per_sm : 1u;
     const uint32_t minTile = 1024 / perSm;   // below this a tile is all interface: use fewer SMs instead
     K1 = std::max(1u, std::min(nSMs * perSm, m.V / std::max(1u, minTile)));
+    // large bodies: enough tiles (whole waves) that a tile fits in shared memory, estimated from the
+    // bytes a tile visit needs (16 B/vertex + double-buffered records, 12 B/edge and 16 B/tet, of
+    // ~1/4 of its constraints, with 25 % headroom for uneven tiles) instead of finding out by
+    // repeated planning
+    const double need = 16.0 * m.V + 2.0 * (12.0 * m.E + 16.0 * m.T) / 4.0;
+    const uint32_t byBytes = (uint32_t)std::ceil(1.25 * need / (double)smemBytes);
+    if (byBytes > K1) K1 = ((byBytes + nSMs - 1) / nSMs) * nSMs;
   }
 
   std::vector<uint32_t> localOf(m.V, NONE), scratch;
@@ -970,8 +977,10 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       fits = ok;
     }
     // second colouring pass: a phase lasts as long as its slowest tile, so tiles that ended above
-    // what most tiles of their phase reached get a longer search
-    if (fits)
+    // what most tiles of their phase reached get a longer search (again spread over host threads)
+    if (fits) {
+      struct Job { TileBuild* tb; int ty; uint32_t goal; };
+      std::vector<Job> jobs;
       for (uint32_t p = 0; p < K; ++p)
         for (int ty = 0; ty < 2; ++ty) {
           std::vector<uint32_t> ncs;
@@ -980,32 +989,47 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           if (ncs.size() < 4) continue;
           std::sort(ncs.begin(), ncs.end());
           const uint32_t goal = ncs[ncs.size() / 4];   // lower quartile
-          for (uint32_t t = 0; t < mainPh[p].size(); ++t) {
-            TileBuild& tb = mainPh[p][t];
-            TypeList& L = tb.ty[ty];
-            if (L.cons.empty() || L.nColours <= goal) continue;
-            uint32_t nLocal;
-            if (tb.contiguous) {
-              nLocal = tb.rangeCount;
-              for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.rangeBegin + i] = i;
-            } else {
-              nLocal = (uint32_t)tb.verts.size();
-              for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.verts[i]] = i;
-            }
-            for (uint32_t attempt2 = 0; attempt2 < 4 && L.nColours > goal; ++attempt2) {
-              TypeList trial;
-              trial.cons = L.cons;
-              colour_list(sets[ty], trial, nLocal, localOf, scratch, 160, goal, 0x85ebca6bu * (attempt2 + 1));
-              if (trial.nColours < L.nColours) L = std::move(trial);
-            }
-            for (size_t i = 0; i < L.cons.size();) {
-              size_t j = i;
-              while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
-              bank_order(sets[ty], localOf, &L.cons[i], (uint32_t)(j - i));
-              i = j;
-            }
+          for (auto& tb : mainPh[p])
+            if (!tb.ty[ty].cons.empty() && tb.ty[ty].nColours > goal) jobs.push_back({&tb, ty, goal});
+        }
+      std::atomic<size_t> next{0};
+      auto worker = [&](std::vector<uint32_t>& lo, std::vector<uint32_t>& sc) {
+        for (size_t i; (i = next.fetch_add(1)) < jobs.size();) {
+          TileBuild& tb = *jobs[i].tb;
+          const int ty = jobs[i].ty;
+          const uint32_t goal = jobs[i].goal;
+          TypeList& L = tb.ty[ty];
+          uint32_t nLocal;
+          if (tb.contiguous) {
+            nLocal = tb.rangeCount;
+            for (uint32_t q = 0; q < nLocal; ++q) lo[tb.rangeBegin + q] = q;
+          } else {
+            nLocal = (uint32_t)tb.verts.size();
+            for (uint32_t q = 0; q < nLocal; ++q) lo[tb.verts[q]] = q;
+          }
+          for (uint32_t attempt2 = 0; attempt2 < 4 && L.nColours > goal; ++attempt2) {
+            TypeList trial;
+            trial.cons = L.cons;
+            colour_list(sets[ty], trial, nLocal, lo, sc, 160, goal, 0x85ebca6bu * (attempt2 + 1));
+            if (trial.nColours < L.nColours) L = std::move(trial);
+          }
+          for (size_t a2 = 0; a2 < L.cons.size();) {
+            size_t b2 = a2;
+            while (b2 < L.cons.size() && L.colour[b2] == L.colour[a2]) ++b2;
+            bank_order(sets[ty], lo, &L.cons[a2], (uint32_t)(b2 - a2));
+            a2 = b2;
           }
         }
+      };
+      // two jobs may share a tile (its edge list and its tet list): they touch different TypeLists
+      // and write the same values into the thread-private numbering, so they are independent
+      const unsigned nThreads = jobs.size() < 8 ? 1u : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+      std::vector<std::thread> pool;
+      std::vector<std::vector<uint32_t>> los(nThreads > 1 ? nThreads - 1 : 0, std::vector<uint32_t>(m.V, NONE)), scs(los.size());
+      for (size_t i = 0; i < los.size(); ++i) pool.emplace_back(worker, std::ref(los[i]), std::ref(scs[i]));
+      worker(localOf, scratch);
+      for (auto& th : pool) th.join();
+    }
     if (!fits) {
       uint32_t next = K1 + (K1 + 1) / 2;
       if (next > nSMs) next = ((next + nSMs - 1) / nSMs) * nSMs;   // whole waves
