@@ -347,6 +347,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="tile backend: lanes per tet (0 = auto, 1, 2, 4)")
     ap.add_argument("--partitions", type=int, default=0, help="tile backend: shifted partitions (0 = auto)")
     ap.add_argument("--tiles-per-sm", type=int, default=0, help="tile backend: resident tiles (CTAs) per SM (0 = auto)")
+    ap.add_argument("--shard", action="store_true",
+                    help="with --gpus N > 1: ONE body of the workload spread over the N GPUs (tiles of other ranks' "
+                         "vertices are read/written in place over NVLink; strong scaling) instead of one body per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
     args = ap.parse_args()
@@ -392,9 +395,14 @@ def main():
                        lanes_per_tet=args.lanes, partitions=args.partitions, tiles_per_sm=args.tiles_per_sm)
 
     t0 = time.perf_counter()
-    stepper = capi.CudaStepper(device=local, options=opt)
-    state = capi.PBDState(prm, x0, edges, tets)
-    body = stepper._bind(state)                      # MSG_INIT: plan + upload (not in the timed region)
+    sharded = args.shard and world > 1
+    if sharded:
+        sb = capi.ShardedBody(prm, x0, edges, tets, rank, world, dist, device=local, options=opt)
+        body, stepper, state = sb.body, None, None
+    else:
+        stepper = capi.CudaStepper(device=local, options=opt)
+        state = capi.PBDState(prm, x0, edges, tets)
+        body = stepper._bind(state)                  # MSG_INIT: plan + upload (not in the timed region)
     init_ms = (time.perf_counter() - t0) * 1e3
     info = body.info()
 
@@ -432,14 +440,21 @@ def main():
 
     # ---- end-to-end through the stepper API with host buffers (step + pack D2H into pinned memory)
     stats = capi.StepStats()
-    for _ in range(2):
-        stepper.step(state, DT, stats)
+
+    def e2e_step():
+        if sharded:                                  # every rank reads back its own part of the body
+            body.step_async(DT, 1)
+            body.sync()
+        else:
+            stepper.step(state, DT, stats)
         body.read_positions(out_ptr=host_pos.data_ptr())
+
+    for _ in range(2):
+        e2e_step()
     sync_all()
     e0 = time.perf_counter()
     for _ in range(args.steps):
-        stepper.step(state, DT, stats)
-        body.read_positions(out_ptr=host_pos.data_ptr())
+        e2e_step()
     e2e_s = time.perf_counter() - e0
     clocks = sampler.stop()
     if dist:
@@ -454,20 +469,25 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    substeps_total = world * args.steps * S
+    bodies = 1 if sharded else world
+    substeps_total = bodies * args.steps * S
     value = substeps_total / (total_ms * 1e-3)
     bytes_sub = info["algorithmic_bytes_per_substep"]
     frame_ms = total_ms / args.steps
-    achieved = bytes_sub * S / (frame_ms * 1e-3) / 1e9
+    achieved = bodies * bytes_sub * S / (frame_ms * 1e-3) / 1e9
     peak, peak_src = load_peaks()
+    peak *= world
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "V": V, "E": E, "T": T, "substeps_per_frame": S, "iterations": I,
                    "dt": DT, "backend": body.name(), "order_mode": args.order,
                    "lanes_per_tet": info.get("lanes_per_tet"), "partitions": info.get("partitions"),
-                   "parallelism": f"{world} independent bodies, one per GPU, no collective" if world > 1 else "1 GPU",
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   f"ONE body across {world} GPUs: tiles read/write other ranks' vertices in place over NVLink "
+                                   "(peer memory, CUDA IPC), per-tile release/acquire counters at system scope; no NCCL on the data path"
+                                   if sharded else f"{world} independent bodies, one per GPU, no collective"),
                    "l2": "not flushed" if flush is None else "flushed between timed frames (256 MiB memset, untimed)",
                    "working_set_bytes": info["device_bytes"]},
         "tet_constraints_per_s": value * T * I,
@@ -476,7 +496,7 @@ def main():
                      "traffic": ncu_traffic(args.workload, body.name()), "peak_source": peak_src,
                      "kernel": "whole frame = %d launches of %s" % (info["launches_per_frame"], body.name()),
                      "algorithmic_bytes_per_substep": bytes_sub, "frac_of_nominal_8TBs": achieved / 8000.0},
-        "e2e": {"value": world * args.steps * S / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 52,
+        "e2e": {"value": bodies * args.steps * S / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 52,
                 "d2h_bytes_per_step": 12 * V, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "CudaStepper.step(state, dt) + pack_positions -> pinned host buffer (C ABI pbd_step + pbd_read_positions)"},
         "gpu_launches": args.steps * info["launches_per_frame"],
@@ -498,7 +518,8 @@ def main():
     emit(line)
     if dist:
         dist.destroy_process_group()
-    stepper.close()
+    if stepper:
+        stepper.close()
     return 0
 
 

@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "pbd_create", "pbd_step", "pbd_step_async", "pbd_sync", "pbd_read_positions", "pbd_destroy",
     "pbd_backend_name", "pbd_get_info", "pbd_set_params", "pbd_get_schedule_order",
     "pbd_get_schedule_sequence", "pbd_get_array",
+    "pbd_shard_export", "pbd_shard_attach_ipc", "pbd_shard_attach_local", "pbd_shard_owner",
     "pbd_plan_create", "pbd_plan_get_info", "pbd_plan_get_order", "pbd_plan_get_sequence",
     "pbd_plan_get_edge_slots", "pbd_plan_get_tet_slots", "pbd_plan_destroy",
     "pbd_batch_create", "pbd_batch_step", "pbd_batch_step_async", "pbd_batch_sync",
@@ -89,7 +90,8 @@ class Options(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("backend", C.c_uint32), ("order_mode", C.c_uint32),
                 ("flags", C.c_uint32), ("tile_vertices", C.c_uint32), ("block_threads", C.c_uint32),
                 ("max_phases", C.c_uint32), ("partitions", C.c_uint32), ("lanes_per_tet", C.c_uint32),
-                ("tiles_per_sm", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+                ("tiles_per_sm", C.c_uint32), ("shard_world", C.c_uint32), ("shard_rank", C.c_uint32),
+                ("plan_sms", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
     def __init__(self, **kw):
         super().__init__()
@@ -146,6 +148,10 @@ def lib() -> C.CDLL:
     L.pbd_get_schedule_order.argtypes = [vp, vp, vp]
     L.pbd_get_schedule_sequence.argtypes = [vp, vp]
     L.pbd_get_array.argtypes = [vp, C.c_int, vp]
+    L.pbd_shard_export.argtypes = [vp, vp]
+    L.pbd_shard_attach_ipc.argtypes = [vp, vp]
+    L.pbd_shard_attach_local.argtypes = [vp, u32]
+    L.pbd_shard_owner.argtypes = [vp, vp]
     L.pbd_plan_create.restype = vp
     L.pbd_plan_create.argtypes = [u32, u32, u32, vp, vp, vp, C.POINTER(Options), C.POINTER(C.c_int)]
     L.pbd_plan_get_info.argtypes = [vp, C.POINTER(Info)]
@@ -204,7 +210,10 @@ class Body:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().pbd_destroy(self.h)
+            try:
+                lib().pbd_destroy(self.h)
+            except TypeError:      # interpreter shutdown: module globals are already gone
+                pass
             self.h = None
 
     __del__ = close
@@ -268,6 +277,88 @@ class Body:
         out = np.zeros(shape, dtype=np.float32)
         _check(lib().pbd_get_array(self.h, what, out.ctypes.data_as(C.c_void_p)))
         return out
+
+
+SHARD_EXPORT_BYTES = 128
+
+
+class ShardedBody:
+    """ONE body spread over several GPUs of a node (BASELINE config 5), this process holding rank
+    ``rank`` of ``world`` (one process per GPU; ``dist`` = an initialised torch.distributed used only
+    to exchange the CUDA IPC handles and to assemble read-back positions).  Every rank passes the
+    same mesh.  Results are bit-identical to ``Body`` run with ``Options(plan_sms=...)`` equal to the
+    SM count the sharded plan was made for."""
+
+    def __init__(self, params: SolverParams, x0, edges, tets, rank: int, world: int, dist, device: int = -1,
+                 options: Options | None = None, pinned=None):
+        import torch
+        opt = Options() if options is None else options
+        opt.backend, opt.shard_world, opt.shard_rank = BACKEND_TILE, world, rank
+        self.rank, self.world, self.dist = rank, world, dist
+        self.body = Body(params, x0, edges, tets, pinned=pinned, device=device, options=opt)
+        L = lib()
+        mine = np.zeros(SHARD_EXPORT_BYTES, dtype=np.uint8)
+        _check(L.pbd_shard_export(self.body.h, _ptr(mine)))
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(mine).to(dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        allh = np.concatenate([o.cpu().numpy() for o in out]).astype(np.uint8)
+        _check(L.pbd_shard_attach_ipc(self.body.h, _ptr(allh)))
+        self.owner = np.zeros(self.body.V, dtype=np.uint8)
+        _check(L.pbd_shard_owner(self.body.h, _ptr(self.owner)))
+        dist.barrier()                       # every rank has mapped every peer before anyone steps
+        self._dev = dev
+
+    def step_async(self, dt: float, frames: int = 1):
+        self.body.step_async(dt, frames)
+
+    def sync(self) -> float:
+        return self.body.sync()
+
+    def step(self, dt: float):
+        self.body.step_async(dt, 1)
+        return self.body.sync()
+
+    def read_positions_local(self) -> np.ndarray:
+        """[V,3]; rows of vertices owned by another rank are stale."""
+        return self.body.read_positions()
+
+    def read_positions(self) -> np.ndarray:
+        """All V committed positions on every rank (owned rows exchanged with an all-reduce)."""
+        import torch
+        pos = self.body.read_positions()
+        pos[self.owner != self.rank] = 0.0
+        t = torch.from_numpy(pos).to(self._dev)
+        self.dist.all_reduce(t)              # every row has exactly one non-zero contributor
+        return t.cpu().numpy()
+
+    def info(self) -> dict:
+        return self.body.info()
+
+    def close(self):
+        self.body.close()
+
+
+def sharded_bodies_one_process(params: SolverParams, x0, edges, tets, devices, options: Options | None = None):
+    """Single-process variant: one ``Body`` per device in ``devices`` (rank = position), attached
+    with peer access.  Step with ``step_async`` on ALL of them before any ``sync``."""
+    bodies = []
+    for r, dev in enumerate(devices):
+        opt = Options() if options is None else options
+        o2 = Options()
+        C.memmove(C.byref(o2), C.byref(opt), C.sizeof(opt))
+        o2.backend, o2.shard_world, o2.shard_rank = BACKEND_TILE, len(devices), r
+        bodies.append(Body(params, x0, edges, tets, device=dev, options=o2))
+    arr = (C.c_void_p * len(bodies))(*[b.h for b in bodies])
+    _check(lib().pbd_shard_attach_local(arr, len(bodies)))
+    return bodies
+
+
+def shard_owner(body: Body) -> np.ndarray:
+    owner = np.zeros(body.V, dtype=np.uint8)
+    _check(lib().pbd_shard_owner(body.h, _ptr(owner)))
+    return owner
 
 
 class Batch:

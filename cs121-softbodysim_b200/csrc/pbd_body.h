@@ -12,6 +12,7 @@
 
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "pbd_math.cuh"
 #include "pbd_plan.h"
@@ -52,6 +53,14 @@ class Backend {
   virtual void debug_dump() {}  // PBD_TILE_TRACE: per-phase timing of the last frame to stderr  // frame shape changed (set_params)
   virtual uint64_t device_bytes() const = 0;
   virtual void fill_info(pbd_info& info) const {}
+  // one body across several GPUs (tile backend only)
+  virtual uint32_t shard_world() const { return 1; }
+  virtual uint32_t shard_rank() const { return 0; }
+  virtual void shard_slot_ranges(std::vector<uint32_t>& begin) const { begin.clear(); }
+  virtual cudaError_t shard_export(void*) { return cudaErrorNotSupported; }
+  virtual cudaError_t shard_attach_ipc(const void*) { return cudaErrorNotSupported; }
+  virtual void shard_local_pointers(void** pos, void** done) { *pos = nullptr; *done = nullptr; }
+  virtual cudaError_t shard_attach_pointers(uint32_t, void*, void*, int) { return cudaErrorNotSupported; }
   // optional per-stage timing (stream backend); returns false if unsupported
   virtual bool stage_ms(double& predict, double& solve, double& commit) { return false; }
 };

@@ -184,7 +184,12 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
   cudaDeviceProp prop{};
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { cuda_fail(ce, "cudaGetDeviceProperties", status); return nullptr; }
   const uint32_t smemBytes = (uint32_t)(prop.sharedMemPerBlockOptin > kSmemReserve ? prop.sharedMemPerBlockOptin - kSmemReserve : 0);
-  if (!build_plan(m, h->opts, prop.multiProcessorCount, smemBytes, h->plan, err)) {
+  const uint32_t world = h->opts.shard_world > 1 ? h->opts.shard_world : 1u;
+  if (world > 1 && (h->opts.shard_rank >= world || world > 8)) { fail(PBD_ERR_INVALID, "shard_rank/shard_world out of range", status); return nullptr; }
+  if (world > 1 && h->opts.backend == PBD_BACKEND_STREAM) { fail(PBD_ERR_UNSUPPORTED, "a sharded body needs the tile backend", status); return nullptr; }
+  // one tile per SM of every GPU the body is spread over (or what the caller asks to plan for)
+  const int planSMs = h->opts.plan_sms ? (int)h->opts.plan_sms : prop.multiProcessorCount * (int)world;
+  if (!build_plan(m, h->opts, planSMs, smemBytes, h->plan, err)) {
     fail(PBD_ERR_INVALID, err, status);
     return nullptr;
   }
@@ -401,6 +406,52 @@ int pbd_get_array(pbd_handle* h, int what, float* out) {
     case PBD_ARRAY_TET_LAMBDA: return scal(d.tetLam, d.T, p.tetDevCount, p.tetOrder, p.tetDev);
     default: return fail(PBD_ERR_INVALID, "unknown array id");
   }
+}
+
+/* ---- one body across several GPUs ---- */
+
+int pbd_shard_export(pbd_handle* h, void* out) {
+  if (!h || !out) return fail(PBD_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(h->be->shard_export(out));
+  return PBD_OK;
+}
+
+int pbd_shard_attach_ipc(pbd_handle* h, const void* all) {
+  if (!h || !all) return fail(PBD_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(h->be->shard_attach_ipc(all));
+  return PBD_OK;
+}
+
+int pbd_shard_attach_local(pbd_handle* const* hs, uint32_t world) {
+  if (!hs || world == 0) return fail(PBD_ERR_INVALID, "null argument");
+  for (uint32_t a = 0; a < world; ++a) {
+    if (!hs[a] || hs[a]->be->shard_world() != world || hs[a]->be->shard_rank() != a)
+      return fail(PBD_ERR_INVALID, "handles must be given in rank order, all created with shard_world = world");
+  }
+  for (uint32_t a = 0; a < world; ++a) {
+    CU(cudaSetDevice(hs[a]->device));
+    for (uint32_t b = 0; b < world; ++b) {
+      void *pos = nullptr, *done = nullptr;
+      hs[b]->be->shard_local_pointers(&pos, &done);
+      CU(hs[a]->be->shard_attach_pointers(b, pos, done, hs[b]->device));
+    }
+  }
+  return PBD_OK;
+}
+
+int pbd_shard_owner(const pbd_handle* h, uint8_t* owner) {
+  if (!h || !owner) return fail(PBD_ERR_INVALID, "null argument");
+  std::vector<uint32_t> begin;
+  h->be->shard_slot_ranges(begin);
+  for (uint32_t v = 0; v < h->plan.V; ++v) {
+    uint32_t r = 0;
+    const uint32_t s = h->plan.vertexToSlot[v];
+    while (r + 2 < begin.size() && s >= begin[r + 1]) ++r;
+    owner[v] = (uint8_t)r;
+  }
+  return PBD_OK;
 }
 
 /* ---- schedule only (host) ---- */

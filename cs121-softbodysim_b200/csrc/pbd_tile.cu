@@ -54,6 +54,7 @@ struct PhaseDesc {
 };
 
 constexpr uint32_t kMaxItems = 128;   // tiles one CTA visits per iteration
+constexpr uint32_t kMaxRanks = 8;     // GPUs one body can be spread over (one node)
 
 struct TileParams {
   float4* pos;
@@ -67,7 +68,16 @@ struct TileParams {
   const uint32_t* tile0Begin;   // nTile0 + 1
   const StepConsts* consts;
   unsigned* barrier;
-  unsigned* done;               // per tile: completed visits this frame (point-to-point sync), or null: grid barrier per phase
+  unsigned* done;               // per tile: completed visits (point-to-point sync), or null: grid barrier per phase
+  // one body across several GPUs: every rank steps the tiles it owns; a vertex / a done counter
+  // lives on the rank that owns its home tile / its tile and is read and written in place over
+  // NVLink (peer pointers, opened with CUDA IPC or peer access).  world == 1: entry 0 = this GPU.
+  float4* posPeers[kMaxRanks];
+  unsigned* donePeers[kMaxRanks];
+  const uint32_t* tileList;     // this rank's tiles, phase by phase (PhaseDesc indexes it)
+  const uint32_t* homeList;     // this rank's home tiles (indices into tile0Begin)
+  uint32_t nHome, world, rank;
+  uint32_t iterBase;            // iterations completed by earlier frames: the done counters never reset
   unsigned long long* trace;    // debug: [phase][cta][2] globaltimer ns of (start, arrive), substep 0, last iteration
   long long* ftrace;            // debug: clock64 stamps of CTA 0, 128 per phase
   uint32_t nTile0, nPhases, substeps, iterations;
@@ -91,7 +101,8 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
 // sweep and for the final commit.  finalCommit: ground (if clamp) + commit, no predict.
 __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConsts& k, int mode, bool clamp,
                                             bool finalCommit) {
-  for (uint32_t t = blockIdx.x; t < P.nTile0; t += gridDim.x) {
+  for (uint32_t q = blockIdx.x; q < P.nHome; q += gridDim.x) {
+    const uint32_t t = P.homeList[q];
     const uint32_t b = P.tile0Begin[t], e = P.tile0Begin[t + 1];
     for (uint32_t s = b + threadIdx.x; s < e; s += blockDim.x) {
       if (finalCommit) {
@@ -119,6 +130,10 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   __shared__ TileCopy itemCopy[kMaxItems];   // copy descriptors of this CTA's tiles: no global latency when prefetching
   __shared__ uint32_t itemTile[kMaxItems];
   __shared__ uint32_t nItemsS;
+  __shared__ float4* posPeerS[kMaxRanks];
+  __shared__ unsigned* donePeerS[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) { posPeerS[threadIdx.x] = P.posPeers[threadIdx.x]; donePeerS[threadIdx.x] = P.donePeers[threadIdx.x]; }
+  const bool multi = P.world > 1;
   const uint32_t svOff = 2u * P.recStride;
   float4* const sv = reinterpret_cast<float4*>(smem + svOff);
 
@@ -140,7 +155,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
     for (uint32_t ph = 0; ph < P.nPhases; ++ph) {
       const PhaseDesc pd = P.phases[ph];
       for (uint32_t t = blockIdx.x; t < pd.tileCount; t += gridDim.x)
-        if (n < kMaxItems) { itemTile[n] = pd.tileBegin + t; itemCopy[n++] = P.copies[pd.tileBegin + t]; }
+        if (n < kMaxItems) { const uint32_t tl = P.tileList[pd.tileBegin + t]; itemTile[n] = tl; itemCopy[n++] = P.copies[tl]; }
     }
     nItemsS = n;
     mbar_init(&mbar[0], 1);
@@ -217,10 +232,11 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           if (P.done) {
             const uint32_t np = (h.flags >> 8) & 0xffu;
             if (tid < np) {
+              // entry: tile (bits 0..23) | owner rank (24..27) | bit 31 = written earlier in THIS iteration
               const uint32_t e = reinterpret_cast<const uint32_t*>(rec + 64)[tid];
-              const uint32_t need = sub * P.iterations + it + (e >> 31);   // bit 31: written earlier in THIS iteration
-              const unsigned* f = P.done + (e & 0x7fffffffu);
-              while (ld_acquire(f) < need) {}
+              const uint32_t need = P.iterBase + sub * P.iterations + it + (e >> 31);
+              const unsigned* f = donePeerS[(e >> 24) & 0xfu] + (e & 0xffffffu);
+              if (multi) { while (ld_acquire_sys(f) < need) {} } else { while (ld_acquire(f) < need) {} }
             }
             __syncthreads();
           }
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const uint32_t i = base + u * nth + tid;
-                if (i < h.vertCount) v[u] = __ldcg(P.pos + vidx[i]);
+                if (i < h.vertCount) { const uint32_t e = vidx[i]; v[u] = __ldcg(posPeerS[e >> 28] + (e & 0x0fffffffu)); }
               }
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
@@ -270,7 +286,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + h.vertBegin + i, sv[i]);
           } else {
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
-            for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + vidx[i], sv[i]);
+            for (uint32_t i = tid; i < h.vertCount; i += nth) { const uint32_t e = vidx[i]; __stcg(posPeerS[e >> 28] + (e & 0x0fffffffu), sv[i]); }
           }
           fence_async_smem();   // lambdas written by the sweeps -> visible to the bulk store
           __syncthreads();      // also: sv and rec are free for the next tile
@@ -280,7 +296,10 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
             bulk_commit();
             if (nItems == 1) bulk_wait_read();   // the block stays resident and is swept again next iteration
-            if (P.done) st_release(P.done + itemTile[j], sub * P.iterations + it + 1u);   // my vertices are in L2
+            if (P.done) {   // my vertices are in L2 (of their owners)
+              const uint32_t v = P.iterBase + sub * P.iterations + it + 1u;
+              if (multi) st_release_sys(P.done + itemTile[j], v); else st_release(P.done + itemTile[j], v);
+            }
           }
           if (nItems == 1) {
             __syncthreads();
@@ -298,7 +317,21 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
     }
   }
   if (tid == 0) bulk_wait_all();
-  if (P.done) grid_barrier(P.barrier, epoch);   // the final commit reads every vertex's last value
+  if (P.done) {
+    // the final commit of a home tile reads its vertices' last values: wait for the tiles that wrote them
+    const uint32_t need = P.iterBase + P.substeps * P.iterations;
+    for (uint32_t q = blockIdx.x; q < P.nHome; q += gridDim.x) {
+      const TileCopy c = P.copies[P.tileList[P.phases[0].tileBegin + q]];   // the q-th home tile I own = my q-th phase-0 tile
+      const uint32_t* hdr = reinterpret_cast<const uint32_t*>(P.blob + c.blobOff);
+      const uint32_t np = (__ldg(hdr + 1) >> 8) & 0xffu;
+      if (tid < np) {
+        const uint32_t e = __ldg(hdr + 16 + tid);
+        const unsigned* f = donePeerS[(e >> 24) & 0xfu] + (e & 0xffffffu);
+        if (multi) { while (ld_acquire_sys(f) < need) {} } else { while (ld_acquire(f) < need) {} }
+      }
+    }
+    __syncthreads();
+  }
   vertex_pass(P, k, LOAD_PLAIN, clamp, true);
 }
 
@@ -306,7 +339,8 @@ class TileBackend final : public Backend {
  public:
   TileBackend(const pbd_options& o, int device) : opts_(o), device_(device) {}
   ~TileBackend() override {
-    cudaFree(done_);
+    for (void* q : ipcOpened_) cudaIpcCloseMemHandle(q);
+    cudaFree(done_); cudaFree(tileList_); cudaFree(homeList_);
     cudaFree(blob_); cudaFree(copies_); cudaFree(phases_); cudaFree(tile0Begin_); cudaFree(barrier_);
     cudaFree(trace_); cudaFree(ftrace_);
   }
@@ -325,8 +359,42 @@ class TileBackend final : public Backend {
     if (plan.edgeDevCount && (err = cudaMemcpy(eRest.data(), d.edgeRest, sizeof(float) * plan.edgeDevCount, cudaMemcpyDeviceToHost)) != cudaSuccess) return err;
     if (plan.tetDevCount && (err = cudaMemcpy(tRest.data(), d.tetRest, sizeof(float) * plan.tetDevCount, cudaMemcpyDeviceToHost)) != cudaSuccess) return err;
 
+    // ---- ownership (one body across `world` GPUs; world == 1: everything is mine).  Home tiles are
+    // dealt out in contiguous runs (they are slot-contiguous and spatially ordered), a vertex belongs
+    // to the rank of its home tile, any other tile to the rank that owns most of its vertices.
+    world_ = std::max(1u, opts_.shard_world);
+    rank_ = opts_.shard_rank;
+    if (world_ > kMaxRanks || rank_ >= world_ || plan.V >= (1u << 28) || plan.tiles.size() >= (1u << 24)) return cudaErrorInvalidValue;
+    std::vector<uint32_t> rankSlotBegin(world_ + 1, plan.V);
+    rankSlotBegin[0] = 0;
+    homeOwner_.assign(nTile0_, 0);
+    for (uint32_t t = 0; t < nTile0_; ++t) {
+      const uint32_t r = (uint32_t)(((uint64_t)t * world_) / std::max(1u, nTile0_));
+      homeOwner_[t] = (uint8_t)r;
+      rankSlotBegin[r] = std::min(rankSlotBegin[r], plan.tile0Begin[t]);
+    }
+    for (uint32_t r = world_; r-- > 0;) rankSlotBegin[r] = std::min(rankSlotBegin[r], rankSlotBegin[r + 1]);
+    auto owner_of_slot = [&](uint32_t s) {
+      uint32_t r = 0;
+      while (r + 1 < world_ && s >= rankSlotBegin[r + 1]) ++r;
+      return r;
+    };
+    slotOwnerBegin_ = rankSlotBegin;
+    std::vector<uint8_t> tileOwner(plan.tiles.size(), 0);
+    for (size_t ti = 0; ti < plan.tiles.size(); ++ti) {
+      const Tile& t = plan.tiles[ti];
+      if (world_ == 1 || t.vertCount == 0) continue;
+      if (t.contiguous) { tileOwner[ti] = (uint8_t)owner_of_slot(t.vertBegin); continue; }
+      uint32_t cnt[kMaxRanks] = {0};
+      for (uint32_t i = 0; i < t.vertCount; ++i) cnt[owner_of_slot(plan.tileVerts[t.vertBegin + i])]++;
+      uint32_t best = 0;
+      for (uint32_t r = 1; r < world_; ++r)
+        if (cnt[r] > cnt[best]) best = r;
+      tileOwner[ti] = (uint8_t)best;
+    }
+
     // ---- point-to-point dependencies: for every tile, the tiles that last wrote one of its vertices
-    // (bit 31 set: earlier in the same iteration; clear: in the previous iteration)
+    // (entry: tile | owner rank << 24 | bit 31 = earlier in the same iteration, else previous iteration)
     std::vector<std::vector<uint32_t>> preds(plan.tiles.size());
     bool flagsOk = !getenv("PBD_TILE_GRIDSYNC");
     {
@@ -341,7 +409,8 @@ class TileBackend final : public Backend {
             if (pass == 1) {
               std::vector<uint32_t>& pr = preds[ti];
               for_verts(t, [&](uint32_t s) {
-                if (lastTile[s] != 0xffffffffu && lastTile[s] != ti) pr.push_back(lastTile[s] | (lastPhase[s] < ph ? 0x80000000u : 0u));
+                if (lastTile[s] != 0xffffffffu && lastTile[s] != ti)
+                  pr.push_back(lastTile[s] | ((uint32_t)tileOwner[lastTile[s]] << 24) | (lastPhase[s] < ph ? 0x80000000u : 0u));
               });
               std::sort(pr.begin(), pr.end());
               pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
@@ -350,7 +419,8 @@ class TileBackend final : public Backend {
             for_verts(t, [&](uint32_t s) { lastTile[s] = ti; lastPhase[s] = (uint32_t)ph; });
           }
     }
-    useFlags_ = flagsOk && plan.tiles.size() < 0x7fffffffull;
+    useFlags_ = flagsOk;
+    if (world_ > 1 && !useFlags_) return cudaErrorNotSupported;   // several GPUs cannot share a grid barrier
 
     // ---- record blocks
     std::vector<TileCopy> copies(plan.tiles.size());
@@ -382,7 +452,13 @@ class TileBackend final : public Backend {
       unsigned char* b = blob.data() + base;
       memcpy(b, &h, sizeof(h));
       if (nPred) memcpy(b + 64, preds[ti].data(), 4u * nPred);
-      if (nVG) memcpy(b + h.offVertIdx, &plan.tileVerts[t.vertBegin], 4u * nVG);
+      if (nVG) {
+        uint32_t* vi = reinterpret_cast<uint32_t*>(b + h.offVertIdx);
+        for (uint32_t q = 0; q < nVG; ++q) {
+          const uint32_t sl = plan.tileVerts[t.vertBegin + q];
+          vi[q] = sl | (owner_of_slot(sl) << 28);
+        }
+      }
       uint32_t* eg = reinterpret_cast<uint32_t*>(b + h.offEdgeGroups);
       for (uint32_t g = 0; g < t.edgeGroupCount; ++g) {
         eg[2 * g] = plan.groups[t.edgeGroupBegin + g].begin - t.edgeBegin;
@@ -442,12 +518,19 @@ class TileBackend final : public Backend {
     smemBytes_ = 2 * (size_t)recStride_ + sizeof(float4) * (size_t)std::max(plan.tileVertexCapacity, 1u);
 
     std::vector<PhaseDesc> pd(plan.phases.size());
-    maxTilesPerPhase_ = nTile0_;
-    std::vector<uint32_t> perCta;
+    std::vector<uint32_t> tileList, homeList;
+    maxTilesPerPhase_ = 0;
     for (size_t i = 0; i < pd.size(); ++i) {
-      pd[i] = PhaseDesc{plan.phases[i].tileBegin, plan.phases[i].tileCount};
-      maxTilesPerPhase_ = std::max(maxTilesPerPhase_, plan.phases[i].tileCount);
+      pd[i].tileBegin = (uint32_t)tileList.size();
+      for (uint32_t ti = plan.phases[i].tileBegin; ti < plan.phases[i].tileBegin + plan.phases[i].tileCount; ++ti)
+        if (tileOwner[ti] == rank_) tileList.push_back(ti);
+      pd[i].tileCount = (uint32_t)tileList.size() - pd[i].tileBegin;
+      maxTilesPerPhase_ = std::max(maxTilesPerPhase_, pd[i].tileCount);
     }
+    for (uint32_t t = 0; t < nTile0_; ++t)
+      if (homeOwner_[t] == rank_) homeList.push_back(t);
+    nHome_ = (uint32_t)homeList.size();
+    maxTilesPerPhase_ = std::max(maxTilesPerPhase_, nHome_);
     auto up = [&](auto** dst, const auto& src) -> cudaError_t {
       using T = typename std::remove_reference<decltype(src)>::type::value_type;
       cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * src.size() + 256);
@@ -460,9 +543,18 @@ class TileBackend final : public Backend {
     if ((err = up(&copies_, copies)) != cudaSuccess) return err;
     if ((err = up(&phases_, pd)) != cudaSuccess) return err;
     if ((err = up(&tile0Begin_, plan.tile0Begin)) != cudaSuccess) return err;
+    if ((err = up(&tileList_, tileList)) != cudaSuccess) return err;
+    if ((err = up(&homeList_, homeList)) != cudaSuccess) return err;
     if ((err = cudaMalloc((void**)&barrier_, 2048)) != cudaSuccess) return err;
     doneBytes_ = sizeof(unsigned) * (plan.tiles.size() + 1);
-    if (useFlags_ && (err = cudaMalloc((void**)&done_, doneBytes_)) != cudaSuccess) return err;
+    if (useFlags_) {
+      if ((err = cudaMalloc((void**)&done_, doneBytes_)) != cudaSuccess) return err;
+      if ((err = cudaMemset(done_, 0, doneBytes_)) != cudaSuccess) return err;   // counters only ever grow
+    }
+    for (uint32_t r = 0; r < kMaxRanks; ++r) { posPeers_[r] = nullptr; donePeers_[r] = nullptr; }
+    posPeers_[rank_] = d.pos;
+    donePeers_[rank_] = done_;
+    attached_ = world_ == 1;
     stagger_ = getenv("PBD_TILE_STAGGER") ? (uint32_t)atoi(getenv("PBD_TILE_STAGGER")) : 0u;
     if (getenv("PBD_TILE_TRACE")) {
       traceN_ = 2 * (size_t)(nPhases_ + 1) * 4096;
@@ -498,8 +590,12 @@ class TileBackend final : public Backend {
     P.recStride = recStride_;
     P.stagger = stagger_;
     P.done = useFlags_ ? done_ : nullptr;
+    if (!attached_) return cudaErrorNotReady;   // pbd_shard_attach_* first
+    for (uint32_t r = 0; r < kMaxRanks; ++r) { P.posPeers[r] = posPeers_[r]; P.donePeers[r] = donePeers_[r]; }
+    P.tileList = tileList_; P.homeList = homeList_; P.nHome = nHome_; P.world = world_; P.rank = rank_;
+    P.iterBase = iterBase_;
+    iterBase_ += f.substeps * f.iterations;
     cudaError_t err = cudaMemsetAsync(barrier_, 0, 2048, s);
-    if (err == cudaSuccess && useFlags_) err = cudaMemsetAsync(done_, 0, doneBytes_, s);
     if (err != cudaSuccess) return err;
     void* args[] = {&P};
     return cudaLaunchCooperativeKernel(kernel(), dim3(grid_), dim3(block_), args, smemBytes_, s);
@@ -539,6 +635,50 @@ class TileBackend final : public Backend {
       fprintf(stderr, "\n");
     }
   }
+  // ---- one body across several GPUs
+  uint32_t shard_world() const override { return world_; }
+  uint32_t shard_rank() const override { return rank_; }
+  void shard_slot_ranges(std::vector<uint32_t>& begin) const override { begin = slotOwnerBegin_; }
+  cudaError_t shard_export(void* out128) override {
+    cudaIpcMemHandle_t hs[2];
+    memset(hs, 0, sizeof(hs));
+    cudaError_t e = cudaIpcGetMemHandle(&hs[0], posPeers_[rank_]);
+    if (e == cudaSuccess && done_) e = cudaIpcGetMemHandle(&hs[1], done_);
+    memcpy(out128, hs, sizeof(hs));
+    return e;
+  }
+  cudaError_t shard_attach_ipc(const void* all) override {
+    const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(all);
+    for (uint32_t r = 0; r < world_; ++r) {
+      if (r == rank_) continue;
+      void *pp = nullptr, *dp = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&pp, hs[2 * r], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return e;
+      ipcOpened_.push_back(pp);
+      e = cudaIpcOpenMemHandle(&dp, hs[2 * r + 1], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return e;
+      ipcOpened_.push_back(dp);
+      posPeers_[r] = static_cast<float4*>(pp);
+      donePeers_[r] = static_cast<unsigned*>(dp);
+    }
+    attached_ = true;
+    return cudaSuccess;
+  }
+  void shard_local_pointers(void** pos, void** done) override { *pos = posPeers_[rank_]; *done = done_; }
+  cudaError_t shard_attach_pointers(uint32_t r, void* pos, void* done, int peerDevice) override {
+    if (r >= world_) return cudaErrorInvalidValue;
+    if (r != rank_) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(peerDevice, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      if (e != cudaSuccess) return e;
+      posPeers_[r] = static_cast<float4*>(pos);
+      donePeers_[r] = static_cast<unsigned*>(done);
+    }
+    bool all = true;
+    for (uint32_t q = 0; q < world_; ++q) all &= posPeers_[q] != nullptr;
+    attached_ = all;
+    return cudaSuccess;
+  }
   uint32_t launches_per_frame(const FrameShape&) const override { return 1; }
   uint64_t device_bytes() const override { return bytes_; }
   void fill_info(pbd_info& info) const override {
@@ -563,6 +703,15 @@ class TileBackend final : public Backend {
   long long* ftrace_ = nullptr;
   size_t traceN_ = 0;
   uint32_t stagger_ = 0;
+  uint32_t world_ = 1, rank_ = 0, nHome_ = 0, iterBase_ = 0;
+  bool attached_ = true;
+  std::vector<uint8_t> homeOwner_;
+  std::vector<uint32_t> slotOwnerBegin_;
+  float4* posPeers_[kMaxRanks] = {};
+  unsigned* donePeers_[kMaxRanks] = {};
+  uint32_t* tileList_ = nullptr;
+  uint32_t* homeList_ = nullptr;
+  std::vector<void*> ipcOpened_;
   unsigned* done_ = nullptr;
   size_t doneBytes_ = 0;
   bool useFlags_ = false;

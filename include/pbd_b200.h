@@ -102,7 +102,10 @@ typedef struct pbd_options {
   uint32_t partitions;     /* tile backend: shifted vertex partitions per sweep, 0 = auto (4)    */
   uint32_t lanes_per_tet;  /* tile backend: 1, 2 or 4 lanes cooperate on one tet, 0 = auto (1)   */
   uint32_t tiles_per_sm;   /* tile backend: tiles (CTAs) resident per SM, 0 = auto               */
-  uint32_t reserved[6];
+  uint32_t shard_world;    /* one body across several GPUs of a node: number of ranks (0/1 = off) */
+  uint32_t shard_rank;     /* ... and which of them this handle is                               */
+  uint32_t plan_sms;       /* plan for this many SMs, 0 = the device's SM count x shard_world     */
+  uint32_t reserved[3];
 } pbd_options;
 
 typedef struct pbd_info {
@@ -178,6 +181,27 @@ enum {
   PBD_ARRAY_XSTAR = 6        /* 3V floats */
 };
 int pbd_get_array(pbd_handle* h, int what, float* out);
+
+/* ---- one body across several GPUs of one node (BASELINE.json config 5) -------------------
+ *
+ * Every rank (one process per GPU, or one handle per device in a single process) calls pbd_create
+ * with the SAME mesh and opts.shard_world / opts.shard_rank set.  All ranks build the same
+ * schedule; a rank steps the tiles it owns.  Vertices live on the rank that owns their home tile
+ * and are read and written IN PLACE by the tiles of other ranks over NVLink (peer pointers); the
+ * per-tile done counters that order the tiles work across GPUs the same way (system-scope
+ * release/acquire).  There is no separate halo-exchange step and the result is bit-identical to
+ * a single-GPU run of the same schedule (opts.plan_sms).
+ *
+ *   multi-process:  pbd_shard_export -> all-gather the 128-byte blobs -> pbd_shard_attach_ipc
+ *   one process:    pbd_shard_attach_local(handles, world)
+ * then pbd_step_async on every rank (all ranks must be launched before any is synchronised),
+ * pbd_sync, and pbd_read_positions, which returns valid positions for the vertices this rank
+ * owns (pbd_shard_owner tells which). */
+#define PBD_SHARD_EXPORT_BYTES 128
+int pbd_shard_export(pbd_handle* h, void* out /* PBD_SHARD_EXPORT_BYTES */);
+int pbd_shard_attach_ipc(pbd_handle* h, const void* all /* world x PBD_SHARD_EXPORT_BYTES, rank order */);
+int pbd_shard_attach_local(pbd_handle* const* handles, uint32_t world);
+int pbd_shard_owner(const pbd_handle* h, uint8_t* ownerOfVertex /* V */);
 
 /* ---- schedule only (pure host code, no CUDA: usable on a machine without a GPU) ------- */
 
