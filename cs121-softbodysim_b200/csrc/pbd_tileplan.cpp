@@ -3,7 +3,8 @@
 // Why: a globally coloured sweep needs one grid-wide barrier per colour (~46 per iteration on the
 // Kuhn grid, 155 on default_Tet), which caps an L2-resident mesh at a few % of the HBM roofline
 // (SURVEY.md 7 "dependent-phase count vs. bytes").  Here one iteration is K grid-wide phases
-// (K = 4 by default).  Phase p uses vertex partition P_p: the vertices are cut into as many tiles
+// (K = 4 by default; the phases are ordered by per-tile dependency counters, not by a grid barrier,
+// see pbd_tile.cu).  Phase p uses vertex partition P_p: the vertices are cut into as many tiles
 // as there are SMs (k-d style multi-way splits in rank space), and P_1..P_{K-1} are the same cuts
 // CYCLICALLY SHIFTED by p/K of a tile along every axis.  A constraint can run in phase p when all
 // its vertices fall into one tile of P_p ("interior"); with four shifts every constraint of a
@@ -15,8 +16,9 @@
 // block barriers only.  Constraints interior to no partition (rare) go through residual phases
 // that re-partition just their own vertices (graph Voronoi), as many as needed.
 //
-// Order: phase by phase, tile by tile, [edge colours, then tet colours], caller index inside a
-// colour.  Tiles of one phase are vertex-disjoint and colour groups are conflict-free, so running
+// Order: phase by phase, tile by tile, [edge colours, then tet colours]; inside a colour the
+// constraints are arranged for conflict-free shared-memory banks (any order gives the same result:
+// they share no vertex).  Tiles of one phase are vertex-disjoint and colour groups are conflict-free, so running
 // them in parallel equals running them sequentially in that order: still Gauss-Seidel over the
 // same constraint set, only permuted (disclosed through pbd_get_schedule_order / _sequence).
 //   PBD_ORDER_STRICT       every iteration projects all edges (K phases), then all tets (K phases),
