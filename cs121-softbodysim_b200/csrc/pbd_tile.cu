@@ -53,7 +53,8 @@ struct PhaseDesc {
   uint32_t tileBegin, tileCount;
 };
 
-constexpr uint32_t kMaxItems = 128;   // tiles one CTA visits per iteration
+constexpr uint32_t kMaxItems = 512;      // tiles one CTA visits per iteration
+constexpr uint32_t kItemCopySmem = 128;  // ... whose copy descriptors are cached in shared memory
 constexpr uint32_t kMaxRanks = 8;     // GPUs one body can be spread over (one node)
 
 struct TileParams {
@@ -127,7 +128,7 @@ template <int LANES>
 __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar[2];
-  __shared__ TileCopy itemCopy[kMaxItems];   // copy descriptors of this CTA's tiles: no global latency when prefetching
+  __shared__ TileCopy itemCopy[kItemCopySmem];   // copy descriptors of this CTA's tiles: no global latency when prefetching
   __shared__ uint32_t itemTile[kMaxItems];
   __shared__ uint32_t nItemsS;
   __shared__ float4* posPeerS[kMaxRanks];
@@ -155,7 +156,12 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
     for (uint32_t ph = 0; ph < P.nPhases; ++ph) {
       const PhaseDesc pd = P.phases[ph];
       for (uint32_t t = blockIdx.x; t < pd.tileCount; t += gridDim.x)
-        if (n < kMaxItems) { const uint32_t tl = P.tileList[pd.tileBegin + t]; itemTile[n] = tl; itemCopy[n++] = P.copies[tl]; }
+        if (n < kMaxItems) {
+          const uint32_t tl = P.tileList[pd.tileBegin + t];
+          itemTile[n] = tl;
+          if (n < kItemCopySmem) itemCopy[n] = P.copies[tl];
+          ++n;
+        }
     }
     nItemsS = n;
     mbar_init(&mbar[0], 1);
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
 
   // fetch the record block of this CTA's item `ji` into buffer `b` (thread 0 only)
   auto fetch = [&](uint32_t ji, uint32_t b) {
-    const TileCopy c = itemCopy[ji];
+    const TileCopy c = ji < kItemCopySmem ? itemCopy[ji] : P.copies[itemTile[ji]];
     unsigned char* dst = smem + b * P.recStride;
     mbar_expect_tx(&mbar[b], c.staticBytes + c.edgeLamBytes + c.tetLamBytes);
     bulk_load(dst, P.blob + c.blobOff, c.staticBytes, &mbar[b]);
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           fence_async_smem();   // lambdas written by the sweeps -> visible to the bulk store
           __syncthreads();      // also: sv and rec are free for the next tile
           if (tid == 0) {
-            const TileCopy c = itemCopy[j];
+            const TileCopy c = j < kItemCopySmem ? itemCopy[j] : P.copies[itemTile[j]];
             if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
             if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
             bulk_commit();
