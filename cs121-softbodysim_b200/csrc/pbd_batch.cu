@@ -257,8 +257,8 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
     std::shared_ptr<Coloured>& col = cache[key];
     if (!col) {
       col = std::make_shared<Coloured>();
-      colour_and_order(m.edges, Eb, 2, Vb, col->eOrder, col->eCounts);
-      colour_and_order(m.tets, Tb, 4, Vb, col->tOrder, col->tCounts);
+      colour_and_order(m.edges, Eb, 2, Vb, 512, col->eOrder, col->eCounts);   // 512 = the kernel's block size
+      colour_and_order(m.tets, Tb, 4, Vb, 512, col->tOrder, col->tCounts);
     }
     std::copy(col->eOrder.begin(), col->eOrder.end(), B->edgeOrder.begin() + eOff[b]);
     std::copy(col->tOrder.begin(), col->tOrder.end(), B->tetOrder.begin() + tOff[b]);

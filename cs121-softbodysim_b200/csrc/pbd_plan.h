@@ -102,9 +102,10 @@ uint32_t greedy_colour(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t
 
 // Colour the constraints of one whole body (largest-degree-first greedy + recolouring pass) and
 // return them sorted by colour, bank-aware inside a colour (pbd_tileplan.cpp): order[k] = constraint
-// projected k-th, counts[c] = size of colour c.  Used by the batch backend (one body = one tile).
-void colour_and_order(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nVerts, std::vector<uint32_t>& order,
-                      std::vector<uint32_t>& counts);
+// projected k-th, counts[g] = size of group g (a colour, split into several groups when it exceeds
+// maxGroup = what one block pass of the sweep takes).  Used by the batch backend (one body = one tile).
+void colour_and_order(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nVerts, uint32_t maxGroup,
+                      std::vector<uint32_t>& order, std::vector<uint32_t>& counts);
 
 // Returns false and fills err on invalid input (index >= V).
 bool validate_mesh(const MeshView& m, std::string& err);

@@ -16,6 +16,13 @@ namespace pbd {
 // The frame kernel calls the sweeps out of line: they then get a register allocation of their
 // own instead of sharing 128 registers with the kernel's schedule-walking state (which spilled
 // inside the colour loops).  One call per tile visit is noise next to a sweep.
+// per-step clock stamps for PBD_TILE_TRACE (compiled in only with -DPBD_TRACE_STEPS: even a
+// predicated-off stamp per colour step costs measurable time in these loops)
+#ifdef PBD_TRACE_STEPS
+#define PBD_STEP_TRACE(ft, g, n) do { if ((ft) && (g) < 40) { (ft)[16 + (g)] = clock64(); (ft)[56 + (g)] = (n); } } while (0)
+#else
+#define PBD_STEP_TRACE(ft, g, n) do { (void)(ft); } while (0)
+#endif
 #ifndef PBD_SWEEP_INLINE
 #define PBD_SWEEP_INLINE static __device__ __noinline__
 #endif
@@ -66,15 +73,17 @@ PBD_SWEEP_INLINE void sweep_edges(const TileHdr& h, uint32_t rec, uint32_t svOff
   for (uint32_t g = 0; g < n; ++g) {
     const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 0u);
     if (have) project(e, id, r, l);
+#ifdef PBD_SWEEP_OVERFLOW   // the planner keeps every group within one block pass (pbd_tileplan.cpp)
     for (uint32_t i = tid + nth; i < gd.y; i += nth) {   // colour groups larger than the block
       const uint32_t e2 = gd.x + i;
       project(e2, idx[e2], rest[e2], lam[e2]);
     }
+#endif
     e = gn.x + tid;
     have = tid < gn.y;
     if (have) { id = idx[e]; r = rest[e]; l = lam[e]; }
     __syncthreads();
-    if (ft && g < 40) { ft[16 + g] = clock64(); ft[56 + g] = gd.y; }
+    PBD_STEP_TRACE(ft, g, gd.y);
     gd = gn;
   }
 }
@@ -116,15 +125,17 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
     for (uint32_t g = 0; g < n; ++g) {
       const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 0u);
       if (have) project(t, id, r, l);
+#ifdef PBD_SWEEP_OVERFLOW
       for (uint32_t i = tid + nth; i < gd.y; i += nth) {
         const uint32_t t2 = gd.x + i;
         project(t2, idx[t2], rest[t2], lam[t2]);
       }
+#endif
       t = gn.x + tid;
       have = tid < gn.y;
       if (have) { id = idx[t]; r = rest[t]; l = lam[t]; }
       __syncthreads();
-      if (ft && g < 40) { ft[16 + g] = clock64(); ft[56 + g] = gd.y; }
+      PBD_STEP_TRACE(ft, g, gd.y);
       gd = gn;
     }
   } else if (LANES == 2) {
@@ -191,17 +202,19 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
     for (uint32_t g = 0; g < n; ++g) {
       const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 1u);
       if (((tid >> 5) << 4) < gd.y) project(t, id, r, l, live);                // warp-uniform: idle warps skip the step
+#ifdef PBD_SWEEP_OVERFLOW
       for (uint32_t i0 = pairs + ((tid >> 5) << 4); i0 < gd.y; i0 += pairs) {   // warp-uniform trip count
         const uint32_t i = i0 + (lane >> 1);
         const bool lv = i < gd.y;
         const uint32_t t2 = gd.x + (lv ? i : gd.y - 1u);
         project(t2, idx[t2], rest[t2], lam[t2], lv);
       }
+#endif
       live = pair < gn.y && g + 1 < n;
       t = gn.x + ((pair < gn.y) ? pair : gn.y - 1u);
       if (g + 1 < n) { id = idx[t]; r = rest[t]; l = lam[t]; }
       __syncthreads();
-      if (ft && g < 40) { ft[16 + g] = clock64(); ft[56 + g] = gd.y; }
+      PBD_STEP_TRACE(ft, g, gd.y);
       gd = gn;
     }
   } else {
@@ -250,6 +263,7 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
     for (uint32_t g = 0; g < n; ++g) {
       const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 1u);
       if (((tid >> 5) << 3) < gd.y) project(t, id, r, l, live);   // warp-uniform: idle warps skip the step
+#ifdef PBD_SWEEP_OVERFLOW
       // colour groups larger than a block's worth of quads: warp-uniform trip count
       for (uint32_t i0 = quads + ((tid >> 5) << 3); i0 < gd.y; i0 += quads) {
         const uint32_t i = i0 + (lane >> 2);
@@ -257,11 +271,12 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
         const uint32_t t2 = gd.x + (lv ? i : gd.y - 1u);
         project(t2, idx[t2], rest[t2], lam[t2], lv);
       }
+#endif
       live = quad < gn.y && g + 1 < n;
       t = gn.x + ((quad < gn.y) ? quad : gn.y - 1u);
       if (g + 1 < n) { id = idx[t]; r = rest[t]; l = lam[t]; }
       __syncthreads();
-      if (ft && g < 40) { ft[16 + g] = clock64(); ft[56 + g] = gd.y; }
+      PBD_STEP_TRACE(ft, g, gd.y);
       gd = gn;
     }
   }

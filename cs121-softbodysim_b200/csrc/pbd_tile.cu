@@ -355,7 +355,7 @@ class TileBackend final : public Backend {
   cudaError_t upload(const Plan& plan, const MeshView& m, DeviceArrays& d) override {
     (void)m;
     cudaError_t err;
-    block_ = plan.blockThreads ? std::min(plan.blockThreads, 512u) : 512u;
+    block_ = plan.blockThreads ? std::min(plan.blockThreads, 512u) : 512u;   // colour groups were cut to fit one pass of this block
     nPhases_ = (uint32_t)plan.phases.size();
     nTile0_ = (uint32_t)plan.tile0Begin.size() - 1;
     lanes_ = opts_.lanes_per_tet == 2 ? 2u : opts_.lanes_per_tet == 4 ? 4u : 1u;   // auto: one thread per tet (fastest measured)

@@ -666,8 +666,8 @@ void build_residual_phases(const CSet sets[2], int ty, std::vector<uint32_t> res
 
 }  // namespace
 
-void colour_and_order(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nVerts, std::vector<uint32_t>& order,
-                      std::vector<uint32_t>& counts) {
+void colour_and_order(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nVerts, uint32_t maxGroup,
+                      std::vector<uint32_t>& order, std::vector<uint32_t>& counts) {
   order.clear();
   counts.clear();
   if (n == 0) return;
@@ -682,7 +682,9 @@ void colour_and_order(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t 
     size_t j = i;
     while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
     bank_order(cs, localOf, &L.cons[i], (uint32_t)(j - i));
-    counts.push_back((uint32_t)(j - i));
+    const uint32_t nGrp = (uint32_t)(j - i), lim = std::max(1u, maxGroup), parts = (nGrp + lim - 1) / lim;
+    for (uint32_t q = 0; q < parts; ++q)   // a colour larger than one block pass becomes several groups
+      counts.push_back((uint32_t)(((uint64_t)nGrp * (q + 1)) / parts - ((uint64_t)nGrp * q) / parts));
     i = j;
   }
   order = L.cons;
@@ -700,7 +702,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   if (opts.order_mode != PBD_ORDER_STRICT && opts.order_mode != PBD_ORDER_INTERLEAVED) { err = "unknown order_mode"; return false; }
   const bool fused = opts.order_mode == PBD_ORDER_INTERLEAVED;
   const uint32_t blockThreads = opts.block_threads ? opts.block_threads : (opts.tiles_per_sm >= 2 ? 256u : 512u);
-  if (blockThreads % 32 || blockThreads > 1024) { err = "block_threads must be a multiple of 32, <= 1024"; return false; }
+  if (blockThreads % 32 || blockThreads > 512) { err = "block_threads must be a multiple of 32, <= 512"; return false; }
   plan.blockThreads = blockThreads;
   if (opts.partitions > kMaxPartitions) { err = "partitions must be <= 8"; return false; }
 
@@ -1137,10 +1139,17 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           while (i < L.cons.size()) {
             size_t j = i;
             while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
-            Group g;
-            g.begin = (uint32_t)order.size();
-            g.count = (uint32_t)(j - i);
-            plan.groups.push_back(g);
+            // one group per colour, split so that no group exceeds what one block pass can take
+            // (the sweep loops then need no second pass and stay half as long)
+            const uint32_t lanes = ty ? std::max(1u, opts.lanes_per_tet) : 1u;
+            const uint32_t lim = std::max(1u, blockThreads / lanes);
+            const uint32_t nGrp = (uint32_t)(j - i), parts = (nGrp + lim - 1) / lim;
+            for (uint32_t q = 0; q < parts; ++q) {
+              Group g;
+              g.begin = (uint32_t)order.size() + (uint32_t)(((uint64_t)nGrp * q) / parts);
+              g.count = (uint32_t)(((uint64_t)nGrp * (q + 1)) / parts - ((uint64_t)nGrp * q) / parts);
+              plan.groups.push_back(g);
+            }
             for (size_t k = i; k < j; ++k) {
               const uint32_t c = L.cons[k];
               cPhase[c] = (uint32_t)plan.phases.size();
