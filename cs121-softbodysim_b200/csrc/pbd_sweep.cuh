@@ -13,15 +13,10 @@
 
 namespace pbd {
 
-// The frame kernel calls the sweeps out of line: they then get a register allocation of their
-// own instead of sharing 128 registers with the kernel's schedule-walking state (which spilled
-// inside the colour loops).  One call per tile visit is noise next to a sweep.
-// per-step clock stamps for PBD_TILE_TRACE (compiled in only with -DPBD_TRACE_STEPS: even a
-// predicated-off stamp per colour step costs measurable time in these loops)
-#ifdef PBD_TRACE_STEPS
-#define PBD_STEP_TRACE(ft, g, n) do { if ((ft) && (g) < 40) { (ft)[16 + (g)] = clock64(); (ft)[56 + (g)] = (n); } } while (0)
-#else
-#define PBD_STEP_TRACE(ft, g, n) do { (void)(ft); } while (0)
+// Inlined into the frame kernels (measured A/B on one box, tools/gpu_ab.sh: +3.7 % over calling
+// them out of line once the colour loops had been reduced to a single pass without prefetch).
+#ifndef PBD_SWEEP_INLINE
+#define PBD_SWEEP_INLINE static __device__ __forceinline__
 #endif
 #ifndef PBD_SWEEP_INLINE
 #define PBD_SWEEP_INLINE static __device__ __noinline__
@@ -39,10 +34,8 @@ static_assert(sizeof(TileHdr) == 64, "TileHdr is the 64-byte block header");
 // ---------------------------------------------------------------- sweeps (shared memory only)
 //
 // Everything a colour step touches lives in shared memory: `rec` / `svOff` are byte offsets into
-// the dynamic shared array, so every access below is an LDS/STS.  The record of a thread's
-// constraint in the NEXT colour group (indices, rest value, lambda: never written by another
-// thread) is fetched before the block barrier; after the barrier the dependent chain is
-// LDS.128 vertices -> arithmetic -> STS.128 -> barrier.
+// the dynamic shared array, so every access below is an LDS/STS.  The dependent chain of a
+// colour step is LDS record -> LDS.128 vertices -> arithmetic -> STS.128 -> block barrier.
 
 PBD_SWEEP_INLINE void sweep_edges(const TileHdr& h, uint32_t rec, uint32_t svOff, float alpha, long long* ft) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -65,26 +58,15 @@ PBD_SWEEP_INLINE void sweep_edges(const TileHdr& h, uint32_t rec, uint32_t svOff
       lam[e] = nl;
     }
   };
-  uint2 gd = groups[0];
-  uint32_t e = gd.x + tid, id = 0;
-  float r = 0.0f, l = 0.0f;
-  bool have = tid < gd.y;
-  if (have) { id = idx[e]; r = rest[e]; l = lam[e]; }
+  // (Fetching a thread's next record before the barrier was measured: no gain, more registers.)
   for (uint32_t g = 0; g < n; ++g) {
-    const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 0u);
-    if (have) project(e, id, r, l);
-#ifdef PBD_SWEEP_OVERFLOW   // the planner keeps every group within one block pass (pbd_tileplan.cpp)
-    for (uint32_t i = tid + nth; i < gd.y; i += nth) {   // colour groups larger than the block
-      const uint32_t e2 = gd.x + i;
-      project(e2, idx[e2], rest[e2], lam[e2]);
+    const uint2 gd = groups[g];
+    if (tid < gd.y) {   // the planner keeps every group within one pass of the block
+      const uint32_t e = gd.x + tid;
+      project(e, idx[e], rest[e], lam[e]);
     }
-#endif
-    e = gn.x + tid;
-    have = tid < gn.y;
-    if (have) { id = idx[e]; r = rest[e]; l = lam[e]; }
     __syncthreads();
     PBD_STEP_TRACE(ft, g, gd.y);
-    gd = gn;
   }
 }
 
@@ -116,27 +98,14 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
         lam[t] = nl;
       }
     };
-    uint2 gd = groups[0];
-    uint32_t t = gd.x + tid;
-    uint2 id = make_uint2(0u, 0u);
-    float r = 0.0f, l = 0.0f;
-    bool have = tid < gd.y;
-    if (have) { id = idx[t]; r = rest[t]; l = lam[t]; }
     for (uint32_t g = 0; g < n; ++g) {
-      const uint2 gn = (g + 1 < n) ? groups[g + 1] : make_uint2(0u, 0u);
-      if (have) project(t, id, r, l);
-#ifdef PBD_SWEEP_OVERFLOW
-      for (uint32_t i = tid + nth; i < gd.y; i += nth) {
-        const uint32_t t2 = gd.x + i;
-        project(t2, idx[t2], rest[t2], lam[t2]);
+      const uint2 gd = groups[g];
+      if (tid < gd.y) {
+        const uint32_t t = gd.x + tid;
+        project(t, idx[t], rest[t], lam[t]);
       }
-#endif
-      t = gn.x + tid;
-      have = tid < gn.y;
-      if (have) { id = idx[t]; r = rest[t]; l = lam[t]; }
       __syncthreads();
       PBD_STEP_TRACE(ft, g, gd.y);
-      gd = gn;
     }
   } else if (LANES == 2) {
     // Two adjacent lanes per tet.  Lane A (even) owns vertices a, b and computes ga, gb; lane B
