@@ -18,6 +18,13 @@ namespace pbd {
 #ifndef PBD_SWEEP_INLINE
 #define PBD_SWEEP_INLINE static __device__ __forceinline__
 #endif
+// per-step clock stamps for PBD_TILE_TRACE (compiled in only with -DPBD_TRACE_STEPS: even a
+// predicated-off stamp per colour step costs measurable time in these loops)
+#ifdef PBD_TRACE_STEPS
+#define PBD_STEP_TRACE(ft, g, n) do { if ((ft) && (g) < 40) { (ft)[16 + (g)] = clock64(); (ft)[56 + (g)] = (n); } } while (0)
+#else
+#define PBD_STEP_TRACE(ft, g, n) do { (void)(ft); } while (0)
+#endif
 #ifndef PBD_SWEEP_INLINE
 #define PBD_SWEEP_INLINE static __device__ __noinline__
 #endif
