@@ -345,6 +345,10 @@ void pbdo_get(const pbdo_state *s, int what, void *out) {
   }
 }
 
+/* a later MSG_INIT would rebuild the state; the C ABI also lets a caller change SolverParams in
+ * place (pbd_set_params) -- mirrored here so that path can be checked */
+void pbdo_set_params(pbdo_state *s, const pbdo_params *prm) { s->prm = *prm; }
+
 void pbdo_set_inv_mass(pbdo_state *s, const float *w) { memcpy(s->w, w, sizeof(float) * s->V); }
 
 void pbdo_stats(pbdo_state *s, double *out5, int reset) {

@@ -130,6 +130,14 @@ class Oracle:
         for _ in range(frames):
             self._f("step")(self.h, C.c_float(dt))
 
+    def set_params(self, params: "Params"):
+        assert self.kind == "port"
+        f = self._f("set_params")
+        f.argtypes = [C.c_void_p, C.POINTER(Params)]
+        f.restype = None
+        f(self.h, C.byref(params))
+        self.params = params
+
     def step_sequence(self, dt: float, items):
         assert self.kind == "port"
         items = np.ascontiguousarray(items, dtype=np.uint32)

@@ -373,3 +373,26 @@ def test_batch_many_identical_bodies_and_limits(capi, po, meshgen):
     with capi.Batch(capi.SolverParams.default(), [], device=0) as empty:
         empty.step(1 / 60)
         assert empty.read_positions().shape == (0, 3)
+
+
+@pytest.mark.parametrize("order", ["strict", "interleaved"])
+def test_set_params_between_frames_bit_exact(order, capi, po, meshgen):
+    """pbd_set_params changes substeps / iterations / compliances between frames; the tile backend's
+    done counters keep counting across frames of different shapes (they are never reset)."""
+    x0, tets, edges = meshgen.kuhn_grid(8)
+    om = capi.ORDER_INTERLEAVED if order == "interleaved" else capi.ORDER_STRICT
+    body = capi.Body(capi.SolverParams.default(substeps=3), x0, edges, tets, device=0,
+                     options=capi.Options(backend=capi.BACKEND_TILE, order_mode=om, tile_vertices=120))
+    ora = po.Oracle(po.Params.default(substeps=3), x0, edges, tets, kind="port")
+    ora.permute_constraints(*body.schedule_order())
+    seq = body.schedule_sequence()
+    shapes = [dict(substeps=3, iterations=6), dict(substeps=1, iterations=2), dict(substeps=5, iterations=0),
+              dict(substeps=2, iterations=7, edgeCompliance=1e-4, friction=0.5), dict(substeps=4, iterations=3)]
+    for kw in shapes:
+        body.set_params(capi.SolverParams.default(**kw))
+        ora.set_params(po.Params.default(**kw))
+        for _ in range(4):
+            body.step(1 / 60)
+            ora.step_sequence(1 / 60, seq)
+        _assert_state_equal(capi, po, body, ora, f"after set_params({kw})")
+    body.close()
