@@ -540,38 +540,85 @@ void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vecto
 // tile-local vertex indices of each role differ modulo 8.  Greedy: fill one quarter-warp at a
 // time with the first remaining constraints whose indices are still free in every role.  The
 // order inside a colour group never changes the result (its constraints share no vertex).
+std::atomic<uint64_t> g_bankWavefronts{0}, g_bankIdeal{0};   // PBD_PLAN_DEBUG statistics
+
 void bank_order(const CSet& cs, const std::vector<uint32_t>& localOf, uint32_t* cons, uint32_t n) {
   if (n <= 1) return;
-  std::vector<uint32_t> rest(cons, cons + n), out;
+  const uint32_t ar = cs.arity;
+  std::vector<uint32_t> item(cons, cons + n), out;
   out.reserve(n);
-  std::vector<uint8_t> taken(n, 0);
-  uint32_t firstFree = 0, left = n;
-  while (left) {
-    uint8_t used[4] = {0, 0, 0, 0};
-    uint32_t filled = 0;
-    for (uint32_t i = firstFree; i < n && filled < 8; ++i) {
-      if (taken[i]) continue;
-      const uint32_t* id = cs.at(rest[i]);
-      bool ok = true;
-      for (uint32_t r = 0; r < cs.arity && ok; ++r) ok = !(used[r] >> (localOf[id[r]] & 7u) & 1u);
-      if (!ok) continue;
-      for (uint32_t r = 0; r < cs.arity; ++r) used[r] |= (uint8_t)(1u << (localOf[id[r]] & 7u));
-      taken[i] = 1;
-      out.push_back(rest[i]);
-      ++filled;
-      --left;
+  // residues of every constraint, one byte per role
+  std::vector<uint8_t> res((size_t)n * 4, 0);
+  for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t r = 0; r < ar; ++r) res[(size_t)i * 4 + r] = (uint8_t)(localOf[cs.at(item[i])[r]] & 7u);
+  std::vector<uint32_t> alive(n);   // indices into item[] not placed yet
+  std::iota(alive.begin(), alive.end(), 0u);
+  uint32_t lcg = 0x2545f491u;
+  std::vector<uint32_t> row, bestRow, perm;
+  while (!alive.empty()) {
+    const uint32_t m = (uint32_t)alive.size();
+    if (m <= 8) {   // last (partial) row: whatever is left
+      for (uint32_t a2 : alive) out.push_back(item[a2]);
+      break;
     }
-    // nothing compatible is left for the open lanes of this quarter-warp: fill them in order
-    for (uint32_t i = firstFree; i < n && filled < 8 && left; ++i) {
-      if (taken[i]) continue;
-      taken[i] = 1;
-      out.push_back(rest[i]);
-      ++filled;
-      --left;
+    bestRow.clear();
+    // randomised greedy with restarts: scan the remaining constraints from a pseudo-random start
+    // with a pseudo-random odd stride (a permutation of the indices when m is a power of two; in
+    // general most indices) and collect constraints whose residues are free in every role
+    const int tries = 24;
+    for (int tr = 0; tr < tries && bestRow.size() < 8; ++tr) {
+      lcg = lcg * 1664525u + 1013904223u;
+      const uint32_t start = (lcg >> 8) % m;
+      row.clear();
+      uint8_t used[4] = {0, 0, 0, 0};
+      for (uint32_t q = 0; q < m && row.size() < 8; ++q) {
+        const uint32_t a2 = alive[(start + q) % m];
+        const uint8_t* rs = &res[(size_t)a2 * 4];
+        bool ok = true;
+        for (uint32_t r = 0; r < ar && ok; ++r) ok = !(used[r] >> rs[r] & 1u);
+        if (!ok) continue;
+        for (uint32_t r = 0; r < ar; ++r) used[r] |= (uint8_t)(1u << rs[r]);
+        row.push_back(a2);
+      }
+      if (row.size() > bestRow.size()) bestRow = row;
     }
-    while (firstFree < n && taken[firstFree]) ++firstFree;
+    // complete a partial row with the constraints that add the fewest collisions
+    if (bestRow.size() < 8) {
+      uint8_t cnt[4][8] = {};
+      std::vector<uint8_t> inRow(n, 0);
+      for (uint32_t a2 : bestRow) { inRow[a2] = 1; for (uint32_t r = 0; r < ar; ++r) cnt[r][res[(size_t)a2 * 4 + r]]++; }
+      while (bestRow.size() < 8) {
+        uint32_t pick = 0xffffffffu, pickCost = 0xffffffffu;
+        for (uint32_t a2 : alive) {
+          if (inRow[a2]) continue;
+          uint32_t cost = 0;
+          for (uint32_t r = 0; r < ar; ++r) cost += cnt[r][res[(size_t)a2 * 4 + r]];
+          if (cost < pickCost) { pickCost = cost; pick = a2; }
+        }
+        if (pick == 0xffffffffu) break;
+        inRow[pick] = 1;
+        for (uint32_t r = 0; r < ar; ++r) cnt[r][res[(size_t)pick * 4 + r]]++;
+        bestRow.push_back(pick);
+      }
+    }
+    std::vector<uint8_t> gone(n, 0);
+    for (uint32_t a2 : bestRow) { out.push_back(item[a2]); gone[a2] = 1; }
+    alive.erase(std::remove_if(alive.begin(), alive.end(), [&](uint32_t a2) { return gone[a2] != 0; }), alive.end());
   }
   std::copy(out.begin(), out.end(), cons);
+  if (getenv("PBD_PLAN_DEBUG")) {
+    uint64_t wf = 0, ideal = 0;
+    for (uint32_t q0 = 0; q0 < n; q0 += 8)
+      for (uint32_t r = 0; r < ar; ++r) {
+        uint8_t cnt[8] = {};
+        uint8_t mx = 0;
+        for (uint32_t q = q0; q < std::min(n, q0 + 8); ++q) mx = std::max<uint8_t>(mx, ++cnt[localOf[cs.at(cons[q])[r]] & 7u]);
+        wf += mx;
+        ++ideal;
+      }
+    g_bankWavefronts += wf;
+    g_bankIdeal += ideal;
+  }
 }
 
 // Finish a tile: vertex list (gathered tiles: the slots its constraints touch), local numbering,
@@ -1184,6 +1231,9 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     break;
   }
   plan.planMs = now_ms() - t0;
+  if (getenv("PBD_PLAN_DEBUG"))
+    fprintf(stderr, "[plan] shared-memory gathers: %.3f wavefronts per quarter-warp role (1.0 = conflict-free)\n",
+            (double)g_bankWavefronts.exchange(0) / (double)std::max<uint64_t>(1, g_bankIdeal.exchange(0)));
   return true;
 }
 
