@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
               // entry: tile (bits 0..23) | owner rank (24..27) | bit 31 = written earlier in THIS iteration
               const uint32_t e = reinterpret_cast<const uint32_t*>(rec + 64)[tid];
               const uint32_t need = P.iterBase + sub * P.iterations + it + (e >> 31);
-              const unsigned* f = donePeerS[(e >> 24) & 0xfu] + (e & 0xffffffu);
-              if (multi) { while (ld_acquire_sys(f) < need) {} } else { while (ld_acquire(f) < need) {} }
+              const uint32_t own = (e >> 24) & 0xfu;
+              const unsigned* f = donePeerS[own] + (e & 0xffffffu);
+              if (multi && own != P.rank) { while (ld_acquire_sys(f) < need) {} } else { while (ld_acquire(f) < need) {} }
             }
             __syncthreads();
           }
@@ -304,7 +305,9 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             if (nItems == 1) bulk_wait_read();   // the block stays resident and is swept again next iteration
             if (P.done) {   // my vertices are in L2 (of their owners)
               const uint32_t v = P.iterBase + sub * P.iterations + it + 1u;
-              if (multi) st_release_sys(P.done + itemTile[j], v); else st_release(P.done + itemTile[j], v);
+              // system scope only when another GPU reads this counter or holds vertices this tile
+              // wrote (flags bit 1): a system-scope release costs several microseconds
+              if (multi && (h.flags & 2u)) st_release_sys(P.done + itemTile[j], v); else st_release(P.done + itemTile[j], v);
             }
           }
           if (nItems == 1) {
@@ -332,8 +335,9 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
       const uint32_t np = (__ldg(hdr + 1) >> 8) & 0xffu;
       if (tid < np) {
         const uint32_t e = __ldg(hdr + 16 + tid);
-        const unsigned* f = donePeerS[(e >> 24) & 0xfu] + (e & 0xffffffu);
-        if (multi) { while (ld_acquire_sys(f) < need) {} } else { while (ld_acquire(f) < need) {} }
+        const uint32_t own = (e >> 24) & 0xfu;
+        const unsigned* f = donePeerS[own] + (e & 0xffffffu);
+        if (multi && own != P.rank) { while (ld_acquire_sys(f) < need) {} } else { while (ld_acquire(f) < need) {} }
       }
     }
     __syncthreads();
@@ -428,6 +432,21 @@ class TileBackend final : public Backend {
     useFlags_ = flagsOk;
     if (world_ > 1 && !useFlags_) return cudaErrorNotSupported;   // several GPUs cannot share a grid barrier
 
+    // A tile that talks to another GPU (a predecessor or a vertex there) goes to the front of its
+    // phase's list, i.e. into the first wave of CTAs: its peers on the other rank are first in line
+    // too, so the NVLink round trips overlap with the rank's interior tiles instead of ending the phase.
+    std::vector<uint8_t> remote(plan.tiles.size(), 0);
+    if (world_ > 1)
+      for (size_t ti = 0; ti < plan.tiles.size(); ++ti) {
+        const Tile& t = plan.tiles[ti];
+        for (uint32_t e : preds[ti]) remote[ti] |= ((e >> 24) & 0xfu) != rank_;
+        if (!t.contiguous)
+          for (uint32_t i = 0; i < t.vertCount && !remote[ti]; ++i) remote[ti] |= owner_of_slot(plan.tileVerts[t.vertBegin + i]) != rank_;
+      }
+    for (uint32_t ti = 0; ti < plan.tiles.size(); ++ti)   // ... and so does a tile another rank waits for
+      for (uint32_t e : preds[ti])
+        if (tileOwner[ti] != tileOwner[e & 0xffffffu]) remote[e & 0xffffffu] = 1;
+
     // ---- record blocks
     std::vector<TileCopy> copies(plan.tiles.size());
     std::vector<unsigned char> blob;
@@ -437,7 +456,7 @@ class TileBackend final : public Backend {
       const uint32_t nVG = t.contiguous ? 0u : t.vertCount;
       TileHdr h{};
       const uint32_t nPred = useFlags_ ? (uint32_t)preds[ti].size() : 0u;
-      h.vertCount = t.vertCount; h.flags = (t.contiguous ? 1u : 0u) | (nPred << 8); h.vertBegin = t.contiguous ? t.vertBegin : 0u;
+      h.vertCount = t.vertCount; h.flags = (t.contiguous ? 1u : 0u) | (remote[ti] ? 2u : 0u) | (nPred << 8); h.vertBegin = t.contiguous ? t.vertBegin : 0u;
       h.nEdgeGroups = t.edgeGroupCount; h.nTetGroups = t.tetGroupCount; h.nEdges = t.edgeCount; h.nTets = t.tetCount;
       uint32_t off = 64 + 4u * kMaxPreds;
       h.offVertIdx = off; off += 4u * pad4(nVG);
@@ -528,13 +547,19 @@ class TileBackend final : public Backend {
     maxTilesPerPhase_ = 0;
     for (size_t i = 0; i < pd.size(); ++i) {
       pd[i].tileBegin = (uint32_t)tileList.size();
-      for (uint32_t ti = plan.phases[i].tileBegin; ti < plan.phases[i].tileBegin + plan.phases[i].tileCount; ++ti)
-        if (tileOwner[ti] == rank_) tileList.push_back(ti);
+      for (int pass = 1; pass >= 0; --pass)
+        for (uint32_t ti = plan.phases[i].tileBegin; ti < plan.phases[i].tileBegin + plan.phases[i].tileCount; ++ti)
+          if (tileOwner[ti] == rank_ && remote[ti] == pass) tileList.push_back(ti);
       pd[i].tileCount = (uint32_t)tileList.size() - pd[i].tileBegin;
       maxTilesPerPhase_ = std::max(maxTilesPerPhase_, pd[i].tileCount);
     }
-    for (uint32_t t = 0; t < nTile0_; ++t)
-      if (homeOwner_[t] == rank_) homeList.push_back(t);
+    if (!pd.empty()) {
+      // phase 0 = my home tiles, in the order just chosen (the final commit walks homeList)
+      for (uint32_t q = 0; q < pd[0].tileCount; ++q) homeList.push_back(tileList[pd[0].tileBegin + q] - plan.phases[0].tileBegin);
+    } else {
+      for (uint32_t t = 0; t < nTile0_; ++t)
+        if (homeOwner_[t] == rank_) homeList.push_back(t);
+    }
     nHome_ = (uint32_t)homeList.size();
     maxTilesPerPhase_ = std::max(maxTilesPerPhase_, nHome_);
     auto up = [&](auto** dst, const auto& src) -> cudaError_t {
