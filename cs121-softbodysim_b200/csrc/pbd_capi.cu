@@ -362,6 +362,15 @@ static int plan_sequence(const Plan& p, uint32_t* items) {
   for (const Phase& ph : p.phases)
     for (uint32_t t = ph.tileBegin; t < ph.tileBegin + ph.tileCount; ++t) {
       const Tile& tl = p.tiles[t];
+      if (tl.mixed) {   // colour step s = edge group s, then tet group s (vertex-disjoint: any order inside a step is the same)
+        for (uint32_t g = 0; g < tl.edgeGroupCount; ++g) {
+          const Group& ge = p.groups[tl.edgeGroupBegin + g];
+          const Group& gt = p.groups[tl.tetGroupBegin + g];
+          for (uint32_t j = 0; j < ge.count; ++j) items[n++] = ge.begin + j;
+          for (uint32_t j = 0; j < gt.count; ++j) items[n++] = 0x80000000u | (gt.begin + j);
+        }
+        continue;
+      }
       for (uint32_t j = 0; j < tl.edgeCount; ++j) items[n++] = tl.edgeBegin + j;
       for (uint32_t j = 0; j < tl.tetCount; ++j) items[n++] = 0x80000000u | (tl.tetBegin + j);
     }

@@ -37,7 +37,8 @@ struct Group {
 
 // One (phase, tile): a set of vertices that fits in one SM's shared memory together with the
 // constraints projected on it in this phase.  A tile may carry edges, tets or both; its edge colour
-// groups run first, then its tet colour groups.
+// groups run first, then its tet colour groups -- or, `mixed`, step s runs edge group s and tet
+// group s together.
 struct Tile {
   uint32_t vertBegin = 0;   // into Plan::tileVerts (device vertex slots), or a contiguous range
   uint32_t vertCount = 0;
@@ -47,6 +48,7 @@ struct Tile {
   uint32_t edgeGroupBegin = 0, edgeGroupCount = 0;  // into Plan::groups (one group per local colour)
   uint32_t tetGroupBegin = 0, tetGroupCount = 0;
   uint32_t edgeDevBegin = 0, tetDevBegin = 0;       // first device index (16-byte aligned ranges)
+  uint32_t mixed = 0;       // 1: edge group s and tet group s form colour step s of the visit (same group count, vertex-disjoint)
 };
 
 struct Phase {

@@ -31,7 +31,7 @@ namespace pbd {
 
 // first 64 bytes of a tile's record block (shared memory); offsets in bytes from the block start
 struct TileHdr {
-  uint32_t vertCount, flags, vertBegin, nEdgeGroups;   // flags: bit 0 = contiguous slot range, bits 8..15 = predecessor count
+  uint32_t vertCount, flags, vertBegin, nEdgeGroups;   // flags: bit 0 = contiguous slot range, bit 1 = system-scope sync, bit 2 = mixed steps, bits 8..15 = predecessor count
   uint32_t nTetGroups, nEdges, nTets, offVertIdx;
   uint32_t offEdgeGroups, offTetGroups, offEdgeIdx, offEdgeRest;
   uint32_t offTetIdx, offTetRest, offEdgeLam, offTetLam;
@@ -255,6 +255,57 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
       PBD_STEP_TRACE(ft, g, gd.y);
       gd = gn;
     }
+  }
+}
+
+// Mixed colour steps (interleaved order, one thread per constraint): the planner coloured the
+// tile's edges and tets TOGETHER, so step s projects edge group s on the block's first threads and
+// tet group s on its last threads -- all vertex-disjoint -- before one block barrier.  The two
+// groups sit in different warps and their sum fits the block (pbd_tileplan.cpp::colour_joint).
+// A visit then needs about max-joint-vertex-load steps instead of edge colours + tet colours, and
+// the warps a tet-only step would leave idle carry the edge work.
+PBD_SWEEP_INLINE void sweep_mixed(const TileHdr& h, uint32_t rec, uint32_t svOff, float alphaE, float alphaT,
+                                  long long* ft) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t n = h.nEdgeGroups;   // == h.nTetGroups
+  if (n == 0) return;
+  const uint2* eGroups = reinterpret_cast<const uint2*>(smem + rec + h.offEdgeGroups);
+  const uint2* tGroups = reinterpret_cast<const uint2*>(smem + rec + h.offTetGroups);
+  const uint32_t* eIdx = reinterpret_cast<const uint32_t*>(smem + rec + h.offEdgeIdx);
+  const float* eRest = reinterpret_cast<const float*>(smem + rec + h.offEdgeRest);
+  float* eLam = reinterpret_cast<float*>(smem + rec + h.offEdgeLam);
+  const uint2* tIdx = reinterpret_cast<const uint2*>(smem + rec + h.offTetIdx);
+  const float* tRest = reinterpret_cast<const float*>(smem + rec + h.offTetRest);
+  float* tLam = reinterpret_cast<float*>(smem + rec + h.offTetLam);
+  float4* sv = reinterpret_cast<float4*>(smem + svOff);
+  const uint32_t tid = threadIdx.x, rtid = blockDim.x - 1u - tid;   // tets are counted from the block's last thread
+  for (uint32_t g = 0; g < n; ++g) {
+    const uint2 ge = eGroups[g], gt = tGroups[g];
+    if (tid < ge.y) {
+      const uint32_t e = ge.x + tid;
+      const uint32_t id = eIdx[e];
+      const uint32_t a = id & 0xffffu, b = id >> 16;
+      const float4 p0 = sv[a], p1 = sv[b];
+      float4 q0, q1;
+      float nl;
+      if (edge_delta(p0, p1, eRest[e], eLam[e], alphaE, q0, q1, nl)) {
+        sv[a] = q0;
+        sv[b] = q1;
+        eLam[e] = nl;
+      }
+    } else if (rtid < gt.y) {
+      const uint32_t t = gt.x + rtid;
+      const uint2 id = tIdx[t];
+      const uint32_t a = id.x & 0xffffu, b = id.x >> 16, c = id.y & 0xffffu, d = id.y >> 16;
+      float4 pa = sv[a], pb = sv[b], pc = sv[c], pd = sv[d];
+      float nl;
+      if (tet_delta(pa, pb, pc, pd, tRest[t], tLam[t], alphaT, nl)) {
+        sv[a] = pa; sv[b] = pb; sv[c] = pc; sv[d] = pd;
+        tLam[t] = nl;
+      }
+    }
+    __syncthreads();
+    PBD_STEP_TRACE(ft, g, ge.y + (gt.y << 16));
   }
 }
 

@@ -284,9 +284,14 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             const long long t0 = clock64();
             while (clock64() - t0 < (long long)stagger) {}
           }
-          sweep_edges(h, recOff, svOff, k.alphaEdge, ft);
-          if (ft) ft[3] = clock64();
-          sweep_tets<LANES>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr);
+          if (LANES == 1 && (h.flags & 4u)) {
+            sweep_mixed(h, recOff, svOff, k.alphaEdge, k.alphaTet, ft);   // edges and tets share the colour steps
+            if (ft) ft[3] = clock64();
+          } else {
+            sweep_edges(h, recOff, svOff, k.alphaEdge, ft);
+            if (ft) ft[3] = clock64();
+            sweep_tets<LANES>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr);
+          }
           if (ft) ft[4] = clock64();
           // ---- write back
           if (contiguous) {
@@ -456,7 +461,7 @@ class TileBackend final : public Backend {
       const uint32_t nVG = t.contiguous ? 0u : t.vertCount;
       TileHdr h{};
       const uint32_t nPred = useFlags_ ? (uint32_t)preds[ti].size() : 0u;
-      h.vertCount = t.vertCount; h.flags = (t.contiguous ? 1u : 0u) | (remote[ti] ? 2u : 0u) | (nPred << 8); h.vertBegin = t.contiguous ? t.vertBegin : 0u;
+      h.vertCount = t.vertCount; h.flags = (t.contiguous ? 1u : 0u) | (remote[ti] ? 2u : 0u) | (t.mixed ? 4u : 0u) | (nPred << 8); h.vertBegin = t.contiguous ? t.vertBegin : 0u;
       h.nEdgeGroups = t.edgeGroupCount; h.nTetGroups = t.tetGroupCount; h.nEdges = t.edgeCount; h.nTets = t.tetCount;
       uint32_t off = 64 + 4u * kMaxPreds;
       h.offVertIdx = off; off += 4u * pad4(nVG);

@@ -365,9 +365,9 @@ struct TileBuild {
   uint32_t rangeBegin = 0, rangeCount = 0;   // contiguous tiles
   std::vector<uint32_t> verts;               // gathered tiles: slots, ascending
   TypeList ty[2];                            // 0 = edges, 1 = tets
+  bool mixed = false;                        // both lists share ONE colouring: colour s of either type = step s of the visit
 };
 
-// colour the constraints of one tile locally and sort them by (colour, id)
 // Try to empty the highest colour classes: move each of their constraints to a lower colour that
 // is free at all its vertices, or that is blocked by a single constraint which can itself move
 // to another free lower colour.  `ids` are tile-local vertex indices, arity per constraint.
@@ -453,20 +453,30 @@ uint32_t reduce_colours(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_
   return top;
 }
 
-// colour the constraints of one tile locally and sort them by (colour, id)
-void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vector<uint32_t>& localOf,
-                 std::vector<uint32_t>& scratch, int maxIter = 48, uint32_t goal = 0, uint32_t seed = 0x9e3779b9u) {
-  const uint32_t n = (uint32_t)tl.cons.size();
-  std::sort(tl.cons.begin(), tl.cons.end());
-  // visiting order: most constrained first (largest vertex degree inside the tile), then id
+// Colour n constraints given by their tile-local vertex indices (`arity` per constraint, caller's
+// order; a constraint may list a vertex more than once).  col[i] receives the colour of
+// constraint i; returns the number of colours.  Largest-degree-first greedy, the recolouring pass
+// above, then iterated greedy.
+uint32_t colour_ids(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nLocal, std::vector<uint32_t>& col,
+                    std::vector<uint32_t>& scratch, int maxIter, uint32_t goal, uint32_t seed) {
+  col.assign(n, 0);
+  if (n == 0) return 0;
+  auto repeated = [&](uint32_t i, uint32_t j) {   // vertex j of constraint i already listed at an earlier position
+    for (uint32_t q = 0; q < j; ++q)
+      if (ids[(size_t)i * arity + q] == ids[(size_t)i * arity + j]) return true;
+    return false;
+  };
+  // visiting order: most constrained first (largest vertex degree inside the tile), then caller's order
   std::vector<uint32_t> deg(nLocal, 0);
   for (uint32_t i = 0; i < n; ++i)
-    for (uint32_t j = 0; j < cs.arity; ++j) deg[localOf[cs.at(tl.cons[i])[j]]]++;
+    for (uint32_t j = 0; j < arity; ++j)
+      if (!repeated(i, j)) deg[ids[(size_t)i * arity + j]]++;
   std::vector<uint32_t> key(n), visit(n);
   for (uint32_t i = 0; i < n; ++i) {
     uint32_t mx = 0, sum = 0;
-    for (uint32_t j = 0; j < cs.arity; ++j) {
-      const uint32_t d = deg[localOf[cs.at(tl.cons[i])[j]]];
+    for (uint32_t j = 0; j < arity; ++j) {
+      if (repeated(i, j)) continue;
+      const uint32_t d = deg[ids[(size_t)i * arity + j]];
       mx = std::max(mx, d);
       sum += d;
     }
@@ -474,12 +484,12 @@ void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vecto
   }
   std::iota(visit.begin(), visit.end(), 0u);
   std::stable_sort(visit.begin(), visit.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
-  scratch.resize((size_t)n * cs.arity);
+  scratch.resize((size_t)n * arity);
   for (uint32_t i = 0; i < n; ++i)
-    for (uint32_t j = 0; j < cs.arity; ++j) scratch[(size_t)i * cs.arity + j] = localOf[cs.at(tl.cons[visit[i]])[j]];
+    for (uint32_t j = 0; j < arity; ++j) scratch[(size_t)i * arity + j] = ids[(size_t)visit[i] * arity + j];
   std::vector<uint32_t> colV;
-  uint32_t nc = greedy_colour(scratch.data(), n, cs.arity, nLocal, colV);
-  nc = reduce_colours(scratch.data(), n, cs.arity, nLocal, colV, nc);
+  uint32_t nc = greedy_colour(scratch.data(), n, arity, nLocal, colV);
+  nc = reduce_colours(scratch.data(), n, arity, nLocal, colV, nc);
   // Iterated greedy (Culberson): re-run first-fit with the constraints grouped by their current
   // colour class and the classes permuted -- never needs more colours than before, often fewer --
   // alternating with the recolouring pass, until the vertex-degree lower bound is met or the
@@ -487,7 +497,7 @@ void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vecto
   uint32_t maxDeg = 0;
   for (uint32_t v = 0; v < nLocal; ++v) maxDeg = std::max(maxDeg, deg[v]);
   {
-    std::vector<uint32_t> ids2((size_t)n * cs.arity), perm(n), col2, classOrder, classStart;
+    std::vector<uint32_t> ids2((size_t)n * arity), perm(n), col2, classOrder, classStart;
     uint32_t lcg = seed, stale = 0;
     const uint32_t stop = std::max(maxDeg, goal);
     const uint32_t staleMax = maxIter > 48 ? (uint32_t)maxIter : 12u;
@@ -511,9 +521,9 @@ void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vecto
       std::iota(perm.begin(), perm.end(), 0u);
       std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return rank[colV[a]] < rank[colV[b]]; });
       for (uint32_t i = 0; i < n; ++i)
-        for (uint32_t j = 0; j < cs.arity; ++j) ids2[(size_t)i * cs.arity + j] = scratch[(size_t)perm[i] * cs.arity + j];
-      uint32_t nc2 = greedy_colour(ids2.data(), n, cs.arity, nLocal, col2);
-      nc2 = reduce_colours(ids2.data(), n, cs.arity, nLocal, col2, nc2);
+        for (uint32_t j = 0; j < arity; ++j) ids2[(size_t)i * arity + j] = scratch[(size_t)perm[i] * arity + j];
+      uint32_t nc2 = greedy_colour(ids2.data(), n, arity, nLocal, col2);
+      nc2 = reduce_colours(ids2.data(), n, arity, nLocal, col2, nc2);
       if (nc2 <= nc) {
         stale = nc2 < nc ? 0 : stale + 1;
         nc = nc2;
@@ -523,9 +533,14 @@ void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vecto
       }
     }
   }
-  std::vector<uint32_t> col(n);
   for (uint32_t i = 0; i < n; ++i) col[visit[i]] = colV[i];
-  tl.nColours = nc;
+  return nc;
+}
+
+// sort a tile's constraint list by (colour, id) given the colours of its current order
+void sort_by_colour(TypeList& tl, const std::vector<uint32_t>& col, uint32_t nColours) {
+  const uint32_t n = (uint32_t)tl.cons.size();
+  tl.nColours = nColours;
   std::vector<uint32_t> order(n);
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return col[a] < col[b]; });
@@ -533,6 +548,107 @@ void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vecto
   for (uint32_t i = 0; i < n; ++i) { c2[i] = tl.cons[order[i]]; k2[i] = col[order[i]]; }
   tl.cons.swap(c2);
   tl.colour.swap(k2);
+}
+
+// colour the constraints of one tile locally and sort them by (colour, id)
+void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vector<uint32_t>& localOf,
+                 std::vector<uint32_t>& scratch, int maxIter = 48, uint32_t goal = 0, uint32_t seed = 0x9e3779b9u) {
+  const uint32_t n = (uint32_t)tl.cons.size();
+  std::sort(tl.cons.begin(), tl.cons.end());
+  std::vector<uint32_t> ids((size_t)n * cs.arity), col;
+  for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t j = 0; j < cs.arity; ++j) ids[(size_t)i * cs.arity + j] = localOf[cs.at(tl.cons[i])[j]];
+  const uint32_t nc = colour_ids(ids.data(), n, cs.arity, nLocal, col, scratch, maxIter, goal, seed);
+  sort_by_colour(tl, col, nc);
+}
+
+// Mixed steps (interleaved order, one thread per constraint): colour a tile's edges AND tets
+// together, so that one colour step of the visit projects a vertex-disjoint set of edges (the
+// block's first warps) and tets (its last warps) at the same time.  A visit then takes about
+// max-joint-vertex-load steps instead of (edge colours + tet colours), and the warps a tet-only
+// step leaves idle do edge work.  `threads` = block size: a step holds at most that many threads,
+// edges and tets in separate warps.  Afterwards both lists are sorted by (step, id) and
+// ty[0].nColours == ty[1].nColours == number of steps.
+void colour_joint(const CSet sets[2], TileBuild& tb, uint32_t nLocal, const std::vector<uint32_t>& localOf,
+                  std::vector<uint32_t>& scratch, uint32_t threads, int maxIter = 48, uint32_t goal = 0,
+                  uint32_t seed = 0x9e3779b9u) {
+  TypeList& LE = tb.ty[0];
+  TypeList& LT = tb.ty[1];
+  std::sort(LE.cons.begin(), LE.cons.end());
+  std::sort(LT.cons.begin(), LT.cons.end());
+  const uint32_t nT = (uint32_t)LT.cons.size(), nE = (uint32_t)LE.cons.size(), n = nT + nE;
+  // joint list: tets first, then edges as (a, b, a, b)
+  std::vector<uint32_t> ids((size_t)n * 4), col;
+  for (uint32_t i = 0; i < nT; ++i)
+    for (uint32_t j = 0; j < 4; ++j) ids[(size_t)i * 4 + j] = localOf[sets[1].at(LT.cons[i])[j]];
+  for (uint32_t i = 0; i < nE; ++i)
+    for (uint32_t j = 0; j < 4; ++j) ids[(size_t)(nT + i) * 4 + j] = localOf[sets[0].at(LE.cons[i])[j & 1u]];
+  uint32_t nc = colour_ids(ids.data(), n, 4, nLocal, col, scratch, maxIter, goal, seed);
+
+  auto pad32 = [](uint32_t x) { return (x + 31u) & ~31u; };
+  if (nc <= 64) {
+    // ---- even out the steps.  A step costs a fixed latency plus issue time that grows with its
+    // warps (a tet ~ twice an edge), and it must fit the block.
+    std::vector<uint64_t> used(nLocal, 0);
+    for (uint32_t k = 0; k < n; ++k)
+      for (uint32_t j = 0; j < 4; ++j) used[ids[(size_t)k * 4 + j]] |= 1ull << col[k];
+    std::vector<uint32_t> cntE(64, 0), cntT(64, 0);
+    for (uint32_t k = 0; k < n; ++k) (k < nT ? cntT : cntE)[col[k]]++;
+    auto cost = [&](uint32_t c) { return cntE[c] + 2u * cntT[c]; };
+    auto fits = [&](uint32_t c, bool tet) { return pad32(cntE[c] + (tet ? 0u : 1u)) + pad32(cntT[c] + (tet ? 1u : 0u)) <= threads; };
+    auto mask_of = [&](uint32_t k) {
+      uint64_t mk = 0;
+      for (uint32_t j = 0; j < 4; ++j) mk |= used[ids[(size_t)k * 4 + j]];
+      return mk;
+    };
+    auto move = [&](uint32_t k, uint32_t d) {
+      const bool tet = k < nT;
+      for (uint32_t j = 0; j < 4; ++j) used[ids[(size_t)k * 4 + j]] &= ~(1ull << col[k]);
+      (tet ? cntT : cntE)[col[k]]--;
+      col[k] = d;
+      for (uint32_t j = 0; j < 4; ++j) used[ids[(size_t)k * 4 + j]] |= 1ull << d;
+      (tet ? cntT : cntE)[d]++;
+    };
+    for (int pass = 0; pass < 6; ++pass) {
+      uint32_t moves = 0;
+      for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t c = col[k], w = k < nT ? 2u : 1u;
+        uint64_t freeMask = ~mask_of(k) & (nc >= 64 ? ~0ull : ((1ull << nc) - 1));
+        uint32_t best = NONE, bestCost = cost(c) - w;   // the target must end cheaper than the source is after the move
+        while (freeMask) {
+          const uint32_t d = (uint32_t)__builtin_ctzll(freeMask);
+          freeMask &= freeMask - 1;
+          if (cost(d) + w < bestCost + 0u && fits(d, k < nT)) { best = d; bestCost = cost(d) + w; }
+        }
+        if (best != NONE) { move(k, best); ++moves; }
+      }
+      if (!moves) break;
+    }
+    // ---- steps that still exceed the block: spill into other free steps, else into a new one
+    for (uint32_t c = 0; c < nc && nc < 64; ++c) {
+      if (pad32(cntE[c]) + pad32(cntT[c]) <= threads) continue;
+      for (uint32_t k = 0; k < n && pad32(cntE[c]) + pad32(cntT[c]) > threads; ++k) {
+        if (col[k] != c) continue;
+        uint64_t freeMask = ~mask_of(k) & ((1ull << nc) - 1);
+        uint32_t best = NONE;
+        while (freeMask) {
+          const uint32_t d = (uint32_t)__builtin_ctzll(freeMask);
+          freeMask &= freeMask - 1;
+          if (fits(d, k < nT) && (best == NONE || cost(d) < cost(best))) best = d;
+        }
+        if (best != NONE) move(k, best);
+      }
+      if (pad32(cntE[c]) + pad32(cntT[c]) > threads && nc < 64) {
+        const uint32_t d = nc++;   // members of one step share no vertex: any subset forms a valid new step
+        for (uint32_t k = 0; k < n && pad32(cntE[c]) + pad32(cntT[c]) > threads; ++k)
+          if (col[k] == c && fits(d, k < nT)) move(k, d);
+      }
+    }
+  }
+  std::vector<uint32_t> colT(col.begin(), col.begin() + nT), colE(col.begin() + nT, col.end());
+  sort_by_colour(LT, colT, nc);
+  sort_by_colour(LE, colE, nc);
+  tb.mixed = true;
 }
 
 // Order the constraints of one colour group so that the shared-memory gathers of a warp do not
@@ -623,7 +739,32 @@ void bank_order(const CSet& cs, const std::vector<uint32_t>& localOf, uint32_t* 
 
 // Finish a tile: vertex list (gathered tiles: the slots its constraints touch), local numbering,
 // colouring of both lists.  localOf is scratch of size V.
-void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& localOf, std::vector<uint32_t>& scratch) {
+// mixedThreads != 0: tiles that carry both types get ONE joint colouring (steps of at most that
+// many threads, see colour_joint).
+bool steps_fit(const TileBuild& tb, uint32_t threads) {
+  std::vector<uint32_t> cnt[2];
+  for (int ty = 0; ty < 2; ++ty) {
+    cnt[ty].assign(tb.ty[ty].nColours, 0);
+    for (uint32_t c : tb.ty[ty].colour) cnt[ty][c]++;
+  }
+  if (cnt[0].size() != cnt[1].size()) return false;
+  for (size_t s = 0; s < cnt[0].size(); ++s)
+    if (((cnt[0][s] + 31u) & ~31u) + ((cnt[1][s] + 31u) & ~31u) > threads) return false;
+  return true;
+}
+
+void order_groups(const CSet sets[2], TileBuild& tb, const std::vector<uint32_t>& localOf, int ty) {
+  TypeList& L = tb.ty[ty];
+  for (size_t i = 0; i < L.cons.size();) {
+    size_t j = i;
+    while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
+    bank_order(sets[ty], localOf, &L.cons[i], (uint32_t)(j - i));
+    i = j;
+  }
+}
+
+void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& localOf, std::vector<uint32_t>& scratch,
+                 uint32_t mixedThreads = 0) {
   uint32_t nLocal;
   if (tb.contiguous) {
     nLocal = tb.rangeCount;
@@ -639,16 +780,16 @@ void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& local
     nLocal = (uint32_t)tb.verts.size();
     for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.verts[i]] = i;
   }
+  tb.mixed = false;
+  if (mixedThreads && !tb.ty[0].cons.empty() && !tb.ty[1].cons.empty()) {
+    colour_joint(sets, tb, nLocal, localOf, scratch, mixedThreads);
+    if (!steps_fit(tb, mixedThreads)) tb.mixed = false;   // (more than 64 joint colours: keep the two sweeps apart)
+  }
   for (int ty = 0; ty < 2; ++ty) {
     TypeList& L = tb.ty[ty];
     if (L.cons.empty()) continue;
-    colour_list(sets[ty], L, nLocal, localOf, scratch);
-    for (size_t i = 0; i < L.cons.size();) {
-      size_t j = i;
-      while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
-      bank_order(sets[ty], localOf, &L.cons[i], (uint32_t)(j - i));
-      i = j;
-    }
+    if (!tb.mixed) colour_list(sets[ty], L, nLocal, localOf, scratch);
+    order_groups(sets, tb, localOf, ty);
   }
 }
 
@@ -751,6 +892,9 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   const uint32_t blockThreads = opts.block_threads ? opts.block_threads : (opts.tiles_per_sm >= 2 ? 256u : 512u);
   if (blockThreads % 32 || blockThreads > 512) { err = "block_threads must be a multiple of 32, <= 512"; return false; }
   plan.blockThreads = blockThreads;
+  // interleaved order, one thread per tet: edges and tets of a tile visit share the colour steps
+  const bool noMixed = getenv("PBD_PLAN_MIXED") && atoi(getenv("PBD_PLAN_MIXED")) == 0;   // debug: A/B against separate sweeps
+  const uint32_t mixedThreads = (fused && opts.lanes_per_tet <= 1 && !noMixed) ? blockThreads : 0u;
   if (opts.partitions > kMaxPartitions) { err = "partitions must be <= 8"; return false; }
 
   // body frame, extents -> axis order for the k-d levels
@@ -868,7 +1012,9 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     std::vector<uint16_t> load((size_t)m.V * K);
     for (int ty = 0; ty < 2; ++ty) {
       const CSet& cs = sets[ty];
-      std::fill(load.begin(), load.end(), (uint16_t)0);
+      // mixed steps: a visit's step count follows the JOINT load of a vertex, so the tets are
+      // balanced on top of the edge loads already placed
+      if (!(mixedThreads && ty == 1 && !getenv("PBD_PLAN_NOJOINTLOAD"))) std::fill(load.begin(), load.end(), (uint16_t)0);
       std::vector<uint8_t> mask(cs.n, 0), phaseOf(cs.n, 0);
       std::vector<uint32_t> bucket[kMaxPartitions + 1];
       for (uint32_t k = 0; k < cs.n; ++k) {
@@ -907,6 +1053,33 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           for (uint32_t j = 0; j < cs.arity; ++j) load[(size_t)id[j] * K + bestP]++;
           phaseOf[k] = (uint8_t)bestP;
         }
+      // potential descent: move a constraint to another admissible phase when that lowers the sum of
+      // squared vertex loads -- evens the loads out where the min-max rule below sees only plateaus
+      for (int sweep = 0; sweep < (getenv("PBD_PLAN_NOPOT") ? 0 : 12); ++sweep) {
+        uint32_t moves = 0;
+        for (uint32_t k = 0; k < cs.n; ++k) {
+          if (mask[k] == 0 || (mask[k] & (mask[k] - 1)) == 0) continue;   // residual or forced
+          const uint32_t* id = cs.at(k);
+          const uint32_t p0 = phaseOf[k];
+          int32_t here = 0;
+          for (uint32_t j = 0; j < cs.arity; ++j) here += load[(size_t)id[j] * K + p0];
+          uint32_t bestP = p0;
+          int32_t bestGain = 0;
+          for (uint32_t p = 0; p < K; ++p) {
+            if (p == p0 || !(mask[k] >> p & 1)) continue;
+            int32_t there = 0;
+            for (uint32_t j = 0; j < cs.arity; ++j) there += load[(size_t)id[j] * K + p];
+            const int32_t gain = here - there - (int32_t)cs.arity;   // = -(delta of the sum of squares) / 2
+            if (gain > bestGain) { bestGain = gain; bestP = p; }
+          }
+          if (bestP != p0) {
+            for (uint32_t j = 0; j < cs.arity; ++j) { load[(size_t)id[j] * K + p0]--; load[(size_t)id[j] * K + bestP]++; }
+            phaseOf[k] = (uint8_t)bestP;
+            ++moves;
+          }
+        }
+        if (!moves) break;
+      }
       // local search: move a constraint to another admissible phase when that lowers the larger
       // of the two peak loads involved (a few sweeps; deterministic)
       for (int sweep = 0; sweep < 6; ++sweep) {
@@ -931,6 +1104,76 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           }
         }
         if (!moves) break;
+      }
+      // peak repair: the colour count of a tile visit follows its most loaded vertex, and after the
+      // passes above only a few vertices per tile sit above the rest.  Lower the ceiling one level
+      // at a time: every constraint on an overloaded (vertex, phase) moves to an admissible phase
+      // with room at all its vertices, if need be after making room there by moving ONE other
+      // constraint away.  Stops at the level that leaves more than one such vertex per tile visit.
+      if (!getenv("PBD_PLAN_NOREPAIR")) {
+        std::vector<uint32_t> incOff((size_t)m.V + 1, 0), inc;
+        for (uint32_t k = 0; k < cs.n; ++k)
+          if (mask[k]) for (uint32_t j = 0; j < cs.arity; ++j) incOff[cs.at(k)[j] + 1]++;
+        for (uint32_t v = 0; v < m.V; ++v) incOff[v + 1] += incOff[v];
+        inc.resize(incOff[m.V]);
+        {
+          std::vector<uint32_t> cur(incOff.begin(), incOff.end() - 1);
+          for (uint32_t k = 0; k < cs.n; ++k)
+            if (mask[k]) for (uint32_t j = 0; j < cs.arity; ++j) inc[cur[cs.at(k)[j]]++] = k;
+        }
+        auto peak_at = [&](uint32_t k, uint32_t p) {
+          uint32_t mxl = 0;
+          for (uint32_t j = 0; j < cs.arity; ++j) mxl = std::max<uint32_t>(mxl, load[(size_t)cs.at(k)[j] * K + p]);
+          return mxl;
+        };
+        auto move_to = [&](uint32_t k, uint32_t p) {
+          const uint32_t* id = cs.at(k);
+          for (uint32_t j = 0; j < cs.arity; ++j) { load[(size_t)id[j] * K + phaseOf[k]]--; load[(size_t)id[j] * K + p]++; }
+          phaseOf[k] = (uint8_t)p;
+        };
+        auto movable = [&](uint32_t k) { return mask[k] != 0 && (mask[k] & (mask[k] - 1)) != 0; };
+        // a phase other than `avoid` where k fits under `target`
+        auto room_for = [&](uint32_t k, uint32_t target, uint32_t avoid) {
+          for (uint32_t p = 0; p < K; ++p)
+            if (p != phaseOf[k] && p != avoid && (mask[k] >> p & 1) && peak_at(k, p) + 1u <= target) return p;
+          return NONE;
+        };
+        uint32_t mxL = 0;
+        for (size_t i = 0; i < load.size(); ++i) mxL = std::max<uint32_t>(mxL, load[i]);
+        for (uint32_t target = mxL ? mxL - 1 : 0; target >= 1; --target) {
+          for (int pass = 0; pass < 3; ++pass) {
+            uint32_t moves = 0;
+            for (uint32_t k = 0; k < cs.n; ++k) {
+              if (!movable(k) || peak_at(k, phaseOf[k]) <= target) continue;
+              uint32_t p = room_for(k, target, NONE);
+              if (p == NONE) {
+                // make room: one phase where exactly one vertex of k is full, and a constraint there that can leave
+                for (uint32_t q = 0; q < K && p == NONE; ++q) {
+                  if (q == phaseOf[k] || !(mask[k] >> q & 1)) continue;
+                  uint32_t full = NONE, nFull = 0;
+                  for (uint32_t j = 0; j < cs.arity; ++j)
+                    if (load[(size_t)cs.at(k)[j] * K + q] + 1u > target) { full = cs.at(k)[j]; ++nFull; }
+                  if (nFull != 1 || load[(size_t)full * K + q] != target) continue;
+                  for (uint32_t a = incOff[full]; a < incOff[full + 1]; ++a) {
+                    const uint32_t k2 = inc[a];
+                    if (k2 == k || phaseOf[k2] != q || !movable(k2)) continue;
+                    const uint32_t p2 = room_for(k2, target, phaseOf[k]);
+                    if (p2 == NONE) continue;
+                    move_to(k2, p2);
+                    if (peak_at(k, q) + 1u <= target) { p = q; break; }
+                  }
+                }
+              }
+              if (p != NONE) { move_to(k, p); ++moves; }
+            }
+            if (!moves) break;
+          }
+          // forced constraints can pin a few vertices above any level; go on while fewer than one
+          // (vertex, phase) pair per tile visit is left above this one
+          size_t above = 0;
+          for (size_t i = 0; i < load.size(); ++i) above += load[i] > target;
+          if (above > (size_t)K * nTilesMax) break;
+        }
       }
       // tile balance: a phase lasts as long as its fullest tile.  Move constraints out of tiles that
       // hold more than the average into emptier admissible tiles, never raising a vertex load above
@@ -1014,7 +1257,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       auto worker = [&](std::vector<uint32_t>& lo, std::vector<uint32_t>& sc) {
         for (size_t i; (i = next.fetch_add(1)) < work.size();) {
           TileBuild& tb = *work[i];
-          finish_tile(sets, tb, lo, sc);
+          finish_tile(sets, tb, lo, sc, mixedThreads);
           const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
           if (nv > 65535u || tile_bytes(tb) > smemBytes) ok = false;
         }
@@ -1030,18 +1273,21 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     // second colouring pass: a phase lasts as long as its slowest tile, so tiles that ended above
     // what most tiles of their phase reached get a longer search (again spread over host threads)
     if (fits) {
-      struct Job { TileBuild* tb; int ty; uint32_t goal; };
+      struct Job { TileBuild* tb; int ty; uint32_t goal; };   // ty == 2: the joint colouring of a mixed tile
       std::vector<Job> jobs;
       for (uint32_t p = 0; p < K; ++p)
-        for (int ty = 0; ty < 2; ++ty) {
+        for (int ty = 0; ty < 3; ++ty) {
+          auto takes = [&](const TileBuild& tb) {
+            return ty == 2 ? tb.mixed : (!tb.mixed && !tb.ty[ty].cons.empty());
+          };
           std::vector<uint32_t> ncs;
           for (auto& tb : mainPh[p])
-            if (!tb.ty[ty].cons.empty()) ncs.push_back(tb.ty[ty].nColours);
+            if (takes(tb)) ncs.push_back(tb.ty[ty & 1].nColours);
           if (ncs.size() < 4) continue;
           std::sort(ncs.begin(), ncs.end());
           const uint32_t goal = ncs[ncs.size() / 4];   // lower quartile
           for (auto& tb : mainPh[p])
-            if (!tb.ty[ty].cons.empty() && tb.ty[ty].nColours > goal) jobs.push_back({&tb, ty, goal});
+            if (takes(tb) && tb.ty[ty & 1].nColours > goal) jobs.push_back({&tb, ty, goal});
         }
       std::atomic<size_t> next{0};
       auto worker = [&](std::vector<uint32_t>& lo, std::vector<uint32_t>& sc) {
@@ -1049,7 +1295,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           TileBuild& tb = *jobs[i].tb;
           const int ty = jobs[i].ty;
           const uint32_t goal = jobs[i].goal;
-          TypeList& L = tb.ty[ty];
+          TypeList& L = tb.ty[ty & 1];
           uint32_t nLocal;
           if (tb.contiguous) {
             nLocal = tb.rangeCount;
@@ -1058,18 +1304,28 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
             nLocal = (uint32_t)tb.verts.size();
             for (uint32_t q = 0; q < nLocal; ++q) lo[tb.verts[q]] = q;
           }
+          if (ty == 2) {
+            for (uint32_t attempt2 = 0; attempt2 < 4 && L.nColours > goal; ++attempt2) {
+              TileBuild trial;
+              trial.ty[0].cons = tb.ty[0].cons;
+              trial.ty[1].cons = tb.ty[1].cons;
+              colour_joint(sets, trial, nLocal, lo, sc, mixedThreads, 160, goal, 0x85ebca6bu * (attempt2 + 1));
+              if (trial.ty[0].nColours < L.nColours && steps_fit(trial, mixedThreads)) {
+                tb.ty[0] = std::move(trial.ty[0]);
+                tb.ty[1] = std::move(trial.ty[1]);
+              }
+            }
+            order_groups(sets, tb, lo, 0);
+            order_groups(sets, tb, lo, 1);
+            continue;
+          }
           for (uint32_t attempt2 = 0; attempt2 < 4 && L.nColours > goal; ++attempt2) {
             TypeList trial;
             trial.cons = L.cons;
             colour_list(sets[ty], trial, nLocal, lo, sc, 160, goal, 0x85ebca6bu * (attempt2 + 1));
             if (trial.nColours < L.nColours) L = std::move(trial);
           }
-          for (size_t a2 = 0; a2 < L.cons.size();) {
-            size_t b2 = a2;
-            while (b2 < L.cons.size() && L.colour[b2] == L.colour[a2]) ++b2;
-            bank_order(sets[ty], lo, &L.cons[a2], (uint32_t)(b2 - a2));
-            a2 = b2;
-          }
+          order_groups(sets, tb, lo, ty);
         }
       };
       // two jobs may share a tile (its edge list and its tet list): they touch different TypeLists
@@ -1151,6 +1407,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
         if (!hasE && !hasT && !(isHome && tb.contiguous)) continue;
         Tile tl;
         tl.contiguous = tb.contiguous ? 1u : 0u;
+        tl.mixed = (tb.mixed && hasE && hasT) ? 1u : 0u;
         uint32_t nLocal;
         if (tb.contiguous) {
           tl.vertBegin = tb.rangeBegin;
@@ -1183,6 +1440,27 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           if (!use) continue;
           const TypeList& L = tb.ty[ty];
           size_t i = 0;
+          if (tl.mixed) {
+            // mixed tile: exactly one group per step and type (possibly empty); the planner kept every step within the block
+            for (uint32_t sIdx = 0; sIdx < L.nColours; ++sIdx) {
+              size_t j = i;
+              while (j < L.cons.size() && L.colour[j] == sIdx) ++j;
+              Group g;
+              g.begin = (uint32_t)order.size();
+              g.count = (uint32_t)(j - i);
+              plan.groups.push_back(g);
+              for (size_t k = i; k < j; ++k) {
+                const uint32_t c = L.cons[k];
+                cPhase[c] = (uint32_t)plan.phases.size();
+                cTile[c] = (uint32_t)plan.tiles.size();
+                cCol[c] = sIdx;
+                for (uint32_t a = 0; a < cs.arity; ++a) local.push_back((uint16_t)localOf[cs.at(c)[a]]);
+                order.push_back(c);
+                dev.push_back(devCur[ty]++);
+              }
+              i = j;
+            }
+          }
           while (i < L.cons.size()) {
             size_t j = i;
             while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;

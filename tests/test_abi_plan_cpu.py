@@ -80,13 +80,35 @@ def test_interleaved_tile_schedule_is_valid_and_sequence_consistent(mesh, tile_v
     pos = seq & 0x7FFFFFFF
     # every schedule position exactly once, each type in increasing schedule order
     assert np.array_equal(pos[is_tet == 0], np.arange(E)) and np.array_equal(pos[is_tet == 1], np.arange(T))
-    # the sequence walks (phase, tile) pairs in order; inside a pair edges come before tets
+    # the sequence walks (phase, tile) pairs in order.  Inside a pair either all edges come before
+    # all tets, or -- mixed colour steps -- it walks the steps in order, edges of a step before its
+    # tets, and the edges AND tets of one step share no vertex
     eo, to = p.order()
-    (eph, etl, _), (tph, ttl, _) = p.slots(False), p.slots(True)
-    ph = np.where(is_tet == 1, tph[to][np.minimum(pos, T - 1)] if T else 0, eph[eo][np.minimum(pos, E - 1)] if E else 0).astype(np.int64)
-    tl = np.where(is_tet == 1, ttl[to][np.minimum(pos, T - 1)] if T else 0, etl[eo][np.minimum(pos, E - 1)] if E else 0).astype(np.int64)
-    key = (ph * (tl.max() + 1) + tl) * 2 + is_tet
-    assert (np.diff(key) >= 0).all()
+    (eph, etl, eco), (tph, ttl, tco) = p.slots(False), p.slots(True)
+
+    def at(e_arr, t_arr):
+        return np.where(is_tet == 1, t_arr[to][np.minimum(pos, T - 1)] if T else 0,
+                        e_arr[eo][np.minimum(pos, E - 1)] if E else 0).astype(np.int64)
+
+    ph, tl, co = at(eph, tph), at(etl, ttl), at(eco, tco)
+    pair = ph * (tl.max() + 1) + tl
+    assert (np.diff(pair) >= 0).all()
+    same = np.diff(pair) == 0
+    tet_then_edge = same & (np.diff(is_tet) < 0)
+    mixed_pairs = np.unique(pair[1:][tet_then_edge])
+    in_mixed = np.isin(pair, mixed_pairs)
+    # separate sweeps: edges before tets
+    k_sep = pair * 2 + is_tet
+    assert (np.diff(k_sep[~in_mixed]) >= 0).all()
+    if len(mixed_pairs):
+        k_mix = (pair * (co.max() + 1) + co) * 2 + is_tet
+        assert (np.diff(k_mix[in_mixed]) >= 0).all()
+        step = (pair * (co.max() + 1) + co)[in_mixed]
+        ids_of = [edges[eo[q]] if not t else tets[to[q]] for q, t in zip(pos[in_mixed], is_tet[in_mixed])]
+        sv = np.concatenate([np.stack([np.full(len(v), s_), v.astype(np.int64)], 1) for s_, v in zip(step, ids_of)])
+        assert len(np.unique(sv, axis=0)) == len(sv), "an edge and a tet of one mixed step share a vertex"
+    if tile_vertices == 0 and mesh == "kuhn7":
+        assert len(mixed_pairs) > 0   # the default interleaved schedule uses mixed steps
     info = p.info()
     assert info["partitions"] >= 1 and info["tiles"] >= 1
 
