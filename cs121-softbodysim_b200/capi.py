@@ -40,7 +40,7 @@ ARRAY_INV_MASS, ARRAY_EDGE_REST, ARRAY_TET_REST, ARRAY_EDGE_LAMBDA, ARRAY_TET_LA
 # every symbol include/pbd_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "pbd_abi_version", "pbd_last_error", "pbd_device_count",
-    "pbd_create", "pbd_step", "pbd_step_async", "pbd_sync", "pbd_read_positions", "pbd_destroy",
+    "pbd_create", "pbd_create_from_init", "pbd_init_payload_size", "pbd_step", "pbd_step_async", "pbd_sync", "pbd_read_positions", "pbd_destroy",
     "pbd_backend_name", "pbd_get_info", "pbd_set_params", "pbd_get_schedule_order",
     "pbd_get_schedule_sequence", "pbd_get_array",
     "pbd_shard_export", "pbd_shard_attach_ipc", "pbd_shard_attach_local", "pbd_shard_owner",
@@ -135,6 +135,10 @@ def lib() -> C.CDLL:
     L.pbd_create.restype = vp
     L.pbd_create.argtypes = [C.POINTER(SolverParams), u32, u32, u32, vp, vp, vp, vp, u32, C.c_int,
                              C.POINTER(Options), C.POINTER(C.c_int)]
+    L.pbd_create_from_init.restype = vp
+    L.pbd_create_from_init.argtypes = [vp, C.c_uint64, C.c_int, C.POINTER(Options), C.POINTER(C.c_int)]
+    L.pbd_init_payload_size.restype = C.c_uint64
+    L.pbd_init_payload_size.argtypes = [u32, u32, u32, u32]
     L.pbd_step.argtypes = [vp, f32, C.POINTER(StepStats)]
     L.pbd_step_async.argtypes = [vp, f32, u32]
     L.pbd_sync.argtypes = [vp, C.POINTER(C.c_double)]
@@ -207,6 +211,22 @@ class Body:
                               C.byref(st))
         if not self.h:
             raise PBDError(st.value, L.pbd_last_error().decode())
+
+    @classmethod
+    def from_init_payload(cls, payload: bytes, device: int = -1, options: Options | None = None) -> "Body":
+        """``pbd_create_from_init``: the body a MSG_INIT payload describes (Server.cpp:30-70)."""
+        L = lib()
+        buf = bytes(payload)
+        self = cls.__new__(cls)
+        st = C.c_int(0)
+        self.h = L.pbd_create_from_init(buf, len(buf), device, C.byref(options) if options is not None else None,
+                                        C.byref(st))
+        if not self.h:
+            raise PBDError(st.value, L.pbd_last_error().decode())
+        i = self.info()
+        self.V, self.E, self.T = i["V"], i["E"], i["T"]
+        self.params = SolverParams.from_buffer_copy(buf[12:60])
+        return self
 
     def close(self):
         if getattr(self, "h", None):
@@ -481,6 +501,19 @@ class Plan:
         f = lib().pbd_plan_get_tet_slots if tets else lib().pbd_plan_get_edge_slots
         _check(f(self.h, _ptr(ph), _ptr(tl), _ptr(co)))
         return ph, tl, co
+
+
+def pack_init_payload(params: SolverParams, x0, edge_ids, tet_ids, pinned=None) -> bytes:
+    """The MSG_INIT payload the Unity client sends (PBDRemoteWorld.cs:294-349, read back by
+    Server.cpp:30-70): u32 V,E,T | SolverParams (48 B) | u32 pinnedCount | pinned | x0 | edgeIds | tetIds,
+    little-endian, packed."""
+    x0 = np.ascontiguousarray(x0, dtype="<f4").reshape(-1, 3)
+    edge_ids = np.ascontiguousarray(edge_ids, dtype="<u4").reshape(-1, 2)
+    tet_ids = np.ascontiguousarray(tet_ids, dtype="<u4").reshape(-1, 4)
+    pinned = np.ascontiguousarray(pinned if pinned is not None else [], dtype="<u4").ravel()
+    head = np.array([x0.shape[0], edge_ids.shape[0], tet_ids.shape[0]], dtype="<u4").tobytes()
+    return b"".join([head, bytes(params), np.array([pinned.size], dtype="<u4").tobytes(), pinned.tobytes(),
+                     x0.tobytes(), edge_ids.tobytes(), tet_ids.tobytes()])
 
 
 # ------------------------------------------------------------------ reference-shaped host mirror

@@ -295,6 +295,42 @@ int pbd_sync(pbd_handle* h, double* device_ms) {
   return PBD_OK;
 }
 
+uint64_t pbd_init_payload_size(uint32_t V, uint32_t E, uint32_t T, uint32_t pinnedCount) {
+  return 64ull + 4ull * pinnedCount + 12ull * V + 8ull * E + 16ull * T;
+}
+
+// comm_loop's MSG_INIT decode (Server.cpp:30-70) with the bounds check the reference leaves out
+pbd_handle* pbd_create_from_init(const void* payload, uint64_t size, int device, const pbd_options* opts, int* status) {
+  if (status) *status = PBD_OK;
+  if (!payload) { fail(PBD_ERR_INVALID, "payload is null", status); return nullptr; }
+  if (size < 64) { fail(PBD_ERR_INVALID, "MSG_INIT payload shorter than its 64-byte fixed part", status); return nullptr; }
+  const unsigned char* p = static_cast<const unsigned char*>(payload);
+  uint32_t head[3], nPinned;
+  pbd_params params;
+  static_assert(sizeof(pbd_params) == 48, "pbd_params is the 48-byte wire block");
+  std::memcpy(head, p, 12);
+  std::memcpy(&params, p + 12, 48);
+  std::memcpy(&nPinned, p + 60, 4);
+  const uint32_t V = head[0], E = head[1], T = head[2];
+  const uint64_t need = pbd_init_payload_size(V, E, T, nPinned);
+  if (size < need) {
+    fail(PBD_ERR_INVALID, "MSG_INIT payload of " + std::to_string(size) + " bytes, but V/E/T/pinnedCount need " + std::to_string(need), status);
+    return nullptr;
+  }
+  // the arrays follow unaligned in general: copy them out, as the reference does
+  std::vector<uint32_t> pinned(nPinned), edges((size_t)E * 2), tets((size_t)T * 4);
+  std::vector<float> x0((size_t)V * 3);
+  p += 64;
+  if (nPinned) std::memcpy(pinned.data(), p, 4ull * nPinned);
+  p += 4ull * nPinned;
+  if (V) std::memcpy(x0.data(), p, 12ull * V);
+  p += 12ull * V;
+  if (E) std::memcpy(edges.data(), p, 8ull * E);
+  p += 8ull * E;
+  if (T) std::memcpy(tets.data(), p, 16ull * T);
+  return pbd_create(&params, V, E, T, x0.data(), edges.data(), tets.data(), pinned.data(), nPinned, device, opts, status);
+}
+
 int pbd_step(pbd_handle* h, float dt, pbd_step_stats* stats) {
   if (!h) return fail(PBD_ERR_INVALID, "handle is null");
   const double t0 = wall_ms();

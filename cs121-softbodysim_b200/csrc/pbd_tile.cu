@@ -303,17 +303,19 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           fence_async_smem();   // lambdas written by the sweeps -> visible to the bulk store
           __syncthreads();      // also: sv and rec are free for the next tile
           if (tid == 0) {
-            const TileCopy c = j < kItemCopySmem ? itemCopy[j] : P.copies[itemTile[j]];
-            if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
-            if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
-            bulk_commit();
-            if (nItems == 1) bulk_wait_read();   // the block stays resident and is swept again next iteration
+            // publish first: the release fence waits for the writes issued before it, and nobody but
+            // this tile reads its lambdas -- their write-back need not be part of that wait
             if (P.done) {   // my vertices are in L2 (of their owners)
               const uint32_t v = P.iterBase + sub * P.iterations + it + 1u;
               // system scope only when another GPU reads this counter or holds vertices this tile
               // wrote (flags bit 1): a system-scope release costs several microseconds
               if (multi && (h.flags & 2u)) st_release_sys(P.done + itemTile[j], v); else st_release(P.done + itemTile[j], v);
             }
+            const TileCopy c = j < kItemCopySmem ? itemCopy[j] : P.copies[itemTile[j]];
+            if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
+            if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
+            bulk_commit();
+            if (nItems == 1) bulk_wait_read();   // the block stays resident and is swept again next iteration
           }
           if (nItems == 1) {
             __syncthreads();

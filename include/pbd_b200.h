@@ -12,6 +12,7 @@
  * What each entry replaces in the reference (paths relative to /root/reference):
  *
  *   pbd_create           the MSG_INIT decode + init helpers:  CProgram/src/Server.cpp:30-114
+ *   pbd_create_from_init the same, straight from the wire payload:  CProgram/src/Server.cpp:30-70
  *                        (builds PBDState), CProgram/src/Sim.cpp:63-79 compute_inv_mass and
  *                        :81-95 build_rest.  Inverse masses and rest values are derived on the
  *                        host in the CALLER'S constraint order, exactly as the reference does.
@@ -146,6 +147,17 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
                        const float* x0, const uint32_t* edgeIds, const uint32_t* tetIds,
                        const uint32_t* pinned, uint32_t nPinned, int device,
                        const pbd_options* opts, int* status);
+
+/* The same from the raw MSG_INIT payload of the reference's wire protocol "PBD1" -- the decode that
+ * comm_loop performs (CProgram/src/Server.cpp:30-70; written by PBDRemoteWorld.cs:294-349).  Little-
+ * endian, packed: u32 V, E, T | pbd_params (48 bytes) | u32 pinnedCount | u32 pinned[pinnedCount]
+ * | f32 x0[3V] | u32 edgeIds[2E] | u32 tetIds[4T].  The payload need not be aligned.  Unlike the
+ * reference, which trusts V/E/T, a payload shorter than its own counts demand is refused with
+ * PBD_ERR_INVALID instead of being read past its end; trailing bytes are ignored as there. */
+pbd_handle* pbd_create_from_init(const void* payload, uint64_t size, int device, const pbd_options* opts,
+                                 int* status);
+/* bytes of a MSG_INIT payload with these counts (what the client computes, PBDRemoteWorld.cs:294-306) */
+uint64_t pbd_init_payload_size(uint32_t V, uint32_t E, uint32_t T, uint32_t pinnedCount);
 
 /* Advance one frame: max(1,substeps) substeps of dt/substeps.  Synchronous (returns after the
  * device finished), like IStepper::step.  stats may be NULL. */

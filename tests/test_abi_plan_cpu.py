@@ -142,6 +142,34 @@ def test_input_validation(capi, meshgen):
     capi.Plan(x0, edges, np.zeros((0, 4), np.uint32))
 
 
+def test_init_payload_decode_validation(capi, meshgen):
+    """pbd_create_from_init = comm_loop's MSG_INIT decode (Server.cpp:30-70) plus the bounds check the
+    reference leaves out: short payloads and bad indices are refused before any device is touched."""
+    x0, tets, edges = meshgen.kuhn_grid(3)
+    prm = capi.SolverParams.default()
+    pay = capi.pack_init_payload(prm, x0, edges, tets, pinned=[0, 5])
+    L = capi.lib()
+    assert len(pay) == L.pbd_init_payload_size(len(x0), len(edges), len(tets), 2) == 64 + 8 + 12 * len(x0) + 8 * len(edges) + 16 * len(tets)
+    for cut in (0, 10, 63, 64, len(pay) - 1):
+        with pytest.raises(capi.PBDError) as e:
+            capi.Body.from_init_payload(pay[:cut])
+        assert e.value.code == capi.PBD_ERR_INVALID
+    bad = bytearray(pay)
+    bad[-4:] = np.array([len(x0)], dtype="<u4").tobytes()      # last tet index = V
+    with pytest.raises(capi.PBDError) as e:
+        capi.Body.from_init_payload(bytes(bad))
+    assert e.value.code == capi.PBD_ERR_INDEX
+    huge = bytearray(pay)
+    huge[0:4] = np.array([0xFFFFFFFF], dtype="<u4").tobytes()  # V = 2^32-1: the reference would read ~48 GB past the buffer
+    with pytest.raises(capi.PBDError) as e:
+        capi.Body.from_init_payload(bytes(huge))
+    assert e.value.code == capi.PBD_ERR_INVALID
+    if capi.device_count() == 0:                               # a complete payload passes the decode and then needs a device
+        with pytest.raises(capi.PBDError) as e:
+            capi.Body.from_init_payload(pay + b"trailing bytes are ignored")
+        assert e.value.code == capi.PBD_ERR_NO_DEVICE
+
+
 def test_no_cpu_fallback(capi, meshgen):
     if capi.device_count() > 0:
         pytest.skip("a CUDA device is present")

@@ -396,3 +396,26 @@ def test_set_params_between_frames_bit_exact(order, capi, po, meshgen):
             ora.step_sequence(1 / 60, seq)
         _assert_state_equal(capi, po, body, ora, f"after set_params({kw})")
     body.close()
+
+
+def test_create_from_init_payload_matches_create(capi, meshgen, golden):
+    """a18, Server.cpp:30-114: a body built from the raw MSG_INIT payload (pinned vertices included) is the body pbd_create builds from the decoded arrays:
+    identical inverse masses, rest values and positions after a few frames."""
+    m = golden("mesh_default.npz")
+    x0, tets, edges = m["vertices"], m["tets"], m["edges"]
+    pinned = np.argsort(-x0[:, 1])[:40].astype(np.uint32)           # top layer, as PBDRemoteSoftBody.cs:163-183 pins it
+    prm = capi.SolverParams.default(substeps=4)
+    pay = capi.pack_init_payload(prm, x0, edges, tets, pinned)
+    opts = capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_INTERLEAVED)
+    a = capi.Body(prm, x0, edges, tets, pinned, device=0, options=opts)
+    b = capi.Body.from_init_payload(pay + b"ignored tail", device=0, options=opts)
+    assert (b.V, b.E, b.T) == (len(x0), len(edges), len(tets)) and bytes(b.params) == bytes(prm)
+    for what in (capi.ARRAY_INV_MASS, capi.ARRAY_EDGE_REST, capi.ARRAY_TET_REST):
+        assert np.array_equal(a.get_array(what), b.get_array(what))
+    assert (a.get_array(capi.ARRAY_INV_MASS)[pinned] == 0).all()
+    for _ in range(3):
+        a.step(1 / 60)
+        b.step(1 / 60)
+    assert np.array_equal(a.read_positions().view(np.uint32), b.read_positions().view(np.uint32))
+    a.close()
+    b.close()
