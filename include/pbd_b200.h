@@ -95,7 +95,11 @@ typedef struct pbd_options {
   uint32_t backend;        /* PBD_BACKEND_*                                                      */
   uint32_t order_mode;     /* PBD_ORDER_STRICT: every iteration projects all edges, then all tets,
                               then the ground clamp -- the reference's sweep order up to a
-                              permutation inside each constraint type.                           */
+                              permutation inside each constraint type.
+                              PBD_ORDER_INTERLEAVED (tile backend): every iteration still projects
+                              every constraint exactly once, but edges and tets interleave -- a
+                              tile visit runs colour steps that each hold a vertex-disjoint set of
+                              its edges and tets.  pbd_get_schedule_sequence discloses the order. */
   uint32_t flags;          /* PBD_FLAG_*                                                         */
   uint32_t tile_vertices;  /* tile backend: target vertices per shared-memory tile, 0 = auto     */
   uint32_t block_threads;  /* 0 = auto                                                           */
