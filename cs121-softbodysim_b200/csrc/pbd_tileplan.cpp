@@ -453,12 +453,138 @@ uint32_t reduce_colours(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_
   return top;
 }
 
+// Tabu search (TabuCol, Hertz & de Werra) on a finished colouring: drop the smallest colour class,
+// give its members the least conflicting of the remaining colours, then repair conflicts one
+// recolouring at a time (best non-tabu move of a conflicting constraint; a move back is tabu for
+// a while).  Repeats while it succeeds and the count is above `floorColours` (the largest vertex
+// degree: no colouring can do better).  Greedy + iterated greedy usually end one or two colours
+// above that bound; each colour is one block barrier per tile visit.  Deterministic (fixed LCG).
+uint32_t tabu_reduce(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nLocal, std::vector<uint32_t>& col,
+                     uint32_t nc, uint32_t floorColours, uint32_t maxIter, uint32_t seed) {
+  if (n < 2 || nc < 2 || nc > 64 || nc <= floorColours) return nc;
+  // conflict graph (constraints sharing a vertex), CSR, neighbours unique
+  std::vector<uint32_t> vOff((size_t)nLocal + 1, 0), vList;
+  auto repeated = [&](uint32_t i, uint32_t j) {
+    for (uint32_t q = 0; q < j; ++q)
+      if (ids[(size_t)i * arity + q] == ids[(size_t)i * arity + j]) return true;
+    return false;
+  };
+  for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t j = 0; j < arity; ++j)
+      if (!repeated(i, j)) vOff[ids[(size_t)i * arity + j] + 1]++;
+  for (uint32_t v = 0; v < nLocal; ++v) vOff[v + 1] += vOff[v];
+  vList.resize(vOff[nLocal]);
+  {
+    std::vector<uint32_t> cur(vOff.begin(), vOff.end() - 1);
+    for (uint32_t i = 0; i < n; ++i)
+      for (uint32_t j = 0; j < arity; ++j)
+        if (!repeated(i, j)) vList[cur[ids[(size_t)i * arity + j]]++] = i;
+  }
+  std::vector<uint32_t> aOff((size_t)n + 1, 0), adj, tmp;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (uint32_t i = 0; i < n; ++i) {
+      tmp.clear();
+      for (uint32_t j = 0; j < arity; ++j) {
+        if (repeated(i, j)) continue;
+        const uint32_t v = ids[(size_t)i * arity + j];
+        for (uint32_t a = vOff[v]; a < vOff[v + 1]; ++a)
+          if (vList[a] != i) tmp.push_back(vList[a]);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      if (pass == 0) aOff[i + 1] = aOff[i] + (uint32_t)tmp.size();
+      else std::copy(tmp.begin(), tmp.end(), adj.begin() + aOff[i]);
+    }
+    if (pass == 0) adj.resize(aOff[n]);
+  }
+  uint32_t lcg = seed | 1u;
+  auto rnd = [&]() { lcg = lcg * 1664525u + 1013904223u; return lcg >> 8; };
+  std::vector<uint32_t> work, conf, confPos(n), gamma, tabuUntil;
+  while (nc > floorColours && nc >= 2) {
+    const uint32_t k = nc - 1;
+    // the smallest class becomes colour k (the one to dissolve)
+    std::vector<uint32_t> size(nc, 0);
+    for (uint32_t i = 0; i < n; ++i) size[col[i]]++;
+    uint32_t drop = 0;
+    for (uint32_t c = 1; c < nc; ++c)
+      if (size[c] < size[drop]) drop = c;
+    work = col;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (work[i] == drop) work[i] = k;
+      else if (work[i] == k) work[i] = drop;
+    }
+    gamma.assign((size_t)n * k, 0);   // gamma[i*k + c] = neighbours of i coloured c
+    for (uint32_t i = 0; i < n; ++i)
+      if (work[i] < k)
+        for (uint32_t a = aOff[i]; a < aOff[i + 1]; ++a) gamma[(size_t)adj[a] * k + work[i]]++;
+    for (uint32_t i = 0; i < n; ++i)
+      if (work[i] == k) {
+        uint32_t best = 0;
+        for (uint32_t c = 1; c < k; ++c)
+          if (gamma[(size_t)i * k + c] < gamma[(size_t)i * k + best]) best = c;
+        work[i] = best;
+        for (uint32_t a = aOff[i]; a < aOff[i + 1]; ++a) gamma[(size_t)adj[a] * k + best]++;
+      }
+    conf.clear();
+    std::fill(confPos.begin(), confPos.end(), NONE);
+    uint64_t nConf = 0;
+    for (uint32_t i = 0; i < n; ++i)
+      if (gamma[(size_t)i * k + work[i]]) { confPos[i] = (uint32_t)conf.size(); conf.push_back(i); nConf += gamma[(size_t)i * k + work[i]]; }
+    nConf /= 2;
+    uint64_t bestSeen = nConf;
+    tabuUntil.assign((size_t)n * k, 0);
+    auto set_conf = [&](uint32_t i) {
+      const bool c = gamma[(size_t)i * k + work[i]] != 0;
+      if (c && confPos[i] == NONE) { confPos[i] = (uint32_t)conf.size(); conf.push_back(i); }
+      else if (!c && confPos[i] != NONE) {
+        const uint32_t last = conf.back();
+        conf[confPos[i]] = last;
+        confPos[last] = confPos[i];
+        conf.pop_back();
+        confPos[i] = NONE;
+      }
+    };
+    uint32_t it = 0;
+    for (; it < maxIter && nConf; ++it) {
+      int64_t bestDelta = INT64_MAX;
+      uint32_t bi = NONE, bc = 0, ties = 0;
+      for (uint32_t i : conf) {
+        const uint32_t* gi = &gamma[(size_t)i * k];
+        const int64_t cur = gi[work[i]];
+        for (uint32_t c = 0; c < k; ++c) {
+          if (c == work[i]) continue;
+          const int64_t d = (int64_t)gi[c] - cur;
+          if (tabuUntil[(size_t)i * k + c] > it && !((int64_t)nConf + d < (int64_t)bestSeen)) continue;
+          if (d < bestDelta) { bestDelta = d; bi = i; bc = c; ties = 1; }
+          else if (d == bestDelta && (rnd() % ++ties) == 0) { bi = i; bc = c; }
+        }
+      }
+      if (bi == NONE) continue;
+      const uint32_t old = work[bi];
+      for (uint32_t a = aOff[bi]; a < aOff[bi + 1]; ++a) {
+        gamma[(size_t)adj[a] * k + old]--;
+        gamma[(size_t)adj[a] * k + bc]++;
+      }
+      work[bi] = bc;
+      nConf = (uint64_t)((int64_t)nConf + bestDelta);
+      tabuUntil[(size_t)bi * k + old] = it + (uint32_t)(0.6 * conf.size()) + rnd() % 10u;
+      set_conf(bi);
+      for (uint32_t a = aOff[bi]; a < aOff[bi + 1]; ++a) set_conf(adj[a]);
+      bestSeen = std::min(bestSeen, nConf);
+    }
+    if (nConf) break;   // could not dissolve this class within the budget
+    col = work;
+    nc = k;
+  }
+  return nc;
+}
+
 // Colour n constraints given by their tile-local vertex indices (`arity` per constraint, caller's
 // order; a constraint may list a vertex more than once).  col[i] receives the colour of
 // constraint i; returns the number of colours.  Largest-degree-first greedy, the recolouring pass
 // above, then iterated greedy.
 uint32_t colour_ids(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nLocal, std::vector<uint32_t>& col,
-                    std::vector<uint32_t>& scratch, int maxIter, uint32_t goal, uint32_t seed) {
+                    std::vector<uint32_t>& scratch, int maxIter, uint32_t goal, uint32_t seed, uint32_t tabuIter = 0) {
   col.assign(n, 0);
   if (n == 0) return 0;
   auto repeated = [&](uint32_t i, uint32_t j) {   // vertex j of constraint i already listed at an earlier position
@@ -533,6 +659,7 @@ uint32_t colour_ids(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nL
       }
     }
   }
+  if (tabuIter && nc > std::max(maxDeg, goal)) nc = tabu_reduce(scratch.data(), n, arity, nLocal, colV, nc, std::max(maxDeg, goal), tabuIter, seed);
   for (uint32_t i = 0; i < n; ++i) col[visit[i]] = colV[i];
   return nc;
 }
@@ -583,7 +710,8 @@ void colour_joint(const CSet sets[2], TileBuild& tb, uint32_t nLocal, const std:
     for (uint32_t j = 0; j < 4; ++j) ids[(size_t)i * 4 + j] = localOf[sets[1].at(LT.cons[i])[j]];
   for (uint32_t i = 0; i < nE; ++i)
     for (uint32_t j = 0; j < 4; ++j) ids[(size_t)(nT + i) * 4 + j] = localOf[sets[0].at(LE.cons[i])[j & 1u]];
-  uint32_t nc = colour_ids(ids.data(), n, 4, nLocal, col, scratch, maxIter, goal, seed);
+  static const uint32_t tabuIter = getenv("PBD_PLAN_TABU") ? (uint32_t)atoi(getenv("PBD_PLAN_TABU")) : 4000u;   // debug override
+  uint32_t nc = colour_ids(ids.data(), n, 4, nLocal, col, scratch, maxIter, goal, seed, tabuIter);
 
   auto pad32 = [](uint32_t x) { return (x + 31u) & ~31u; };
   if (nc <= 64) {
@@ -1010,12 +1138,154 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     for (uint32_t p = 0; p < K; ++p) mainPh[p].resize(nTilesMax);
     std::vector<uint32_t> resid[2];
     std::vector<uint16_t> load((size_t)m.V * K);
+    std::vector<uint8_t> maskA[2], phaseA[2];
+    // tile balance: a phase lasts as long as its fullest tile.  Move constraints out of tiles that
+    // hold more than the average into emptier admissible tiles, never raising a vertex load above
+    // the peak the passes above settled on.  Then hand the constraints to their tiles.
+    auto finish_type = [&](int ty) {
+      const CSet& cs = sets[ty];
+      std::vector<uint8_t>& mask = maskA[ty];
+      std::vector<uint8_t>& phaseOf = phaseA[ty];
+      {
+        // cap = the load 99 % of the (vertex, phase) pairs stay within: balancing must not turn
+        // the rare peak into the norm (colours follow the per-tile peak)
+        uint32_t peak = 0;
+        {
+          std::vector<uint64_t> hist(64, 0);
+          uint64_t n99 = 0, acc = 0;
+          for (size_t i = 0; i < load.size(); ++i)
+            if (load[i]) { hist[std::min<uint32_t>(load[i], 63u)]++; ++n99; }
+          n99 = n99 - n99 / 100;
+          for (uint32_t l = 0; l < 64; ++l) { acc += hist[l]; if (acc >= n99) { peak = l; break; } }
+          // one below that: a tile whose vertices all sit at the 99 % load needs ~2 more colours
+          const uint32_t margin = getenv("PBD_PLAN_CAPM") ? (uint32_t)atoi(getenv("PBD_PLAN_CAPM")) : 1u;
+          peak = peak > margin ? peak - margin : 0u;
+        }
+        std::vector<std::vector<uint32_t>> cnt(K, std::vector<uint32_t>(nTilesMax, 0));
+        uint64_t total = 0;
+        for (uint32_t k = 0; k < cs.n; ++k)
+          if (mask[k]) { cnt[phaseOf[k]][tileOfS[phaseOf[k]][cs.at(k)[0]]]++; ++total; }
+        const uint32_t mean = (uint32_t)(total / std::max<uint64_t>(1, (uint64_t)K * nTilesMax));
+        for (int sweep = 0; sweep < (getenv("PBD_PLAN_NOBAL") ? 0 : 8); ++sweep) {
+          uint32_t moves = 0;
+          for (uint32_t k = 0; k < cs.n; ++k) {
+            if (mask[k] == 0 || (mask[k] & (mask[k] - 1)) == 0) continue;
+            const uint32_t* id = cs.at(k);
+            const uint32_t p0 = phaseOf[k], t0 = tileOfS[p0][id[0]];
+            if (cnt[p0][t0] <= mean) continue;
+            uint32_t bestP = p0, bestCnt = cnt[p0][t0] - 1;   // must end strictly emptier than the source is now
+            for (uint32_t p = 0; p < K; ++p) {
+              if (p == p0 || !(mask[k] >> p & 1)) continue;
+              uint32_t mxl = 0;
+              for (uint32_t j = 0; j < cs.arity; ++j) mxl = std::max<uint32_t>(mxl, load[(size_t)id[j] * K + p] + 1u);
+              const uint32_t c = cnt[p][tileOfS[p][id[0]]];
+              if (mxl <= peak && c < bestCnt) { bestCnt = c; bestP = p; }
+            }
+            if (bestP != p0) {
+              for (uint32_t j = 0; j < cs.arity; ++j) { load[(size_t)id[j] * K + p0]--; load[(size_t)id[j] * K + bestP]++; }
+              cnt[p0][t0]--;
+              cnt[bestP][tileOfS[bestP][id[0]]]++;
+              phaseOf[k] = (uint8_t)bestP;
+              ++moves;
+            }
+          }
+          if (!moves) break;
+        }
+      }
+      for (uint32_t k = 0; k < cs.n; ++k)
+        if (mask[k]) mainPh[phaseOf[k]][tileOfS[phaseOf[k]][cs.at(k)[0]]].ty[ty].cons.push_back(k);
+      if (getenv("PBD_PLAN_DEBUG")) {
+        // forced load: constraints with a single admissible phase
+        std::vector<uint16_t> forced((size_t)m.V * K, 0);
+        for (uint32_t k = 0; k < cs.n; ++k) {
+          if (mask[k] == 0 || (mask[k] & (mask[k] - 1)) != 0) continue;
+          const uint32_t p = (uint32_t)__builtin_ctz(mask[k]);
+          for (uint32_t j = 0; j < cs.arity; ++j) forced[(size_t)cs.at(k)[j] * K + p]++;
+        }
+        uint32_t mxF = 0, mxL = 0;
+        for (size_t i = 0; i < forced.size(); ++i) { mxF = std::max<uint32_t>(mxF, forced[i]); mxL = std::max<uint32_t>(mxL, load[i]); }
+        fprintf(stderr, "[plan] type %d max forced load %u, max load %u\n", ty, mxF, mxL);
+      }
+    };
+    // Mixed steps: the step count of a visit follows the JOINT load of its most loaded vertex.  The
+    // per-type passes above moved tets only (on top of fixed edge loads); here every constraint
+    // of either type that sits on an overloaded (vertex, phase) may move, one level at a time.
+    auto joint_repair = [&]() {
+      if (getenv("PBD_PLAN_NOJOINTREPAIR")) return;
+      std::vector<uint32_t> incOff((size_t)m.V + 1, 0), inc;   // vertex -> (type << 31 | constraint)
+      for (int ty = 0; ty < 2; ++ty)
+        for (uint32_t k = 0; k < sets[ty].n; ++k)
+          if (maskA[ty][k]) for (uint32_t j = 0; j < sets[ty].arity; ++j) incOff[sets[ty].at(k)[j] + 1]++;
+      for (uint32_t v = 0; v < m.V; ++v) incOff[v + 1] += incOff[v];
+      inc.resize(incOff[m.V]);
+      {
+        std::vector<uint32_t> cur(incOff.begin(), incOff.end() - 1);
+        for (int ty = 0; ty < 2; ++ty)
+          for (uint32_t k = 0; k < sets[ty].n; ++k)
+            if (maskA[ty][k]) for (uint32_t j = 0; j < sets[ty].arity; ++j) inc[cur[sets[ty].at(k)[j]]++] = ((uint32_t)ty << 31) | k;
+      }
+      auto peak_at = [&](int ty, uint32_t k, uint32_t p) {
+        uint32_t mxl = 0;
+        for (uint32_t j = 0; j < sets[ty].arity; ++j) mxl = std::max<uint32_t>(mxl, load[(size_t)sets[ty].at(k)[j] * K + p]);
+        return mxl;
+      };
+      auto move_to = [&](int ty, uint32_t k, uint32_t p) {
+        const uint32_t* id = sets[ty].at(k);
+        for (uint32_t j = 0; j < sets[ty].arity; ++j) { load[(size_t)id[j] * K + phaseA[ty][k]]--; load[(size_t)id[j] * K + p]++; }
+        phaseA[ty][k] = (uint8_t)p;
+      };
+      auto movable = [&](int ty, uint32_t k) { const uint8_t mk = maskA[ty][k]; return mk != 0 && (mk & (mk - 1)) != 0; };
+      auto room_for = [&](int ty, uint32_t k, uint32_t target, uint32_t avoid) {
+        for (uint32_t p = 0; p < K; ++p)
+          if (p != phaseA[ty][k] && p != avoid && (maskA[ty][k] >> p & 1) && peak_at(ty, k, p) + 1u <= target) return p;
+        return NONE;
+      };
+      uint32_t mxL = 0;
+      for (size_t i = 0; i < load.size(); ++i) mxL = std::max<uint32_t>(mxL, load[i]);
+      for (uint32_t target = mxL ? mxL - 1 : 0; target >= 1; --target) {
+        for (int pass = 0; pass < 3; ++pass) {
+          uint32_t moves = 0;
+          for (int ty = 0; ty < 2; ++ty)
+            for (uint32_t k = 0; k < sets[ty].n; ++k) {
+              if (!movable(ty, k) || peak_at(ty, k, phaseA[ty][k]) <= target) continue;
+              uint32_t p = room_for(ty, k, target, NONE);
+              if (p == NONE) {
+                // make room: a phase where exactly one vertex of k is full, and a constraint (either type) there that can leave
+                for (uint32_t q = 0; q < K && p == NONE; ++q) {
+                  if (q == phaseA[ty][k] || !(maskA[ty][k] >> q & 1)) continue;
+                  uint32_t full = NONE, nFull = 0;
+                  for (uint32_t j = 0; j < sets[ty].arity; ++j)
+                    if (load[(size_t)sets[ty].at(k)[j] * K + q] + 1u > target) { full = sets[ty].at(k)[j]; ++nFull; }
+                  if (nFull != 1 || load[(size_t)full * K + q] != target) continue;
+                  for (uint32_t a = incOff[full]; a < incOff[full + 1]; ++a) {
+                    const int ty2 = (int)(inc[a] >> 31);
+                    const uint32_t k2 = inc[a] & 0x7fffffffu;
+                    if ((ty2 == ty && k2 == k) || phaseA[ty2][k2] != q || !movable(ty2, k2)) continue;
+                    const uint32_t p2 = room_for(ty2, k2, target, phaseA[ty][k]);
+                    if (p2 == NONE) continue;
+                    move_to(ty2, k2, p2);
+                    if (peak_at(ty, k, q) + 1u <= target) { p = q; break; }
+                  }
+                }
+              }
+              if (p != NONE) { move_to(ty, k, p); ++moves; }
+            }
+          if (!moves) break;
+        }
+        size_t above = 0;
+        for (size_t i = 0; i < load.size(); ++i) above += load[i] > target;
+        if (above > (size_t)K * nTilesMax) break;
+      }
+    };
     for (int ty = 0; ty < 2; ++ty) {
       const CSet& cs = sets[ty];
       // mixed steps: a visit's step count follows the JOINT load of a vertex, so the tets are
       // balanced on top of the edge loads already placed
       if (!(mixedThreads && ty == 1 && !getenv("PBD_PLAN_NOJOINTLOAD"))) std::fill(load.begin(), load.end(), (uint16_t)0);
-      std::vector<uint8_t> mask(cs.n, 0), phaseOf(cs.n, 0);
+      std::vector<uint8_t>& mask = maskA[ty];
+      std::vector<uint8_t>& phaseOf = phaseA[ty];
+      mask.assign(cs.n, 0);
+      phaseOf.assign(cs.n, 0);
       std::vector<uint32_t> bucket[kMaxPartitions + 1];
       for (uint32_t k = 0; k < cs.n; ++k) {
         const uint32_t* id = cs.at(k);
@@ -1175,70 +1445,13 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           if (above > (size_t)K * nTilesMax) break;
         }
       }
-      // tile balance: a phase lasts as long as its fullest tile.  Move constraints out of tiles that
-      // hold more than the average into emptier admissible tiles, never raising a vertex load above
-      // the peak the passes above settled on.
-      {
-        // cap = the load 99 % of the (vertex, phase) pairs stay within: balancing must not turn
-        // the rare peak into the norm (colours follow the per-tile peak)
-        uint32_t peak = 0;
-        {
-          std::vector<uint64_t> hist(64, 0);
-          uint64_t n99 = 0, acc = 0;
-          for (size_t i = 0; i < load.size(); ++i)
-            if (load[i]) { hist[std::min<uint32_t>(load[i], 63u)]++; ++n99; }
-          n99 = n99 - n99 / 100;
-          for (uint32_t l = 0; l < 64; ++l) { acc += hist[l]; if (acc >= n99) { peak = l; break; } }
-          // one below that: a tile whose vertices all sit at the 99 % load needs ~2 more colours
-          const uint32_t margin = getenv("PBD_PLAN_CAPM") ? (uint32_t)atoi(getenv("PBD_PLAN_CAPM")) : 1u;
-          peak = peak > margin ? peak - margin : 0u;
-        }
-        std::vector<std::vector<uint32_t>> cnt(K, std::vector<uint32_t>(nTilesMax, 0));
-        uint64_t total = 0;
-        for (uint32_t k = 0; k < cs.n; ++k)
-          if (mask[k]) { cnt[phaseOf[k]][tileOfS[phaseOf[k]][cs.at(k)[0]]]++; ++total; }
-        const uint32_t mean = (uint32_t)(total / std::max<uint64_t>(1, (uint64_t)K * nTilesMax));
-        for (int sweep = 0; sweep < (getenv("PBD_PLAN_NOBAL") ? 0 : 8); ++sweep) {
-          uint32_t moves = 0;
-          for (uint32_t k = 0; k < cs.n; ++k) {
-            if (mask[k] == 0 || (mask[k] & (mask[k] - 1)) == 0) continue;
-            const uint32_t* id = cs.at(k);
-            const uint32_t p0 = phaseOf[k], t0 = tileOfS[p0][id[0]];
-            if (cnt[p0][t0] <= mean) continue;
-            uint32_t bestP = p0, bestCnt = cnt[p0][t0] - 1;   // must end strictly emptier than the source is now
-            for (uint32_t p = 0; p < K; ++p) {
-              if (p == p0 || !(mask[k] >> p & 1)) continue;
-              uint32_t mxl = 0;
-              for (uint32_t j = 0; j < cs.arity; ++j) mxl = std::max<uint32_t>(mxl, load[(size_t)id[j] * K + p] + 1u);
-              const uint32_t c = cnt[p][tileOfS[p][id[0]]];
-              if (mxl <= peak && c < bestCnt) { bestCnt = c; bestP = p; }
-            }
-            if (bestP != p0) {
-              for (uint32_t j = 0; j < cs.arity; ++j) { load[(size_t)id[j] * K + p0]--; load[(size_t)id[j] * K + bestP]++; }
-              cnt[p0][t0]--;
-              cnt[bestP][tileOfS[bestP][id[0]]]++;
-              phaseOf[k] = (uint8_t)bestP;
-              ++moves;
-            }
-          }
-          if (!moves) break;
-        }
-      }
-      for (uint32_t k = 0; k < cs.n; ++k)
-        if (mask[k]) mainPh[phaseOf[k]][tileOfS[phaseOf[k]][cs.at(k)[0]]].ty[ty].cons.push_back(k);
-      if (getenv("PBD_PLAN_DEBUG")) {
-        // forced load: constraints with a single admissible phase
-        std::vector<uint16_t> forced((size_t)m.V * K, 0);
-        for (uint32_t k : bucket[1]) {
-          const uint32_t p = (uint32_t)__builtin_ctz(mask[k]);
-          for (uint32_t j = 0; j < cs.arity; ++j) forced[(size_t)cs.at(k)[j] * K + p]++;
-        }
-        uint32_t mxF = 0, mxL = 0;
-        for (size_t i = 0; i < forced.size(); ++i) { mxF = std::max<uint32_t>(mxF, forced[i]); mxL = std::max<uint32_t>(mxL, load[i]); }
-        fprintf(stderr, "[plan] type %d max forced load %u, max load %u\n", ty, mxF, mxL);
-      }
+      if (!mixedThreads) finish_type(ty);
     }
-
+    if (mixedThreads) {
+      joint_repair();
+      finish_type(0);
+      finish_type(1);
+    }
     // ---- finish the main tiles (independent of each other: spread over host threads; the result
     // does not depend on the thread count)
     bool fits = true;
