@@ -664,6 +664,61 @@ uint32_t colour_ids(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nL
   return nc;
 }
 
+// Even out colour classes so that none holds more than `cap` constraints (what one block pass of
+// the sweep takes; a larger class costs a second colour step): constraints of oversized classes
+// move to classes with room where all their vertices are free; when the classes cannot hold
+// everything (nc * cap < n) new classes are opened.  Colourings with more than 64 classes are left
+// alone (the caller splits oversized groups anyway).  Returns the new number of classes.
+uint32_t cap_classes(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nLocal, std::vector<uint32_t>& col,
+                     uint32_t nc, uint32_t cap) {
+  if (cap == 0 || nc == 0 || nc > 64) return nc;
+  std::vector<uint32_t> size(64, 0);
+  for (uint32_t k = 0; k < n; ++k) size[col[k]]++;
+  bool over = false;
+  for (uint32_t c = 0; c < nc; ++c) over |= size[c] > cap;
+  if (!over) return nc;
+  uint32_t nc2 = std::max(nc, (n + cap - 1) / cap);
+  if (nc2 > 64) return nc;
+  std::vector<uint64_t> used(nLocal, 0);
+  for (uint32_t k = 0; k < n; ++k)
+    for (uint32_t j = 0; j < arity; ++j) used[ids[(size_t)k * arity + j]] |= 1ull << col[k];
+  auto mask_of = [&](uint32_t k) {
+    uint64_t mk = 0;
+    for (uint32_t j = 0; j < arity; ++j) mk |= used[ids[(size_t)k * arity + j]];
+    return mk;
+  };
+  for (int round = 0; round < 4; ++round) {
+    for (uint32_t k = 0; k < n; ++k) {
+      const uint32_t c = col[k];
+      if (size[c] <= cap) continue;
+      uint64_t freeMask = ~mask_of(k) & (nc2 >= 64 ? ~0ull : ((1ull << nc2) - 1));
+      uint32_t best = NONE;
+      while (freeMask) {
+        const uint32_t d = (uint32_t)__builtin_ctzll(freeMask);
+        freeMask &= freeMask - 1;
+        if (size[d] < cap && (best == NONE || size[d] < size[best])) best = d;
+      }
+      if (best == NONE) continue;
+      for (uint32_t j = 0; j < arity; ++j) used[ids[(size_t)k * arity + j]] &= ~(1ull << c);
+      for (uint32_t j = 0; j < arity; ++j) used[ids[(size_t)k * arity + j]] |= 1ull << best;
+      col[k] = best;
+      size[c]--;
+      size[best]++;
+    }
+    over = false;
+    for (uint32_t c = 0; c < nc2; ++c) over |= size[c] > cap;
+    if (!over || nc2 >= 64) break;
+    ++nc2;   // one more class and another round
+  }
+  // drop classes that stayed empty
+  std::vector<uint32_t> remap(64, NONE);
+  uint32_t m2 = 0;
+  for (uint32_t c = 0; c < nc2; ++c)
+    if (size[c]) remap[c] = m2++;
+  for (uint32_t k = 0; k < n; ++k) col[k] = remap[col[k]];
+  return m2;
+}
+
 // sort a tile's constraint list by (colour, id) given the colours of its current order
 void sort_by_colour(TypeList& tl, const std::vector<uint32_t>& col, uint32_t nColours) {
   const uint32_t n = (uint32_t)tl.cons.size();
@@ -678,14 +733,18 @@ void sort_by_colour(TypeList& tl, const std::vector<uint32_t>& col, uint32_t nCo
 }
 
 // colour the constraints of one tile locally and sort them by (colour, id)
+// `cap`: most constraints one colour step can take (0 = no limit)
 void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vector<uint32_t>& localOf,
-                 std::vector<uint32_t>& scratch, int maxIter = 48, uint32_t goal = 0, uint32_t seed = 0x9e3779b9u) {
+                 std::vector<uint32_t>& scratch, uint32_t cap, int maxIter = 48, uint32_t goal = 0,
+                 uint32_t seed = 0x9e3779b9u, uint32_t tabuBudget = 2000u) {
+  const uint32_t tabuIter = getenv("PBD_PLAN_TABU") ? (uint32_t)atoi(getenv("PBD_PLAN_TABU")) : tabuBudget;   // debug override
   const uint32_t n = (uint32_t)tl.cons.size();
   std::sort(tl.cons.begin(), tl.cons.end());
   std::vector<uint32_t> ids((size_t)n * cs.arity), col;
   for (uint32_t i = 0; i < n; ++i)
     for (uint32_t j = 0; j < cs.arity; ++j) ids[(size_t)i * cs.arity + j] = localOf[cs.at(tl.cons[i])[j]];
-  const uint32_t nc = colour_ids(ids.data(), n, cs.arity, nLocal, col, scratch, maxIter, goal, seed);
+  uint32_t nc = colour_ids(ids.data(), n, cs.arity, nLocal, col, scratch, maxIter, goal, seed, tabuIter);
+  nc = cap_classes(ids.data(), n, cs.arity, nLocal, col, nc, cap);
   sort_by_colour(tl, col, nc);
 }
 
@@ -892,7 +951,7 @@ void order_groups(const CSet sets[2], TileBuild& tb, const std::vector<uint32_t>
 }
 
 void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& localOf, std::vector<uint32_t>& scratch,
-                 uint32_t mixedThreads = 0) {
+                 const uint32_t caps[2], uint32_t mixedThreads = 0) {
   uint32_t nLocal;
   if (tb.contiguous) {
     nLocal = tb.rangeCount;
@@ -916,7 +975,7 @@ void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& local
   for (int ty = 0; ty < 2; ++ty) {
     TypeList& L = tb.ty[ty];
     if (L.cons.empty()) continue;
-    if (!tb.mixed) colour_list(sets[ty], L, nLocal, localOf, scratch);
+    if (!tb.mixed) colour_list(sets[ty], L, nLocal, localOf, scratch, caps[ty]);
     order_groups(sets, tb, localOf, ty);
   }
 }
@@ -931,7 +990,7 @@ uint32_t tile_bytes(const TileBuild& tb) {
 // Residual phases of one type: re-partition until nothing is left.
 void build_residual_phases(const CSet sets[2], int ty, std::vector<uint32_t> res, uint32_t V, uint32_t cap,
                            std::vector<std::vector<TileBuild>>& phases, std::vector<uint32_t>& localOf,
-                           std::vector<uint32_t>& scratch) {
+                           std::vector<uint32_t>& scratch, const uint32_t caps[2]) {
   const CSet& cs = sets[ty];
   std::vector<uint32_t> compactOf(V, NONE), tileOfSlot(V, NONE);
   const uint32_t target = std::max(16u, (uint32_t)(cap * 0.75));
@@ -970,7 +1029,7 @@ void build_residual_phases(const CSet sets[2], int ty, std::vector<uint32_t> res
     std::vector<TileBuild> kept;
     for (auto& tb : ph) {
       if (tb.ty[ty].cons.empty()) continue;
-      finish_tile(sets, tb, localOf, scratch);
+      finish_tile(sets, tb, localOf, scratch, caps);
       kept.push_back(std::move(tb));
     }
     for (auto& vs : g.verts)
@@ -993,7 +1052,9 @@ void colour_and_order(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t 
   TypeList L;
   L.cons.resize(n);
   std::iota(L.cons.begin(), L.cons.end(), 0u);
-  colour_list(cs, L, nVerts, localOf, scratch);
+  // a whole body is coloured once per topology (the batch backend caches it) and every colour is a
+  // block barrier per iteration for every body of that topology: a long tabu search pays
+  colour_list(cs, L, nVerts, localOf, scratch, maxGroup, 48, 0, 0x9e3779b9u, 30000u);
   for (size_t i = 0; i < L.cons.size();) {
     size_t j = i;
     while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
@@ -1023,6 +1084,8 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   // interleaved order, one thread per tet: edges and tets of a tile visit share the colour steps
   const bool noMixed = getenv("PBD_PLAN_MIXED") && atoi(getenv("PBD_PLAN_MIXED")) == 0;   // debug: A/B against separate sweeps
   const uint32_t mixedThreads = (fused && opts.lanes_per_tet <= 1 && !noMixed) ? blockThreads : 0u;
+  // most constraints of one type a colour step can take: one block pass
+  const uint32_t caps[2] = {blockThreads, std::max(1u, blockThreads / std::max(1u, opts.lanes_per_tet))};
   if (opts.partitions > kMaxPartitions) { err = "partitions must be <= 8"; return false; }
 
   // body frame, extents -> axis order for the k-d levels
@@ -1470,7 +1533,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       auto worker = [&](std::vector<uint32_t>& lo, std::vector<uint32_t>& sc) {
         for (size_t i; (i = next.fetch_add(1)) < work.size();) {
           TileBuild& tb = *work[i];
-          finish_tile(sets, tb, lo, sc, mixedThreads);
+          finish_tile(sets, tb, lo, sc, caps, mixedThreads);
           const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
           if (nv > 65535u || tile_bytes(tb) > smemBytes) ok = false;
         }
@@ -1535,7 +1598,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           for (uint32_t attempt2 = 0; attempt2 < 4 && L.nColours > goal; ++attempt2) {
             TypeList trial;
             trial.cons = L.cons;
-            colour_list(sets[ty], trial, nLocal, lo, sc, 160, goal, 0x85ebca6bu * (attempt2 + 1));
+            colour_list(sets[ty], trial, nLocal, lo, sc, caps[ty], 160, goal, 0x85ebca6bu * (attempt2 + 1));
             if (trial.nColours < L.nColours) L = std::move(trial);
           }
           order_groups(sets, tb, lo, ty);
@@ -1565,7 +1628,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       bool ok = true;
       for (int ty = 0; ty < 2; ++ty) {
         resPh[ty].clear();
-        build_residual_phases(sets, ty, resid[ty], m.V, resCap, resPh[ty], localOf, scratch);
+        build_residual_phases(sets, ty, resid[ty], m.V, resCap, resPh[ty], localOf, scratch, caps);
         for (auto& ph : resPh[ty])
           for (auto& tb : ph)
             if (tile_bytes(tb) > smemBytes) ok = false;
