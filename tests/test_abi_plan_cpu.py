@@ -113,6 +113,30 @@ def test_interleaved_tile_schedule_is_valid_and_sequence_consistent(mesh, tile_v
     assert info["partitions"] >= 1 and info["tiles"] >= 1
 
 
+@pytest.mark.parametrize("order", ["strict", "interleaved"])
+def test_colour_steps_fit_one_block_pass(order, capi, meshgen):
+    """The sweep loops take a colour step in ONE pass of the 512-thread block: the planner caps every
+    colour class at 512 constraints (cap_classes) and, with mixed steps, keeps a step's edges and
+    tets in separate warps whose sum fits the block."""
+    x0, tets, edges = meshgen.kuhn_grid(20)                       # 48k tets: ~8 tiles of ~1k vertices per partition
+    om = capi.ORDER_INTERLEAVED if order == "interleaved" else capi.ORDER_STRICT
+    p = capi.Plan(x0, edges, tets, capi.Options(backend=capi.BACKEND_TILE, order_mode=om))
+    (eph, etl, eco), (tph, ttl, tco) = p.slots(False), p.slots(True)
+    nco = int(max(eco.max(), tco.max())) + 1
+    ke, ce = np.unique(etl.astype(np.int64) * nco + eco, return_counts=True)
+    kt, ct = np.unique(ttl.astype(np.int64) * nco + tco, return_counts=True)
+    assert ce.max() <= 512 and ct.max() <= 512
+    if order == "interleaved":                                    # tile ids are unique per (phase, tile): same id = same visit
+        both = np.intersect1d(ke, kt)
+        assert len(both) > 0
+        pad = lambda c: (c + 31) // 32 * 32
+        assert (pad(ce[np.isin(ke, both)]) + pad(ct[np.isin(kt, both)])).max() <= 512
+    # fewer steps than a plain first-fit colouring of the same lists would need (the Kuhn grid's
+    # vertex valences are 14 edges / 24 tets: 4 phases -> about 4 + 7 colours per visit)
+    steps_per_visit = (len(np.union1d(ke, kt)) if order == "interleaved" else len(ke) + len(kt)) / len(np.unique(np.concatenate([etl, ttl])))
+    assert steps_per_visit <= (14 if order == "interleaved" else 9)
+
+
 def test_stream_colour_counts_match_survey_probe(capi, meshgen, golden):
     """greedy first-fit needs 30 tet + 15 edge colours on the Kuhn grid and
     101 tet + 54 edge colours on default_Tet."""
