@@ -45,6 +45,40 @@ namespace {
 constexpr uint32_t NONE = 0xffffffffu;
 constexpr uint32_t kMaxPartitions = 8;
 
+// Debug switches of the planner, read from the environment ONCE (A/B runs: tools/gpu_ab_env.sh).
+// None of them is needed in production; the defaults are what every measurement in DESIGN.md uses.
+struct PlanKnobs {
+  bool debug;            // PBD_PLAN_DEBUG=1          stage timings and statistics on stderr
+  bool mixed;            // PBD_PLAN_MIXED=0          interleaved order without mixed colour steps
+  bool potential;        // PBD_PLAN_NOPOT=1          skip the potential-descent pass of the assignment
+  bool repair;           // PBD_PLAN_NOREPAIR=1       skip the per-type peak repair
+  bool jointRepair;      // PBD_PLAN_NOJOINTREPAIR=1  skip the joint (edges + tets) peak repair
+  bool jointLoad;        // PBD_PLAN_NOJOINTLOAD=1    balance the tets without the edge loads
+  bool tileBalance;      // PBD_PLAN_NOBAL=1          skip the tile balance
+  int snapLevels;        // PBD_PLAN_NOSNAP=n         k-d levels whose cuts are NOT gap-snapped (default 4)
+  int capMargin;         // PBD_PLAN_CAPM=n           tile balance: cap = p99 load - n (default 1)
+  int tabu;              // PBD_PLAN_TABU=n           tabu-search iterations per class (-1: built-in budgets)
+};
+const PlanKnobs& knobs() {
+  static const PlanKnobs k = [] {
+    auto flag = [](const char* n) { const char* e = getenv(n); return e && atoi(e) != 0; };
+    auto num = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
+    PlanKnobs q;
+    q.debug = getenv("PBD_PLAN_DEBUG") != nullptr;
+    q.mixed = num("PBD_PLAN_MIXED", 1) != 0;
+    q.potential = !flag("PBD_PLAN_NOPOT");
+    q.repair = !flag("PBD_PLAN_NOREPAIR");
+    q.jointRepair = !flag("PBD_PLAN_NOJOINTREPAIR");
+    q.jointLoad = !flag("PBD_PLAN_NOJOINTLOAD");
+    q.tileBalance = !flag("PBD_PLAN_NOBAL");
+    q.snapLevels = num("PBD_PLAN_NOSNAP", 4);
+    q.capMargin = num("PBD_PLAN_CAPM", 1);
+    q.tabu = num("PBD_PLAN_TABU", -1);
+    return q;
+  }();
+  return k;
+}
+
 double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -59,7 +93,7 @@ double now_ms() {
 // fall BETWEEN vertex planes (and the shifted partitions' cuts between other planes), on
 // unstructured meshes the snap is a no-op in effect.
 static int nosnapLevels() {
-  static const int v = getenv("PBD_PLAN_NOSNAP") ? atoi(getenv("PBD_PLAN_NOSNAP")) : 4;   // debug override
+  static const int v = knobs().snapLevels;
   return v;
 }
 
@@ -742,7 +776,7 @@ void sort_by_colour(TypeList& tl, const std::vector<uint32_t>& col, uint32_t nCo
 void colour_list(const CSet& cs, TypeList& tl, uint32_t nLocal, const std::vector<uint32_t>& localOf,
                  std::vector<uint32_t>& scratch, uint32_t cap, int maxIter = 48, uint32_t goal = 0,
                  uint32_t seed = 0x9e3779b9u, uint32_t tabuBudget = 2000u) {
-  const uint32_t tabuIter = getenv("PBD_PLAN_TABU") ? (uint32_t)atoi(getenv("PBD_PLAN_TABU")) : tabuBudget;   // debug override
+  const uint32_t tabuIter = knobs().tabu >= 0 ? (uint32_t)knobs().tabu : tabuBudget;
   const uint32_t n = (uint32_t)tl.cons.size();
   std::sort(tl.cons.begin(), tl.cons.end());
   std::vector<uint32_t> ids((size_t)n * cs.arity), col;
@@ -774,7 +808,7 @@ void colour_joint(const CSet sets[2], TileBuild& tb, uint32_t nLocal, const std:
     for (uint32_t j = 0; j < 4; ++j) ids[(size_t)i * 4 + j] = localOf[sets[1].at(LT.cons[i])[j]];
   for (uint32_t i = 0; i < nE; ++i)
     for (uint32_t j = 0; j < 4; ++j) ids[(size_t)(nT + i) * 4 + j] = localOf[sets[0].at(LE.cons[i])[j & 1u]];
-  static const uint32_t tabuIter = getenv("PBD_PLAN_TABU") ? (uint32_t)atoi(getenv("PBD_PLAN_TABU")) : 4000u;   // debug override
+  const uint32_t tabuIter = knobs().tabu >= 0 ? (uint32_t)knobs().tabu : 4000u;
   uint32_t nc = colour_ids(ids.data(), n, 4, nLocal, col, scratch, maxIter, goal, seed, tabuIter);
 
   auto pad32 = [](uint32_t x) { return (x + 31u) & ~31u; };
@@ -914,7 +948,7 @@ void bank_order(const CSet& cs, const std::vector<uint32_t>& localOf, uint32_t* 
     alive.erase(std::remove_if(alive.begin(), alive.end(), [&](uint32_t a2) { return gone[a2] != 0; }), alive.end());
   }
   std::copy(out.begin(), out.end(), cons);
-  if (getenv("PBD_PLAN_DEBUG")) {
+  if (knobs().debug) {
     uint64_t wf = 0, ideal = 0;
     for (uint32_t q0 = 0; q0 < n; q0 += 8)
       for (uint32_t r = 0; r < ar; ++r) {
@@ -1077,7 +1111,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   const double t0 = now_ms();
   // PBD_PLAN_DEBUG: wall time of every planning stage
   double tStage = t0;
-  const bool stageLog = getenv("PBD_PLAN_DEBUG") != nullptr;
+  const bool stageLog = knobs().debug;
 #define PBD_PLAN_STAGE(name) do { if (stageLog) { const double t1_ = now_ms(); fprintf(stderr, "[plan] %-16s %8.0f ms\n", name, t1_ - tStage); tStage = t1_; } } while (0)
   if (nSMs == 0) nSMs = 148;
   if (smemBytes < 16384) { err = "shared memory too small for a vertex tile"; return false; }
@@ -1091,7 +1125,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   if (blockThreads % 32 || blockThreads > 512) { err = "block_threads must be a multiple of 32, <= 512"; return false; }
   plan.blockThreads = blockThreads;
   // interleaved order, one thread per tet: edges and tets of a tile visit share the colour steps
-  const bool noMixed = getenv("PBD_PLAN_MIXED") && atoi(getenv("PBD_PLAN_MIXED")) == 0;   // debug: A/B against separate sweeps
+  const bool noMixed = !knobs().mixed;   // debug: A/B against separate sweeps
   const uint32_t mixedThreads = (fused && opts.lanes_per_tet <= 1 && !noMixed) ? blockThreads : 0u;
   // most constraints of one type a colour step can take: one block pass
   const uint32_t caps[2] = {blockThreads, std::max(1u, blockThreads / std::max(1u, opts.lanes_per_tet))};
@@ -1232,7 +1266,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           n99 = n99 - n99 / 100;
           for (uint32_t l = 0; l < 64; ++l) { acc += hist[l]; if (acc >= n99) { peak = l; break; } }
           // one below that: a tile whose vertices all sit at the 99 % load needs ~2 more colours
-          const uint32_t margin = getenv("PBD_PLAN_CAPM") ? (uint32_t)atoi(getenv("PBD_PLAN_CAPM")) : 1u;
+          const uint32_t margin = (uint32_t)std::max(0, knobs().capMargin);
           peak = peak > margin ? peak - margin : 0u;
         }
         std::vector<std::vector<uint32_t>> cnt(K, std::vector<uint32_t>(nTilesMax, 0));
@@ -1240,7 +1274,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
         for (uint32_t k = 0; k < cs.n; ++k)
           if (mask[k]) { cnt[phaseOf[k]][tileOfS[phaseOf[k]][cs.at(k)[0]]]++; ++total; }
         const uint32_t mean = (uint32_t)(total / std::max<uint64_t>(1, (uint64_t)K * nTilesMax));
-        for (int sweep = 0; sweep < (getenv("PBD_PLAN_NOBAL") ? 0 : 8); ++sweep) {
+        for (int sweep = 0; sweep < (knobs().tileBalance ? 8 : 0); ++sweep) {
           uint32_t moves = 0;
           for (uint32_t k = 0; k < cs.n; ++k) {
             if (mask[k] == 0 || (mask[k] & (mask[k] - 1)) == 0) continue;
@@ -1268,7 +1302,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       }
       for (uint32_t k = 0; k < cs.n; ++k)
         if (mask[k]) mainPh[phaseOf[k]][tileOfS[phaseOf[k]][cs.at(k)[0]]].ty[ty].cons.push_back(k);
-      if (getenv("PBD_PLAN_DEBUG")) {
+      if (knobs().debug) {
         // forced load: constraints with a single admissible phase
         std::vector<uint16_t> forced((size_t)m.V * K, 0);
         for (uint32_t k = 0; k < cs.n; ++k) {
@@ -1285,7 +1319,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     // per-type passes above moved tets only (on top of fixed edge loads); here every constraint
     // of either type that sits on an overloaded (vertex, phase) may move, one level at a time.
     auto joint_repair = [&]() {
-      if (getenv("PBD_PLAN_NOJOINTREPAIR")) return;
+      if (!knobs().jointRepair) return;
       std::vector<uint32_t> incOff((size_t)m.V + 1, 0), inc;   // vertex -> (type << 31 | constraint)
       for (int ty = 0; ty < 2; ++ty)
         for (uint32_t k = 0; k < sets[ty].n; ++k)
@@ -1355,7 +1389,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       const CSet& cs = sets[ty];
       // mixed steps: a visit's step count follows the JOINT load of a vertex, so the tets are
       // balanced on top of the edge loads already placed
-      if (!(mixedThreads && ty == 1 && !getenv("PBD_PLAN_NOJOINTLOAD"))) std::fill(load.begin(), load.end(), (uint16_t)0);
+      if (!(mixedThreads && ty == 1 && knobs().jointLoad)) std::fill(load.begin(), load.end(), (uint16_t)0);
       std::vector<uint8_t>& mask = maskA[ty];
       std::vector<uint8_t>& phaseOf = phaseA[ty];
       mask.assign(cs.n, 0);
@@ -1374,7 +1408,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
         bucket[__builtin_popcount(mk)].push_back(k);
       }
       resid[ty] = bucket[0];
-      if (getenv("PBD_PLAN_DEBUG")) {
+      if (knobs().debug) {
         fprintf(stderr, "[plan] type %d admissible-phase popcount histogram:", ty);
         for (uint32_t f = 0; f <= K; ++f) fprintf(stderr, " %zu", bucket[f].size());
         fprintf(stderr, "\n");
@@ -1401,7 +1435,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       PBD_PLAN_STAGE("  greedy");
       // potential descent: move a constraint to another admissible phase when that lowers the sum of
       // squared vertex loads -- evens the loads out where the min-max rule below sees only plateaus
-      for (int sweep = 0; sweep < (getenv("PBD_PLAN_NOPOT") ? 0 : 12); ++sweep) {
+      for (int sweep = 0; sweep < (knobs().potential ? 12 : 0); ++sweep) {
         uint32_t moves = 0;
         for (uint32_t k = 0; k < cs.n; ++k) {
           if (mask[k] == 0 || (mask[k] & (mask[k] - 1)) == 0) continue;   // residual or forced
@@ -1458,7 +1492,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       // at a time: every constraint on an overloaded (vertex, phase) moves to an admissible phase
       // with room at all its vertices, if need be after making room there by moving ONE other
       // constraint away.  Stops at the level that leaves more than one such vertex per tile visit.
-      if (!getenv("PBD_PLAN_NOREPAIR")) {
+      if (knobs().repair) {
         std::vector<uint32_t> incOff((size_t)m.V + 1, 0), inc;
         for (uint32_t k = 0; k < cs.n; ++k)
           if (mask[k]) for (uint32_t j = 0; j < cs.arity; ++j) incOff[cs.at(k)[j] + 1]++;
@@ -1807,7 +1841,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   }
   PBD_PLAN_STAGE("flatten");
   plan.planMs = now_ms() - t0;
-  if (getenv("PBD_PLAN_DEBUG"))
+  if (knobs().debug)
     fprintf(stderr, "[plan] shared-memory gathers: %.3f wavefronts per quarter-warp role (1.0 = conflict-free)\n",
             (double)g_bankWavefronts.exchange(0) / (double)std::max<uint64_t>(1, g_bankIdeal.exchange(0)));
   return true;
