@@ -1577,7 +1577,31 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       tb.rangeBegin = tile0Begin[t];
       tb.rangeCount = tile0Begin[t + 1] - tile0Begin[t];
     }
+    // Cheap necessary condition first: a tile's vertices and constraint records (with the smallest
+    // possible colour-group tables) must fit.  A tile count that fails it is abandoned before any
+    // colouring (a failed attempt used to cost as much as the successful one).
     {
+      std::vector<uint32_t> stamp(m.V, NONE);
+      uint32_t tileId = 0;
+      for (uint32_t p = 0; p < K && fits; ++p)
+        for (auto& tb : mainPh[p]) {
+          uint32_t nv = tb.rangeCount;
+          if (!tb.contiguous) {
+            nv = 0;
+            for (int ty = 0; ty < 2; ++ty)
+              for (uint32_t k : tb.ty[ty].cons)
+                for (uint32_t j = 0; j < sets[ty].arity; ++j) {
+                  const uint32_t sl = sets[ty].at(k)[j];
+                  if (stamp[sl] != tileId) { stamp[sl] = tileId; ++nv; }
+                }
+          }
+          ++tileId;
+          const uint32_t nE = (uint32_t)tb.ty[0].cons.size(), nT = (uint32_t)tb.ty[1].cons.size();
+          const uint32_t rec = tile_record_bytes(tb.contiguous ? 0u : nv, nE ? 1u : 0u, nT ? 1u : 0u, nE, nT);
+          if (nv > 65535u || 16u * nv + 2u * rec > smemBytes) { fits = false; break; }
+        }
+    }
+    if (fits) {
       std::vector<TileBuild*> work;
       for (uint32_t p = 0; p < K; ++p)
         for (auto& tb : mainPh[p]) work.push_back(&tb);
@@ -1585,6 +1609,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       std::atomic<bool> ok{true};
       auto worker = [&](std::vector<uint32_t>& lo, std::vector<uint32_t>& sc) {
         for (size_t i; (i = next.fetch_add(1)) < work.size();) {
+          if (!ok.load(std::memory_order_relaxed)) break;   // some tile does not fit: this attempt is void anyway
           TileBuild& tb = *work[i];
           finish_tile(sets, tb, lo, sc, caps, mixedThreads);
           const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
