@@ -350,6 +350,10 @@ def main():
     ap.add_argument("--shard", action="store_true",
                     help="with --gpus N > 1: ONE body of the workload spread over the N GPUs (tiles of other ranks' "
                          "vertices are read/written in place over NVLink; strong scaling) instead of one body per GPU")
+    ap.add_argument("--fast", action="store_true",
+                    help="PBD_FLAG_FAST_ARITH: FFMA / SFU forms of the projections (tolerance-validated, not bit-exact)")
+    ap.add_argument("--tagged", action="store_true",
+                    help="PBD_FLAG_TAGGED_HANDOVER: positions travel between tiles as {value, tag} pairs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
     args = ap.parse_args()
@@ -392,7 +396,8 @@ def main():
     opt = capi.Options(backend={"auto": 0, "stream": 1, "tile": 2}[args.backend],
                        order_mode=1 if args.order == "interleaved" else 0,
                        block_threads=args.block_threads, tile_vertices=args.tile_vertices,
-                       lanes_per_tet=args.lanes, partitions=args.partitions, tiles_per_sm=args.tiles_per_sm)
+                       lanes_per_tet=args.lanes, partitions=args.partitions, tiles_per_sm=args.tiles_per_sm,
+                       flags=(capi.FLAG_FAST_ARITH if args.fast else 0) | (capi.FLAG_TAGGED_HANDOVER if args.tagged else 0))
 
     t0 = time.perf_counter()
     sharded = args.shard and world > 1

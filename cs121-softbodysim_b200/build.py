@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpbd_b200.so")
 SOURCES = ["pbd_plan.cpp", "pbd_tileplan.cpp", "pbd_stream.cu", "pbd_tile.cu", "pbd_batch.cu", "pbd_capi.cu"]
-HEADERS = ["pbd_plan.h", "pbd_body.h", "pbd_math.cuh", os.path.join("..", "..", "include", "pbd_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "pbd_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only; no PTX for other archs, no fallbacks

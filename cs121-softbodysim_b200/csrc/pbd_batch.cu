@@ -20,6 +20,8 @@
 // pbd_batch_get_schedule_order -- the unmodified reference run on the permuted arrays matches bit
 // for bit (tests/test_parity_gpu.py).
 #include <chrono>
+#include <cstddef>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -60,6 +62,8 @@ struct BatchParams {
   uint32_t recStride;
 };
 
+// LANES: threads cooperating on one tet (1, 2, 4: bit-identical results); FAST: PBD_FLAG_FAST_ARITH forms
+template <int LANES, bool FAST>
 __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -95,8 +99,8 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
           for (uint32_t i = tid; i < h.vertCount; i += nth) { float4 p = sv[i]; ground_vertex(p, k); sv[i] = p; }
           __syncthreads();
         }
-        sweep_edges(h, 0, svOff, k.alphaEdge, nullptr);
-        sweep_tets<1>(h, 0, svOff, k.alphaTet, nullptr);
+        sweep_edges<FAST>(h, 0, svOff, k.alphaEdge, nullptr);
+        sweep_tets<LANES, FAST>(h, 0, svOff, k.alphaTet, nullptr);
       }
       const bool last = sub + 1 == P.substeps;
       for (uint32_t i = tid; i < h.vertCount; i += nth) {
@@ -157,6 +161,13 @@ struct pbd_batch {
   uint64_t bytes = 0;
   double planMs = 0.0, uploadMs = 0.0;
   bool pending = false;
+  uint32_t lanes = 1;
+  bool fast = false;
+  const void* kernel() const {
+    if (fast) return (const void*)batch_frame_kernel<1, true>;
+    return lanes == 2 ? (const void*)batch_frame_kernel<2, false>
+           : lanes == 4 ? (const void*)batch_frame_kernel<4, false> : (const void*)batch_frame_kernel<1, false>;
+  }
 
   ~pbd_batch() {
     cudaFree(d.pos); cudaFree(d.prev); cudaFree(d.vel); cudaFree(d.edgeLam); cudaFree(d.tetLam);
@@ -192,7 +203,6 @@ extern "C" {
 pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const uint64_t* vOff, const uint64_t* eOff,
                             const uint64_t* tOff, const float* x0, const uint32_t* edgeIds, const uint32_t* tetIds,
                             int device, const pbd_options* opts, int* status) {
-  (void)opts;
   if (status) *status = PBD_OK;
   if (!params || !vOff || !eOff || !tOff) { bfail(PBD_ERR_INVALID, "null argument", status); return nullptr; }
   const uint64_t Vtot = vOff[nBodies], Etot = eOff[nBodies], Ttot = tOff[nBodies];
@@ -202,6 +212,8 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
     if (vOff[b + 1] < vOff[b] || eOff[b + 1] < eOff[b] || tOff[b + 1] < tOff[b]) { bfail(PBD_ERR_INVALID, "offsets must be non-decreasing", status); return nullptr; }
     const uint64_t Vb = vOff[b + 1] - vOff[b];
     if (Vb > 65535) { bfail(PBD_ERR_UNSUPPORTED, "a batch body has more than 65535 vertices: use pbd_create for it", status); return nullptr; }
+    for (uint64_t i = 3 * vOff[b]; i < 3 * vOff[b + 1]; ++i)
+      if (!std::isfinite(x0[i])) { bfail(PBD_ERR_INVALID, "x0 is not finite in body " + std::to_string(b), status); return nullptr; }
     for (uint64_t i = 2 * eOff[b]; i < 2 * eOff[b + 1]; ++i)
       if (edgeIds[i] >= Vb) { bfail(PBD_ERR_INDEX, "edge index out of range in body " + std::to_string(b), status); return nullptr; }
     for (uint64_t i = 4 * tOff[b]; i < 4 * tOff[b + 1]; ++i)
@@ -220,7 +232,8 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
     bfail(e == cudaErrorMemoryAllocation ? PBD_ERR_OOM : PBD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e), status);
     return nullptr;
   };
-  if ((ce = cudaSetDevice(device)) != cudaSuccess) return cbail(ce, "cudaSetDevice");
+  DeviceScope onDevice(device);
+  if ((ce = onDevice.err) != cudaSuccess) return cbail(ce, "cudaSetDevice");
   cudaDeviceProp prop{};
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cbail(ce, "cudaGetDeviceProperties");
   const size_t smemLimit = prop.sharedMemPerBlockOptin > 1024 ? prop.sharedMemPerBlockOptin - 1024 : 0;
@@ -230,6 +243,12 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
   B->params = *params;
   B->nBodies = nBodies;
   B->Vtot = Vtot; B->Etot = Etot; B->Ttot = Ttot;
+  // options honoured by the batch backend: PBD_FLAG_FAST_ARITH and lanes_per_tet (struct_size-guarded)
+  if (opts) {
+    const uint32_t sz = opts->struct_size ? opts->struct_size : (uint32_t)sizeof(pbd_options);
+    if (sz >= offsetof(pbd_options, flags) + 4u) B->fast = (opts->flags & PBD_FLAG_FAST_ARITH) != 0u;
+    if (sz >= offsetof(pbd_options, lanes_per_tet) + 4u && !B->fast && (opts->lanes_per_tet == 2 || opts->lanes_per_tet == 4)) B->lanes = opts->lanes_per_tet;
+  }
 
   // ---- host: per-body derived state (reference init helpers, caller's order) + colouring
   const double tPlan = wall_ms();
@@ -258,11 +277,14 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
     if (!col) {
       col = std::make_shared<Coloured>();
       colour_and_order(m.edges, Eb, 2, Vb, 512, col->eOrder, col->eCounts);   // 512 = the kernel's block size
-      colour_and_order(m.tets, Tb, 4, Vb, 512, col->tOrder, col->tCounts);
+      colour_and_order(m.tets, Tb, 4, Vb, 512 / B->lanes, col->tOrder, col->tCounts);
     }
     std::copy(col->eOrder.begin(), col->eOrder.end(), B->edgeOrder.begin() + eOff[b]);
     std::copy(col->tOrder.begin(), col->tOrder.end(), B->tetOrder.begin() + tOff[b]);
     const uint32_t nEG = (uint32_t)col->eCounts.size(), nTG = (uint32_t)col->tCounts.size();
+    // the sweeps project a colour group in ONE pass of the 512-thread block: a larger group would lose constraints
+    for (uint32_t cnt : col->eCounts) if (cnt > 512u) { bfail(PBD_ERR_INVALID, "internal: edge colour group exceeds the block", status); return nullptr; }
+    for (uint32_t cnt : col->tCounts) if (cnt * B->lanes > 512u) { bfail(PBD_ERR_INVALID, "internal: tet colour group exceeds the block", status); return nullptr; }
     B->edgeColorsMax = std::max(B->edgeColorsMax, nEG);
     B->tetColorsMax = std::max(B->tetColorsMax, nTG);
     B->maxVerts = std::max(B->maxVerts, Vb);
@@ -338,9 +360,9 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
   B->bytes += sizeof(float4) * Vtot + sizeof(float) * ((size_t)eDev + tDev + 3 * Vtot);
   if ((ce = upload_vec(&B->blob, blob, B->bytes)) != cudaSuccess) return cbail(ce, "upload blob");
   if ((ce = upload_vec(&B->bodies, descs, B->bytes)) != cudaSuccess) return cbail(ce, "upload bodies");
-  if ((ce = cudaFuncSetAttribute(batch_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smemBytes)) != cudaSuccess) return cbail(ce, "cudaFuncSetAttribute");
+  if ((ce = cudaFuncSetAttribute(B->kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smemBytes)) != cudaSuccess) return cbail(ce, "cudaFuncSetAttribute");
   int perSM = 0;
-  if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, batch_frame_kernel, 512, B->smemBytes)) != cudaSuccess) return cbail(ce, "occupancy");
+  if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, B->kernel(), 512, B->smemBytes)) != cudaSuccess) return cbail(ce, "occupancy");
   if (perSM < 1) { bfail(PBD_ERR_UNSUPPORTED, "batch kernel does not fit on an SM", status); return nullptr; }
   B->grid = std::max(1u, std::min(nBodies, (uint32_t)(perSM * prop.multiProcessorCount)));
   if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return cbail(ce, "cudaDeviceSynchronize");
@@ -350,7 +372,8 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
 
 int pbd_batch_step_async(pbd_batch* b, float dt, uint32_t frames) {
   if (!b) return bfail(PBD_ERR_INVALID, "batch is null");
-  BCU(cudaSetDevice(b->device));
+  DeviceScope onDevice(b->device);
+  BCU(onDevice.err);
   const StepConsts k = make_consts(b->params, dt);
   BCU(cudaMemcpyAsync(b->d.consts, &k, sizeof(k), cudaMemcpyHostToDevice, b->stream));
   BatchParams P{};
@@ -360,8 +383,10 @@ int pbd_batch_step_async(pbd_batch* b, float dt, uint32_t frames) {
   P.recStride = b->recStride;
   BCU(cudaEventRecord(b->ev0, b->stream));
   for (uint32_t f = 0; f < frames; ++f) {
-    if (b->nBodies) batch_frame_kernel<<<b->grid, 512, b->smemBytes, b->stream>>>(P);
-    BCU(cudaGetLastError());
+    if (b->nBodies) {
+      void* args[] = {&P};
+      BCU(cudaLaunchKernel(b->kernel(), dim3(b->grid), dim3(512), args, b->smemBytes, b->stream));
+    }
   }
   BCU(cudaEventRecord(b->ev1, b->stream));
   b->pending = true;
@@ -370,7 +395,8 @@ int pbd_batch_step_async(pbd_batch* b, float dt, uint32_t frames) {
 
 int pbd_batch_sync(pbd_batch* b, double* device_ms) {
   if (!b) return bfail(PBD_ERR_INVALID, "batch is null");
-  BCU(cudaSetDevice(b->device));
+  DeviceScope onDevice(b->device);
+  BCU(onDevice.err);
   BCU(cudaStreamSynchronize(b->stream));
   if (device_ms) {
     float ms = 0.f;
@@ -395,7 +421,8 @@ int pbd_batch_step(pbd_batch* b, float dt, pbd_step_stats* stats) {
 int pbd_batch_read_positions(pbd_batch* b, float* out, double* packMs) {
   if (!b || !out) return bfail(PBD_ERR_INVALID, "null argument");
   const double t0 = wall_ms();
-  BCU(cudaSetDevice(b->device));
+  DeviceScope onDevice(b->device);
+  BCU(onDevice.err);
   BCU(launch_pack(b->d, b->stream));
   if (b->Vtot) BCU(cudaMemcpyAsync(out, b->d.packed, sizeof(float) * 3 * b->Vtot, cudaMemcpyDeviceToHost, b->stream));
   BCU(cudaStreamSynchronize(b->stream));
@@ -420,7 +447,7 @@ int pbd_batch_get_info(const pbd_batch* b, pbd_info* out) {
   out->tiles = b->nBodies;
   out->launches_per_frame = 1;
   out->grid_blocks = b->grid; out->block_threads = 512;
-  out->partitions = 1; out->lanes_per_tet = 1;
+  out->partitions = 1; out->lanes_per_tet = b->lanes;
   out->device_bytes = b->bytes;
   out->algorithmic_bytes_per_substep = algorithmic_bytes_per_substep((uint32_t)b->Vtot, (uint32_t)b->Etot, (uint32_t)b->Ttot, b->params.iterations);
   out->plan_ms = b->planMs;
@@ -430,7 +457,7 @@ int pbd_batch_get_info(const pbd_batch* b, pbd_info* out) {
 
 void pbd_batch_destroy(pbd_batch* b) {
   if (!b) return;
-  cudaSetDevice(b->device);
+  DeviceScope onDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   delete b;
 }

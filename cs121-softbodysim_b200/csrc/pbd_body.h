@@ -53,6 +53,10 @@ class Backend {
   virtual void debug_dump() {}  // PBD_TILE_TRACE: per-phase timing of the last frame to stderr  // frame shape changed (set_params)
   virtual uint64_t device_bytes() const = 0;
   virtual void fill_info(pbd_info& info) const {}
+  // true (once) if a kernel gave up waiting for another CTA / GPU since the last call (bounded spins)
+  virtual bool take_abort() { return false; }
+  // bring d.pos up to date before the host reads it (backends that keep positions in another layout)
+  virtual cudaError_t export_pos(const DeviceArrays&, cudaStream_t) { return cudaSuccess; }
   // one body across several GPUs (tile backend only)
   virtual uint32_t shard_world() const { return 1; }
   virtual uint32_t shard_rank() const { return 0; }
@@ -72,6 +76,20 @@ Backend* make_tile_backend(const pbd_options& opts, int device);
 cudaError_t launch_pack(const DeviceArrays& d, cudaStream_t s);
 
 StepConsts make_consts(const pbd_params& p, float dt);
+
+// Every entry point runs on its handle's device and leaves the caller's current device as it found it.
+struct DeviceScope {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceScope(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != dev) { err = cudaSetDevice(dev); switched = err == cudaSuccess; }
+  }
+  ~DeviceScope() { if (switched && prev >= 0) cudaSetDevice(prev); }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
 
 // message returned by pbd_last_error() on this thread (pbd_capi.cu)
 void set_last_error(const std::string& msg);

@@ -174,7 +174,8 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
   }
   if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
   if (device >= nDev) { fail(PBD_ERR_INVALID, "device ordinal out of range", status); return nullptr; }
-  if ((ce = cudaSetDevice(device)) != cudaSuccess) { cuda_fail(ce, "cudaSetDevice", status); return nullptr; }
+  DeviceScope onDevice(device);
+  if ((ce = onDevice.err) != cudaSuccess) { cuda_fail(ce, "cudaSetDevice", status); return nullptr; }
 
   std::unique_ptr<pbd_handle> h(new pbd_handle());
   h->device = device;
@@ -256,7 +257,7 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
 
 void pbd_destroy(pbd_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceScope onDevice(h->device);
   cudaStreamSynchronize(h->stream);
   delete h;
 }
@@ -264,7 +265,8 @@ void pbd_destroy(pbd_handle* h) {
 const char* pbd_backend_name(const pbd_handle* h) { return h && h->be ? h->be->name() : "none"; }
 
 static int enqueue_frames(pbd_handle* h, float dt, uint32_t frames) {
-  CU(cudaSetDevice(h->device));
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
   const StepConsts k = make_consts(h->params, dt);
   CU(cudaMemcpyAsync(h->d.consts, &k, sizeof(k), cudaMemcpyHostToDevice, h->stream));
   const FrameShape f = h->shape();
@@ -282,7 +284,8 @@ int pbd_step_async(pbd_handle* h, float dt, uint32_t frames) {
 
 int pbd_sync(pbd_handle* h, double* device_ms) {
   if (!h) return fail(PBD_ERR_INVALID, "handle is null");
-  CU(cudaSetDevice(h->device));
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
   CU(cudaStreamSynchronize(h->stream));
   if (device_ms) {
     float ms = 0.f;
@@ -292,6 +295,9 @@ int pbd_sync(pbd_handle* h, double* device_ms) {
   h->pending = false;
   static const bool trace = getenv("PBD_TILE_TRACE") != nullptr;
   if (trace) h->be->debug_dump();
+  if (h->be->take_abort())
+    return fail(PBD_ERR_CUDA, "a tile waited longer than PBD_SPIN_LIMIT_MS for another tile (was every rank of a sharded body "
+                              "launched?); the frame ran to its end but the state is invalid");
   return PBD_OK;
 }
 
@@ -351,7 +357,8 @@ int pbd_step(pbd_handle* h, float dt, pbd_step_stats* stats) {
 int pbd_read_positions(pbd_handle* h, float* out, double* packMs) {
   if (!h || !out) return fail(PBD_ERR_INVALID, "null argument");
   const double t0 = wall_ms();
-  CU(cudaSetDevice(h->device));
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
   CU(launch_pack(h->d, h->stream));
   if (h->d.V) CU(cudaMemcpyAsync(out, h->d.packed, sizeof(float) * 3 * (size_t)h->d.V, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -361,7 +368,8 @@ int pbd_read_positions(pbd_handle* h, float* out, double* packMs) {
 
 int pbd_set_params(pbd_handle* h, const pbd_params* p) {
   if (!h || !p) return fail(PBD_ERR_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
   CU(cudaStreamSynchronize(h->stream));
   h->params = *p;
   h->be->invalidate();
@@ -420,10 +428,15 @@ int pbd_get_schedule_sequence(const pbd_handle* h, uint32_t* items) {
 
 int pbd_get_array(pbd_handle* h, int what, float* out) {
   if (!h || !out) return fail(PBD_ERR_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
   CU(cudaStreamSynchronize(h->stream));
   const Plan& p = h->plan;
   const DeviceArrays& d = h->d;
+  if (what == PBD_ARRAY_INV_MASS || what == PBD_ARRAY_XSTAR) {
+    CU(h->be->export_pos(d, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   auto vec4 = [&](const float4* src, int comps, bool wOnly) -> int {
     std::vector<float4> tmp(d.V);
     if (d.V) CU(cudaMemcpy(tmp.data(), src, sizeof(float4) * d.V, cudaMemcpyDeviceToHost));
@@ -457,14 +470,16 @@ int pbd_get_array(pbd_handle* h, int what, float* out) {
 
 int pbd_shard_export(pbd_handle* h, void* out) {
   if (!h || !out) return fail(PBD_ERR_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
   CU(h->be->shard_export(out));
   return PBD_OK;
 }
 
 int pbd_shard_attach_ipc(pbd_handle* h, const void* all) {
   if (!h || !all) return fail(PBD_ERR_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
   CU(h->be->shard_attach_ipc(all));
   return PBD_OK;
 }
@@ -476,7 +491,8 @@ int pbd_shard_attach_local(pbd_handle* const* hs, uint32_t world) {
       return fail(PBD_ERR_INVALID, "handles must be given in rank order, all created with shard_world = world");
   }
   for (uint32_t a = 0; a < world; ++a) {
-    CU(cudaSetDevice(hs[a]->device));
+    DeviceScope onDevice(hs[a]->device);
+    CU(onDevice.err);
     for (uint32_t b = 0; b < world; ++b) {
       void *pos = nullptr, *done = nullptr;
       hs[b]->be->shard_local_pointers(&pos, &done);

@@ -53,6 +53,10 @@ bool validate_mesh(const MeshView& m, std::string& err) {
   if (m.V > 0 && !m.x0) { err = "x0 is null"; return false; }
   if (m.E > 0 && !m.edges) { err = "edgeIds is null"; return false; }
   if (m.T > 0 && !m.tets) { err = "tetIds is null"; return false; }
+  // NaN / Inf positions would only propagate in the reference; here they would reach the planner's
+  // sorts (not a strict weak ordering with NaN) and llround() of the bounding box: refuse them
+  for (size_t i = 0; i < (size_t)m.V * 3; ++i)
+    if (!std::isfinite(m.x0[i])) { err = "x0 is not finite (vertex " + std::to_string(i / 3) + ")"; return false; }
   for (size_t i = 0; i < (size_t)m.E * 2; ++i)
     if (m.edges[i] >= m.V) { err = "edge index out of range (edge " + std::to_string(i / 2) + ")"; return false; }
   for (size_t i = 0; i < (size_t)m.T * 4; ++i)

@@ -38,39 +38,99 @@ struct TileHdr {
 };
 static_assert(sizeof(TileHdr) == 64, "TileHdr is the 64-byte block header");
 
+// ---------------------------------------------------------------- raw shared-memory accesses
+//
+// The one-thread-per-constraint sweeps address shared memory with 32-bit shared-window addresses
+// computed ONCE per tile visit.  Going through generic pointers (smem + offset) made the compiler
+// rebuild the window base in every colour step (S2UR SR_CgaCtaId / UMOV / ULEA / LDC: ~10 of the
+// ~110 instructions an edge thread issued per step, and on its dependent path).  `volatile` +
+// "memory" keep the accesses on their side of the block barriers.
+PBD_DEV uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+PBD_DEV float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+PBD_DEV uint2 lds_v2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+PBD_DEV float4 lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+PBD_DEV void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+PBD_DEV void sts_v4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+PBD_DEV uint32_t smem_window(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one edge / one tet whose record sits at the given shared addresses; sv = address of the tile's vertex 0
+template <bool FAST>
+PBD_DEV void project_edge_rec(uint32_t sv, uint32_t id, float r, float l, uint32_t lamA, float alpha) {
+  const uint32_t a = sv + ((id & 0xffffu) << 4), b = sv + ((id >> 16) << 4);
+  const float4 p0 = lds_v4(a), p1 = lds_v4(b);
+  float4 q0, q1;
+  float nl;
+  if (FAST ? edge_delta_fast(p0, p1, r, l, alpha, q0, q1, nl) : edge_delta(p0, p1, r, l, alpha, q0, q1, nl)) {
+    sts_v4(a, q0);
+    sts_v4(b, q1);
+    sts_f32(lamA, nl);
+  }
+}
+template <bool FAST>
+PBD_DEV void project_edge_at(uint32_t sv, uint32_t idA, uint32_t restA, uint32_t lamA, float alpha) {
+  const uint32_t id = lds_u32(idA);
+  const float r = lds_f32(restA), l = lds_f32(lamA);
+  project_edge_rec<FAST>(sv, id, r, l, lamA, alpha);
+}
+template <bool FAST>
+PBD_DEV void project_tet_rec(uint32_t sv, uint2 id, float r, float l, uint32_t lamA, float alpha) {
+  const uint32_t a = sv + ((id.x & 0xffffu) << 4), b = sv + ((id.x >> 16) << 4);
+  const uint32_t c = sv + ((id.y & 0xffffu) << 4), d = sv + ((id.y >> 16) << 4);
+  float4 pa = lds_v4(a), pb = lds_v4(b), pc = lds_v4(c), pd = lds_v4(d);
+  float nl;
+  if (FAST ? tet_delta_fast(pa, pb, pc, pd, r, l, alpha, nl) : tet_delta(pa, pb, pc, pd, r, l, alpha, nl)) {
+    sts_v4(a, pa); sts_v4(b, pb); sts_v4(c, pc); sts_v4(d, pd);
+    sts_f32(lamA, nl);
+  }
+}
+template <bool FAST>
+PBD_DEV void project_tet_at(uint32_t sv, uint32_t idA, uint32_t restA, uint32_t lamA, float alpha) {
+  const uint2 id = lds_v2(idA);
+  const float r = lds_f32(restA), l = lds_f32(lamA);
+  project_tet_rec<FAST>(sv, id, r, l, lamA, alpha);
+}
+
 // ---------------------------------------------------------------- sweeps (shared memory only)
 //
 // Everything a colour step touches lives in shared memory: `rec` / `svOff` are byte offsets into
 // the dynamic shared array, so every access below is an LDS/STS.  The dependent chain of a
 // colour step is LDS record -> LDS.128 vertices -> arithmetic -> STS.128 -> block barrier.
 
+// FAST: the PBD_FLAG_FAST_ARITH forms of pbd_math.cuh (FFMA + SFU reciprocal / rsqrt) instead of the
+// bit-exact ones; same records, same schedule.
+template <bool FAST>
 PBD_SWEEP_INLINE void sweep_edges(const TileHdr& h, uint32_t rec, uint32_t svOff, float alpha, long long* ft) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t n = h.nEdgeGroups;
   if (n == 0) return;
-  const uint2* groups = reinterpret_cast<const uint2*>(smem + rec + h.offEdgeGroups);
-  const uint32_t* idx = reinterpret_cast<const uint32_t*>(smem + rec + h.offEdgeIdx);
-  const float* rest = reinterpret_cast<const float*>(smem + rec + h.offEdgeRest);
-  float* lam = reinterpret_cast<float*>(smem + rec + h.offEdgeLam);
-  float4* sv = reinterpret_cast<float4*>(smem + svOff);
-  const uint32_t tid = threadIdx.x, nth = blockDim.x;
-  auto project = [&](uint32_t e, uint32_t id, float r, float l) {
-    const uint32_t a = id & 0xffffu, b = id >> 16;
-    const float4 p0 = sv[a], p1 = sv[b];
-    float4 q0, q1;
-    float nl;
-    if (edge_delta(p0, p1, r, l, alpha, q0, q1, nl)) {
-      sv[a] = q0;
-      sv[b] = q1;
-      lam[e] = nl;
-    }
-  };
+  const uint32_t base = smem_window(smem), sv = base + svOff, tid = threadIdx.x;
+  uint32_t grp = base + rec + h.offEdgeGroups;
+  const uint32_t idA = base + rec + h.offEdgeIdx + 4u * tid, restA = base + rec + h.offEdgeRest + 4u * tid,
+                 lamA = base + rec + h.offEdgeLam + 4u * tid;
   // (Fetching a thread's next record before the barrier was measured: no gain, more registers.)
-  for (uint32_t g = 0; g < n; ++g) {
-    const uint2 gd = groups[g];
-    if (tid < gd.y) {   // the planner keeps every group within one pass of the block
-      const uint32_t e = gd.x + tid;
-      project(e, idx[e], rest[e], lam[e]);
+  for (uint32_t g = 0; g < n; ++g, grp += 8u) {
+    const uint2 gd = lds_v2(grp);
+    if (tid < gd.y) {   // the planner keeps every group within one pass of the block (checked at upload)
+      const uint32_t o = gd.x << 2;
+      project_edge_at<FAST>(sv, idA + o, restA + o, lamA + o, alpha);
     }
     __syncthreads();
     PBD_STEP_TRACE(ft, g, gd.y);
@@ -84,7 +144,7 @@ PBD_SWEEP_INLINE void sweep_edges(const TileHdr& h, uint32_t rec, uint32_t svOff
 // so every lane runs the same instructions on role-selected operands; the reduction terms are
 // exchanged with quad shuffles and summed in the reference's order, which keeps the result
 // bit-identical while shortening the dependent instruction stream of a colour step.
-template <int LANES>
+template <int LANES, bool FAST>
 PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff, float alpha, long long* ft) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t n = h.nTetGroups;
@@ -94,22 +154,17 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
   const float* rest = reinterpret_cast<const float*>(smem + rec + h.offTetRest);
   float* lam = reinterpret_cast<float*>(smem + rec + h.offTetLam);
   float4* sv = reinterpret_cast<float4*>(smem + svOff);
-  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  const uint32_t tid = threadIdx.x;
   if (LANES == 1) {
-    auto project = [&](uint32_t t, uint2 id, float r, float l) {
-      const uint32_t a = id.x & 0xffffu, b = id.x >> 16, c = id.y & 0xffffu, d = id.y >> 16;
-      float4 pa = sv[a], pb = sv[b], pc = sv[c], pd = sv[d];
-      float nl;
-      if (tet_delta(pa, pb, pc, pd, r, l, alpha, nl)) {
-        sv[a] = pa; sv[b] = pb; sv[c] = pc; sv[d] = pd;
-        lam[t] = nl;
-      }
-    };
-    for (uint32_t g = 0; g < n; ++g) {
-      const uint2 gd = groups[g];
+    const uint32_t base = smem_window(smem), svA = base + svOff;
+    uint32_t grp = base + rec + h.offTetGroups;
+    const uint32_t idA = base + rec + h.offTetIdx + 8u * tid, restA = base + rec + h.offTetRest + 4u * tid,
+                   lamA = base + rec + h.offTetLam + 4u * tid;
+    for (uint32_t g = 0; g < n; ++g, grp += 8u) {
+      const uint2 gd = lds_v2(grp);
       if (tid < gd.y) {
-        const uint32_t t = gd.x + tid;
-        project(t, idx[t], rest[t], lam[t]);
+        const uint32_t o = gd.x << 2;
+        project_tet_at<FAST>(svA, idA + 2u * o, restA + o, lamA + o, alpha);
       }
       __syncthreads();
       PBD_STEP_TRACE(ft, g, gd.y);
@@ -124,7 +179,10 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
     // w|g|^2 terms are exchanged with one shuffle pair and summed in the reference's order on
     // both lanes, so both derive the identical delta-lambda.
     const uint32_t half = tid & 1u, lane = tid & 31u;
-    const uint32_t pairs = nth >> 1, pair = tid >> 1;
+    const uint32_t pair = tid >> 1;
+#ifdef PBD_SWEEP_OVERFLOW
+    const uint32_t pairs = blockDim.x >> 1;
+#endif
     const unsigned m = 0xffffffffu;
     const bool isB = half != 0u;
     auto project = [&](uint32_t t, uint2 id, float r, float l0, bool live) {
@@ -198,7 +256,10 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
     const uint32_t fo = (0x00000001u >> (role * 8u)) & 3u;        // {1,0,0,0}
     const uint32_t fx = (0x01030203u >> (role * 8u)) & 3u;        // {3,2,3,1}
     const uint32_t fy = (0x02010302u >> (role * 8u)) & 3u;        // {2,3,1,2}
-    const uint32_t quads = nth >> 2, quad = tid >> 2;
+    const uint32_t quad = tid >> 2;
+#ifdef PBD_SWEEP_OVERFLOW
+    const uint32_t quads = blockDim.x >> 2;
+#endif
     const unsigned m = 0xffffffffu;
     // `live` is quad-uniform; idle quads run the same instructions on the group's last tet and
     // write nothing, so every lane of a warp takes part in the shuffles
@@ -264,49 +325,81 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
 // groups sit in different warps and their sum fits the block (pbd_tileplan.cpp::colour_joint).
 // A visit then needs about max-joint-vertex-load steps instead of edge colours + tet colours, and
 // the warps a tet-only step would leave idle carry the edge work.
+template <bool FAST>
 PBD_SWEEP_INLINE void sweep_mixed(const TileHdr& h, uint32_t rec, uint32_t svOff, float alphaE, float alphaT,
                                   long long* ft) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t n = h.nEdgeGroups;   // == h.nTetGroups
   if (n == 0) return;
-  const uint2* eGroups = reinterpret_cast<const uint2*>(smem + rec + h.offEdgeGroups);
-  const uint2* tGroups = reinterpret_cast<const uint2*>(smem + rec + h.offTetGroups);
-  const uint32_t* eIdx = reinterpret_cast<const uint32_t*>(smem + rec + h.offEdgeIdx);
-  const float* eRest = reinterpret_cast<const float*>(smem + rec + h.offEdgeRest);
-  float* eLam = reinterpret_cast<float*>(smem + rec + h.offEdgeLam);
-  const uint2* tIdx = reinterpret_cast<const uint2*>(smem + rec + h.offTetIdx);
-  const float* tRest = reinterpret_cast<const float*>(smem + rec + h.offTetRest);
-  float* tLam = reinterpret_cast<float*>(smem + rec + h.offTetLam);
-  float4* sv = reinterpret_cast<float4*>(smem + svOff);
+  const uint32_t base = smem_window(smem), sv = base + svOff;
   const uint32_t tid = threadIdx.x, rtid = blockDim.x - 1u - tid;   // tets are counted from the block's last thread
-  for (uint32_t g = 0; g < n; ++g) {
-    const uint2 ge = eGroups[g], gt = tGroups[g];
+  uint32_t eGrp = base + rec + h.offEdgeGroups, tGrp = base + rec + h.offTetGroups;
+  const uint32_t eIdA = base + rec + h.offEdgeIdx + 4u * tid, eRestA = base + rec + h.offEdgeRest + 4u * tid,
+                 eLamA = base + rec + h.offEdgeLam + 4u * tid;
+  const uint32_t tIdA = base + rec + h.offTetIdx + 8u * rtid, tRestA = base + rec + h.offTetRest + 4u * rtid,
+                 tLamA = base + rec + h.offTetLam + 4u * rtid;
+#ifdef PBD_SWEEP_PREFETCH
+  // The record of a thread's NEXT constraint (group entry, indices, rest value, lambda -- none of
+  // which another constraint ever writes) is fetched before the block barrier, so that after the
+  // barrier the dependent chain starts at the vertex gathers.
+  uint32_t role, lamA = 0u;
+  uint2 id = make_uint2(0u, 0u);
+  float r = 0.f, l = 0.f;
+  auto fetch = [&]() {
+    const uint2 ge = lds_v2(eGrp), gt = lds_v2(tGrp);
+    role = 0u;
     if (tid < ge.y) {
-      const uint32_t e = ge.x + tid;
-      const uint32_t id = eIdx[e];
-      const uint32_t a = id & 0xffffu, b = id >> 16;
-      const float4 p0 = sv[a], p1 = sv[b];
+      const uint32_t o = ge.x << 2;
+      role = 1u; id.x = lds_u32(eIdA + o); r = lds_f32(eRestA + o); lamA = eLamA + o; l = lds_f32(lamA);
+    } else if (rtid < gt.y) {
+      const uint32_t o = gt.x << 2;
+      role = 2u; id = lds_v2(tIdA + 2u * o); r = lds_f32(tRestA + o); lamA = tLamA + o; l = lds_f32(lamA);
+    }
+  };
+  fetch();
+  for (uint32_t g = 0; g < n; ++g) {
+    const uint32_t roleC = role, lamC = lamA;
+    const uint2 idC = id;
+    const float rC = r, lC = l;
+    eGrp += 8u; tGrp += 8u;
+    if (roleC == 1u) {
+      const uint32_t a = sv + ((idC.x & 0xffffu) << 4), b = sv + ((idC.x >> 16) << 4);
+      const float4 p0 = lds_v4(a), p1 = lds_v4(b);
+      if (g + 1 < n) fetch();
       float4 q0, q1;
       float nl;
-      if (edge_delta(p0, p1, eRest[e], eLam[e], alphaE, q0, q1, nl)) {
-        sv[a] = q0;
-        sv[b] = q1;
-        eLam[e] = nl;
+      if (FAST ? edge_delta_fast(p0, p1, rC, lC, alphaE, q0, q1, nl) : edge_delta(p0, p1, rC, lC, alphaE, q0, q1, nl)) {
+        sts_v4(a, q0); sts_v4(b, q1); sts_f32(lamC, nl);
       }
-    } else if (rtid < gt.y) {
-      const uint32_t t = gt.x + rtid;
-      const uint2 id = tIdx[t];
-      const uint32_t a = id.x & 0xffffu, b = id.x >> 16, c = id.y & 0xffffu, d = id.y >> 16;
-      float4 pa = sv[a], pb = sv[b], pc = sv[c], pd = sv[d];
+    } else if (roleC == 2u) {
+      const uint32_t a = sv + ((idC.x & 0xffffu) << 4), b = sv + ((idC.x >> 16) << 4);
+      const uint32_t c = sv + ((idC.y & 0xffffu) << 4), d = sv + ((idC.y >> 16) << 4);
+      float4 pa = lds_v4(a), pb = lds_v4(b), pc = lds_v4(c), pd = lds_v4(d);
+      if (g + 1 < n) fetch();
       float nl;
-      if (tet_delta(pa, pb, pc, pd, tRest[t], tLam[t], alphaT, nl)) {
-        sv[a] = pa; sv[b] = pb; sv[c] = pc; sv[d] = pd;
-        tLam[t] = nl;
+      if (FAST ? tet_delta_fast(pa, pb, pc, pd, rC, lC, alphaT, nl) : tet_delta(pa, pb, pc, pd, rC, lC, alphaT, nl)) {
+        sts_v4(a, pa); sts_v4(b, pb); sts_v4(c, pc); sts_v4(d, pd); sts_f32(lamC, nl);
       }
+    } else if (g + 1 < n) {
+      fetch();
+    }
+    __syncthreads();
+    PBD_STEP_TRACE(ft, g, 0);
+  }
+#else
+  for (uint32_t g = 0; g < n; ++g, eGrp += 8u, tGrp += 8u) {
+    const uint2 ge = lds_v2(eGrp), gt = lds_v2(tGrp);
+    if (tid < ge.y) {
+      const uint32_t o = ge.x << 2;
+      project_edge_at<FAST>(sv, eIdA + o, eRestA + o, eLamA + o, alphaE);
+    } else if (rtid < gt.y) {
+      const uint32_t o = gt.x << 2;
+      project_tet_at<FAST>(sv, tIdA + 2u * o, tRestA + o, tLamA + o, alphaT);
     }
     __syncthreads();
     PBD_STEP_TRACE(ft, g, ge.y + (gt.y << 16));
   }
+#endif
 }
 
 }  // namespace pbd

@@ -59,6 +59,7 @@ constexpr uint32_t kMaxRanks = 8;     // GPUs one body can be spread over (one n
 
 struct TileParams {
   float4* pos;
+  ulonglong2* posT;             // tagged hand-over (experimental): 2 x {value|tag<<32, value|tag<<32} per vertex, else null
   float4* prev;
   float4* vel;
   const unsigned char* blob;
@@ -83,37 +84,121 @@ struct TileParams {
   long long* ftrace;            // debug: clock64 stamps of CTA 0, 128 per phase
   uint32_t nTile0, nPhases, substeps, iterations;
   uint32_t recStride;           // bytes of one record buffer
+  long long spinLimit;          // cycles a CTA may wait for another CTA before it gives up (bounded spins)
+  unsigned* abortWord;          // device: set by the first wait that gives up; every later wait bails out at once
+  unsigned* abortHost;          // mapped host word: what pbd_sync checks after the frame
   uint32_t stagger;             // cycles by which every second CTA of an SM delays its sweeps (tiles_per_sm >= 2)
 };
 
 
+// Every wait on another CTA (or another GPU) is BOUNDED: a peer rank that was never launched, or a
+// lost update, must not hang the GPU until reset.  Every 1024 polls the waiter looks at the clock and
+// at the abort word; the first waiter that exceeds P.spinLimit sets the word (and its mapped host
+// copy), every other wait then bails out at its next check, the kernel runs to its end with
+// meaningless results and pbd_sync reports PBD_ERR_CUDA instead of hanging.
+struct SpinGuard {
+  uint32_t polls = 0;
+  long long t0 = 0;
+};
+__device__ __forceinline__ bool spin_expired(SpinGuard& g, const TileParams& P) {
+  if ((++g.polls & 1023u) != 0u) return false;
+  if (g.polls == 1024u) g.t0 = clock64();
+  if (ld_acquire(P.abortWord) != 0u) return true;
+  if (clock64() - g.t0 > P.spinLimit) {
+    atomicExch(P.abortWord, 1u);
+    *reinterpret_cast<volatile unsigned*>(P.abortHost) = 1u;
+    __threadfence_system();
+    return true;
+  }
+  return false;
+}
+// done counters and barrier epochs only ever grow and may wrap: compare by signed distance
+__device__ __forceinline__ bool reached(unsigned have, unsigned need) { return (int)(have - need) >= 0; }
+
 // All CTAs are co-resident (cooperative launch).  The counter is zeroed before the launch.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+__device__ __forceinline__ void grid_barrier(const TileParams& P, unsigned* counter, unsigned& epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
     red_release(counter, 1u);
-    while (ld_acquire(counter) < epoch) {}
+    SpinGuard g;
+    while (!reached(ld_acquire(counter), epoch) && !spin_expired(g, P)) {}
   }
   __syncthreads();
 }
 
+// ---- tagged hand-over (EXPERIMENTAL, PBD_FLAG_TAGGED_HANDOVER) ----------------------
+// A position is four 64-bit {value, tag} pairs (x, y, z, invMass), read and written as two 128-bit
+// accesses of two b64 elements each.  A 64-bit element is single-copy atomic, so a reader that finds
+// the expected tag in all four pairs holds the values written WITH that tag -- no release fence on the
+// writer, no done flag, no separate poll round trip.  Tags: a tile visit with sequence number
+// seq = iteration * nPhases + phase (iterations counted across frames) writes 2*seq + 2 and, every
+// phase covering every vertex exactly once, expects 2*seq (the visit before it); the commit pass at
+// the end of a frame writes 2*seqEnd + 1, which is what the first visit of the next frame expects.
+__device__ __forceinline__ void ld_pairs(const ulonglong2* p, ulonglong2& v) {
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_pairs(ulonglong2* p, ulonglong2 v) {
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+__device__ __forceinline__ bool tagged_unpack(ulonglong2 a, ulonglong2 b, uint32_t expect, float4& out) {
+  out = make_float4(__uint_as_float((uint32_t)a.x), __uint_as_float((uint32_t)a.y), __uint_as_float((uint32_t)b.x),
+                    __uint_as_float((uint32_t)b.y));
+  return (uint32_t)(a.x >> 32) == expect && (uint32_t)(a.y >> 32) == expect && (uint32_t)(b.x >> 32) == expect &&
+         (uint32_t)(b.y >> 32) == expect;
+}
+__device__ __forceinline__ float4 tagged_wait_load(const TileParams& P, uint32_t s, uint32_t expect) {
+  float4 out;
+  ulonglong2 a, b;
+  SpinGuard g;
+  do {
+    ld_pairs(P.posT + 2 * (size_t)s, a);
+    ld_pairs(P.posT + 2 * (size_t)s + 1, b);
+  } while (!tagged_unpack(a, b, expect, out) && !spin_expired(g, P));
+  return out;
+}
+__device__ __forceinline__ float4 tagged_load_any(const ulonglong2* posT, uint32_t s) {   // own earlier write: no wait
+  float4 out;
+  ulonglong2 a, b;
+  ld_pairs(posT + 2 * (size_t)s, a);
+  ld_pairs(posT + 2 * (size_t)s + 1, b);
+  tagged_unpack(a, b, 0u, out);
+  return out;
+}
+__device__ __forceinline__ void tagged_store(ulonglong2* posT, uint32_t s, float4 p, uint32_t tag) {
+  const unsigned long long t = (unsigned long long)tag << 32;
+  st_pairs(posT + 2 * (size_t)s, make_ulonglong2(t | __float_as_uint(p.x), t | __float_as_uint(p.y)));
+  st_pairs(posT + 2 * (size_t)s + 1, make_ulonglong2(t | __float_as_uint(p.z), t | __float_as_uint(p.w)));
+}
+
 // vertex-only pass over the phase-0 partition (no constraints): used when there is nothing to
 // sweep and for the final commit.  finalCommit: ground (if clamp) + commit, no predict.
+// TAGGED: `waitTag` != 0: wait for that tag (values written by other CTAs); 0: the vertex was last
+// written by this very thread.  Stores carry `writeTag`.
+template <bool TAGGED>
 __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConsts& k, int mode, bool clamp,
-                                            bool finalCommit) {
+                                            bool finalCommit, uint32_t waitTag = 0, uint32_t writeTag = 0) {
   for (uint32_t q = blockIdx.x; q < P.nHome; q += gridDim.x) {
     const uint32_t t = P.homeList[q];
     const uint32_t b = P.tile0Begin[t], e = P.tile0Begin[t + 1];
     for (uint32_t s = b + threadIdx.x; s < e; s += blockDim.x) {
       if (finalCommit) {
-        float4 p = __ldcg(P.pos + s), x = __ldcg(P.prev + s), v;
+        float4 p, x = __ldcg(P.prev + s), v;
+        if (TAGGED) p = waitTag ? tagged_wait_load(P, s, waitTag) : tagged_load_any(P.posT, s);
+        else p = __ldcg(P.pos + s);
         if (clamp) ground_vertex(p, k);
         commit_vertex(p, x, v, k);
         v.w = 0.0f;
         __stcg(P.prev + s, x);
         __stcg(P.vel + s, v);
-        __stcg(P.pos + s, p);
+        if (TAGGED) tagged_store(P.posT, s, p, writeTag); else __stcg(P.pos + s, p);
+      } else if (TAGGED) {
+        VertexIn in;
+        in.p = tagged_load_any(P.posT, s);
+        in.x = in.v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mode == LOAD_PREDICT || mode == LOAD_COMMIT_PREDICT) in.x = __ldcg(P.prev + s);
+        if (mode == LOAD_PREDICT) in.v = __ldcg(P.vel + s);
+        tagged_store(P.posT, s, finish_vertex(P, k, s, mode, clamp, in), writeTag);
       } else {
         const float4 p = load_transform(P, k, s, mode, clamp);
         __stcg(P.pos + s, p);
@@ -124,7 +209,7 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
 
 // ---------------------------------------------------------------- the frame kernel
 
-template <int LANES>
+template <int LANES, bool TAGGED, bool FAST>
 __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar[2];
@@ -145,8 +230,10 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
 
   if (!sweeping) {
     // vertex-local work only: a vertex always belongs to the same CTA, no grid barrier needed
-    for (uint32_t sub = 0; sub < P.substeps; ++sub) vertex_pass(P, k, sub == 0 ? LOAD_PREDICT : LOAD_COMMIT_PREDICT, clamp, false);
-    vertex_pass(P, k, LOAD_PLAIN, clamp, true);
+    const uint32_t frameTag = 2u * (P.iterBase * P.nPhases) + 1u;   // nothing advances: keep the frame-start tag
+    for (uint32_t sub = 0; sub < P.substeps; ++sub)
+      vertex_pass<TAGGED>(P, k, sub == 0 ? LOAD_PREDICT : LOAD_COMMIT_PREDICT, clamp, false, 0u, frameTag);
+    vertex_pass<TAGGED>(P, k, LOAD_PLAIN, clamp, true, 0u, frameTag);
     return;
   }
 
@@ -225,6 +312,10 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           unsigned char* rec = smem + recOff;
           const TileHdr h = *reinterpret_cast<const TileHdr*>(rec);
           const bool contiguous = (h.flags & 1u) != 0u;
+          // tagged hand-over: what this visit expects in its vertices and what it leaves in them
+          const uint32_t seq = (P.iterBase + sub * P.iterations + it) * P.nPhases + ph;
+          const uint32_t expectTag = (sub == 0 && it == 0 && ph == 0) ? 2u * seq + 1u : 2u * seq;
+          const uint32_t writeTag = 2u * seq + 2u;
           if (ft) ft[1] = clock64();
           // ---- prefetch the next tile's block into the other buffer
           const uint32_t jn = (j + 1 == nItems) ? 0u : j + 1;
@@ -235,7 +326,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           }
           // ---- vertices L2 -> shared memory (all of a thread's loads are issued before the first use)
           // ---- point-to-point sync: wait until the tiles that last wrote my vertices have stored them
-          if (P.done) {
+          if (!TAGGED && P.done) {
             const uint32_t np = (h.flags >> 8) & 0xffu;
             if (tid < np) {
               // entry: tile (bits 0..23) | owner rank (24..27) | bit 31 = written earlier in THIS iteration
@@ -243,11 +334,43 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
               const uint32_t need = P.iterBase + sub * P.iterations + it + (e >> 31);
               const uint32_t own = (e >> 24) & 0xfu;
               const unsigned* f = donePeerS[own] + (e & 0xffffffu);
-              if (multi && own != P.rank) { while (ld_acquire_sys(f) < need) {} } else { while (ld_acquire(f) < need) {} }
+              SpinGuard g;
+              if (multi && own != P.rank) { while (!reached(ld_acquire_sys(f), need) && !spin_expired(g, P)) {} }
+              else { while (!reached(ld_acquire(f), need) && !spin_expired(g, P)) {} }
             }
             __syncthreads();
           }
-          if (contiguous) {
+          if (ft) ft[14] = clock64();
+          if (TAGGED) {
+            // the values ARE the synchronisation: issue every load of the batch, then wait only for
+            // the vertices whose tag is not there yet
+            const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
+            for (uint32_t base = 0; base < h.vertCount; base += 3u * nth) {
+              ulonglong2 ta[3], tb[3];
+              VertexIn in[3];
+              uint32_t slot[3];
+#pragma unroll
+              for (int u = 0; u < 3; ++u) {
+                const uint32_t i = base + u * nth + tid;
+                if (i < h.vertCount) {
+                  slot[u] = contiguous ? h.vertBegin + i : (vidx[i] & 0x0fffffffu);
+                  ld_pairs(P.posT + 2 * (size_t)slot[u], ta[u]);
+                  ld_pairs(P.posT + 2 * (size_t)slot[u] + 1, tb[u]);
+                  in[u].x = in[u].v = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (mode == LOAD_PREDICT || mode == LOAD_COMMIT_PREDICT) in[u].x = __ldcg(P.prev + slot[u]);
+                  if (mode == LOAD_PREDICT) in[u].v = __ldcg(P.vel + slot[u]);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 3; ++u) {
+                const uint32_t i = base + u * nth + tid;
+                if (i < h.vertCount) {
+                  if (!tagged_unpack(ta[u], tb[u], expectTag, in[u].p)) in[u].p = tagged_wait_load(P, slot[u], expectTag);
+                  sv[i] = finish_vertex(P, k, slot[u], mode, true, in[u]);   // (mode != LOAD_PLAIN only on contiguous home tiles)
+                }
+              }
+            }
+          } else if (contiguous) {
             for (uint32_t base = 0; base < h.vertCount; base += 3u * nth) {
               VertexIn in[3];
 #pragma unroll
@@ -285,32 +408,39 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             while (clock64() - t0 < (long long)stagger) {}
           }
           if (LANES == 1 && (h.flags & 4u)) {
-            sweep_mixed(h, recOff, svOff, k.alphaEdge, k.alphaTet, ft);   // edges and tets share the colour steps
+            sweep_mixed<FAST>(h, recOff, svOff, k.alphaEdge, k.alphaTet, ft);   // edges and tets share the colour steps
             if (ft) ft[3] = clock64();
           } else {
-            sweep_edges(h, recOff, svOff, k.alphaEdge, ft);
+            sweep_edges<FAST>(h, recOff, svOff, k.alphaEdge, ft);
             if (ft) ft[3] = clock64();
-            sweep_tets<LANES>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr);
+            sweep_tets<LANES, FAST>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr);
           }
           if (ft) ft[4] = clock64();
           // ---- write back
-          if (contiguous) {
+          if (TAGGED) {
+            const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
+            for (uint32_t i = tid; i < h.vertCount; i += nth)
+              tagged_store(P.posT, contiguous ? h.vertBegin + i : (vidx[i] & 0x0fffffffu), sv[i], writeTag);
+          } else if (contiguous) {
             for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + h.vertBegin + i, sv[i]);
           } else {
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
             for (uint32_t i = tid; i < h.vertCount; i += nth) { const uint32_t e = vidx[i]; __stcg(posPeerS[e >> 28] + (e & 0x0fffffffu), sv[i]); }
           }
+          if (ft) ft[11] = clock64();
           fence_async_smem();   // lambdas written by the sweeps -> visible to the bulk store
           __syncthreads();      // also: sv and rec are free for the next tile
+          if (ft) ft[12] = clock64();
           if (tid == 0) {
             // publish first: the release fence waits for the writes issued before it, and nobody but
             // this tile reads its lambdas -- their write-back need not be part of that wait
-            if (P.done) {   // my vertices are in L2 (of their owners)
+            if (!TAGGED && P.done) {   // my vertices are in L2 (of their owners)
               const uint32_t v = P.iterBase + sub * P.iterations + it + 1u;
               // system scope only when another GPU reads this counter or holds vertices this tile
               // wrote (flags bit 1): a system-scope release costs several microseconds
               if (multi && (h.flags & 2u)) st_release_sys(P.done + itemTile[j], v); else st_release(P.done + itemTile[j], v);
             }
+            if (ft) ft[13] = clock64();
             const TileCopy c = j < kItemCopySmem ? itemCopy[j] : P.copies[itemTile[j]];
             if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
             if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
@@ -328,11 +458,17 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           if (ft) { ft[5] = clock64(); ft[6] = h.nEdgeGroups; ft[7] = h.nTetGroups; ft[8] = h.vertCount; ft[9] = h.nEdges; ft[10] = h.nTets; }
         }
         if (tr) P.trace[2 * ((size_t)ph * gridDim.x + blockIdx.x) + 1] = globaltimer_ns();
-        if (!P.done) grid_barrier(P.barrier, epoch);
+        if (!TAGGED && !P.done) grid_barrier(P, P.barrier, epoch);
       }
     }
   }
   if (tid == 0) bulk_wait_all();
+  if (TAGGED) {
+    // the final commit waits for the tag of the frame's last visit in every vertex it commits
+    const uint32_t seqEnd = (P.iterBase + P.substeps * P.iterations) * P.nPhases;
+    vertex_pass<true>(P, k, LOAD_PLAIN, clamp, true, 2u * seqEnd, 2u * seqEnd + 1u);
+    return;
+  }
   if (P.done) {
     // the final commit of a home tile reads its vertices' last values: wait for the tiles that wrote them
     const uint32_t need = P.iterBase + P.substeps * P.iterations;
@@ -344,12 +480,24 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
         const uint32_t e = __ldg(hdr + 16 + tid);
         const uint32_t own = (e >> 24) & 0xfu;
         const unsigned* f = donePeerS[own] + (e & 0xffffffu);
-        if (multi && own != P.rank) { while (ld_acquire_sys(f) < need) {} } else { while (ld_acquire(f) < need) {} }
+        SpinGuard g;
+        if (multi && own != P.rank) { while (!reached(ld_acquire_sys(f), need) && !spin_expired(g, P)) {} }
+        else { while (!reached(ld_acquire(f), need) && !spin_expired(g, P)) {} }
       }
     }
     __syncthreads();
   }
-  vertex_pass(P, k, LOAD_PLAIN, clamp, true);
+  vertex_pass<false>(P, k, LOAD_PLAIN, clamp, true);
+}
+
+// float4 positions <-> tagged pairs (upload / host reads only)
+__global__ void to_tagged_kernel(const float4* pos, ulonglong2* posT, uint32_t n, uint32_t tag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tagged_store(posT, i, pos[i], tag);
+}
+__global__ void from_tagged_kernel(const ulonglong2* posT, float4* pos, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pos[i] = tagged_load_any(posT, i);
 }
 
 class TileBackend final : public Backend {
@@ -359,9 +507,12 @@ class TileBackend final : public Backend {
     for (void* q : ipcOpened_) cudaIpcCloseMemHandle(q);
     cudaFree(done_); cudaFree(tileList_); cudaFree(homeList_);
     cudaFree(blob_); cudaFree(copies_); cudaFree(phases_); cudaFree(tile0Begin_); cudaFree(barrier_);
-    cudaFree(trace_); cudaFree(ftrace_);
+    cudaFree(trace_); cudaFree(ftrace_); cudaFree(posT_);
+    if (abortHost_) cudaFreeHost(abortHost_);
   }
-  const char* name() const override { return "b200-tile"; }
+  const char* name() const override {
+    return tagged_ ? (fast_ ? "b200-tile-tagged-fast" : "b200-tile-tagged") : (fast_ ? "b200-tile-fast" : "b200-tile");
+  }
 
   cudaError_t upload(const Plan& plan, const MeshView& m, DeviceArrays& d) override {
     (void)m;
@@ -370,6 +521,8 @@ class TileBackend final : public Backend {
     nPhases_ = (uint32_t)plan.phases.size();
     nTile0_ = (uint32_t)plan.tile0Begin.size() - 1;
     lanes_ = opts_.lanes_per_tet == 2 ? 2u : opts_.lanes_per_tet == 4 ? 4u : 1u;   // auto: one thread per tet (fastest measured)
+    fast_ = (opts_.flags & PBD_FLAG_FAST_ARITH) != 0u;
+    if (fast_) lanes_ = 1;   // the fast forms exist for one thread per constraint
 
     // rest values are already on the device at the plan's device indices (pbd_capi.cu)
     std::vector<float> eRest(plan.edgeDevCount), tRest(plan.tetDevCount);
@@ -465,6 +618,16 @@ class TileBackend final : public Backend {
       const uint32_t nPred = useFlags_ ? (uint32_t)preds[ti].size() : 0u;
       h.vertCount = t.vertCount; h.flags = (t.contiguous ? 1u : 0u) | (remote[ti] ? 2u : 0u) | (t.mixed ? 4u : 0u) | (nPred << 8); h.vertBegin = t.contiguous ? t.vertBegin : 0u;
       h.nEdgeGroups = t.edgeGroupCount; h.nTetGroups = t.tetGroupCount; h.nEdges = t.edgeCount; h.nTets = t.tetCount;
+      // planner invariants the sweeps rely on (pbd_sweep.cuh projects a colour group in ONE pass of the
+      // block and would silently drop the rest): fail loudly instead
+      if (t.mixed && t.edgeGroupCount != t.tetGroupCount) return cudaErrorInvalidConfiguration;
+      for (uint32_t g = 0; g < t.edgeGroupCount; ++g) {
+        const uint32_t ne = plan.groups[t.edgeGroupBegin + g].count;
+        const uint32_t nt = t.mixed ? plan.groups[t.tetGroupBegin + g].count : 0u;
+        if (ne + nt > block_) return cudaErrorInvalidConfiguration;
+      }
+      for (uint32_t g = 0; g < t.tetGroupCount; ++g)
+        if (plan.groups[t.tetGroupBegin + g].count * lanes_ > block_) return cudaErrorInvalidConfiguration;
       uint32_t off = 64 + 4u * kMaxPreds;
       h.offVertIdx = off; off += 4u * pad4(nVG);
       h.offEdgeGroups = off; off += 8u * (pad4(t.edgeGroupCount * 2) / 2);
@@ -584,10 +747,25 @@ class TileBackend final : public Backend {
     if ((err = up(&tileList_, tileList)) != cudaSuccess) return err;
     if ((err = up(&homeList_, homeList)) != cudaSuccess) return err;
     if ((err = cudaMalloc((void**)&barrier_, 2048)) != cudaSuccess) return err;
+    // bounded spins: a mapped host word the kernel sets when a wait gives up (checked by pbd_sync for free)
+    if ((err = cudaHostAlloc((void**)&abortHost_, 64, cudaHostAllocMapped)) != cudaSuccess) return err;
+    *abortHost_ = 0u;
+    if ((err = cudaHostGetDevicePointer((void**)&abortHostDev_, abortHost_, 0)) != cudaSuccess) return err;
+    {
+      int khz = 0;
+      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_);
+      const char* e = getenv("PBD_SPIN_LIMIT_MS");
+      const double ms = e ? atof(e) : 10000.0;
+      spinLimit_ = (long long)(ms * (double)std::max(khz, 1000000));
+    }
     doneBytes_ = sizeof(unsigned) * (plan.tiles.size() + 1);
+    // debug/test hook: start the iteration count (done counters, tags) near the 32-bit wrap
+    if (const char* e = getenv("PBD_DEBUG_ITERBASE")) iterBase_ = (uint32_t)strtoull(e, nullptr, 10);
     if (useFlags_) {
       if ((err = cudaMalloc((void**)&done_, doneBytes_)) != cudaSuccess) return err;
-      if ((err = cudaMemset(done_, 0, doneBytes_)) != cudaSuccess) return err;   // counters only ever grow
+      // counters only ever grow (compared by signed distance, so the 32-bit wrap is harmless)
+      std::vector<unsigned> init(plan.tiles.size() + 1, iterBase_);
+      if ((err = cudaMemcpy(done_, init.data(), doneBytes_, cudaMemcpyHostToDevice)) != cudaSuccess) return err;
     }
     for (uint32_t r = 0; r < kMaxRanks; ++r) { posPeers_[r] = nullptr; donePeers_[r] = nullptr; }
     posPeers_[rank_] = d.pos;
@@ -600,6 +778,25 @@ class TileBackend final : public Backend {
       cudaMemset(trace_, 0, sizeof(unsigned long long) * traceN_);
       if ((err = cudaMalloc((void**)&ftrace_, sizeof(long long) * 256 * (nPhases_ + 1))) != cudaSuccess) return err;
       cudaMemset(ftrace_, 0, sizeof(long long) * 256 * (nPhases_ + 1));
+    }
+
+    // ---- tagged hand-over (experimental): one GPU, one thread per tet, and every phase must cover
+    // every vertex exactly once (then a vertex's previous writer is always the previous visit)
+    tagged_ = false;
+    if ((opts_.flags & PBD_FLAG_TAGGED_HANDOVER) && world_ == 1 && lanes_ == 1 && !plan.phases.empty()) {
+      bool full = true;
+      for (const Phase& ph : plan.phases) {
+        uint64_t covered = 0;
+        for (uint32_t ti = ph.tileBegin; ti < ph.tileBegin + ph.tileCount; ++ti) covered += plan.tiles[ti].vertCount;
+        full &= covered == plan.V;   // tiles of one phase are vertex-disjoint
+      }
+      tagged_ = full;
+    }
+    if (tagged_) {
+      if ((err = cudaMalloc((void**)&posT_, sizeof(ulonglong2) * 2 * ((size_t)plan.V + 1))) != cudaSuccess) return err;
+      bytes_ += sizeof(ulonglong2) * 2 * (size_t)plan.V;
+      to_tagged_kernel<<<(plan.V + 255) / 256, 256>>>(d.pos, posT_, plan.V, 2u * (iterBase_ * nPhases_) + 1u);   // the frame-start tag
+      if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
 
     const void* fn = kernel();
@@ -620,7 +817,7 @@ class TileBackend final : public Backend {
 
   cudaError_t enqueue_frame(const DeviceArrays& d, const FrameShape& f, cudaStream_t s) override {
     TileParams P{};
-    P.pos = d.pos; P.prev = d.prev; P.vel = d.vel;
+    P.pos = d.pos; P.posT = tagged_ ? posT_ : nullptr; P.prev = d.prev; P.vel = d.vel;
     P.blob = blob_; P.copies = copies_; P.edgeLam = d.edgeLam; P.tetLam = d.tetLam;
     P.phases = phases_; P.tile0Begin = tile0Begin_; P.consts = d.consts; P.barrier = barrier_;
     P.trace = trace_; P.ftrace = ftrace_;
@@ -633,6 +830,7 @@ class TileBackend final : public Backend {
     P.tileList = tileList_; P.homeList = homeList_; P.nHome = nHome_; P.world = world_; P.rank = rank_;
     P.iterBase = iterBase_;
     iterBase_ += f.substeps * f.iterations;
+    P.spinLimit = spinLimit_; P.abortWord = barrier_ + 64; P.abortHost = abortHostDev_;
     cudaError_t err = cudaMemsetAsync(barrier_, 0, 2048, s);
     if (err != cudaSuccess) return err;
     void* args[] = {&P};
@@ -662,8 +860,10 @@ class TileBackend final : public Backend {
     cudaMemcpy(f.data(), ftrace_, sizeof(long long) * f.size(), cudaMemcpyDeviceToHost);
     for (uint32_t ph = 0; ph < nPhases_; ++ph) {
       const long long* q = &f[256 * (size_t)ph];
-      fprintf(stderr, "[pbd-ftrace] phase %u CTA0: verts %lld edges %lld tets %lld | groups %lld+%lld | wait rec %lld cyc | vertex load %lld | edge sweep %lld | tet sweep %lld | store %lld\n",
-              ph, q[8], q[9], q[10], q[6], q[7], q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4]);
+      fprintf(stderr, "[pbd-ftrace] phase %u CTA0: verts %lld edges %lld tets %lld | groups %lld+%lld | wait rec %lld cyc | poll %lld | vertex load %lld | edge sweep %lld | tet sweep %lld | "
+                      "store issue %lld | fence+barrier %lld | release %lld | lambda bulk %lld\n",
+              ph, q[8], q[9], q[10], q[6], q[7], q[1] - q[0], q[14] - q[1], q[2] - q[14], q[3] - q[2], q[4] - q[3], q[11] - q[4], q[12] - q[11],
+              q[13] - q[12], q[5] - q[13]);
       fprintf(stderr, "[pbd-steps] phase %u edges (cycles/size):", ph);
       long long prev = q[2];
       for (int g = 0; g < 20 && g < q[6]; ++g) { fprintf(stderr, " %lld/%lld", q[16 + g] - prev, q[56 + g]); prev = q[16 + g]; }
@@ -717,6 +917,16 @@ class TileBackend final : public Backend {
     attached_ = all;
     return cudaSuccess;
   }
+  cudaError_t export_pos(const DeviceArrays& d, cudaStream_t s) override {
+    if (!tagged_ || d.V == 0) return cudaSuccess;
+    from_tagged_kernel<<<(d.V + 255) / 256, 256, 0, s>>>(posT_, d.pos, d.V);
+    return cudaGetLastError();
+  }
+  bool take_abort() override {
+    if (!abortHost_ || *reinterpret_cast<volatile unsigned*>(abortHost_) == 0u) return false;
+    *abortHost_ = 0u;
+    return true;
+  }
   uint32_t launches_per_frame(const FrameShape&) const override { return 1; }
   uint64_t device_bytes() const override { return bytes_; }
   void fill_info(pbd_info& info) const override {
@@ -727,11 +937,19 @@ class TileBackend final : public Backend {
 
  private:
   const void* kernel() const {
-    return lanes_ == 1 ? (const void*)tile_frame_kernel<1>
-           : lanes_ == 2 ? (const void*)tile_frame_kernel<2> : (const void*)tile_frame_kernel<4>;
+    if (tagged_) return fast_ ? (const void*)tile_frame_kernel<1, true, true> : (const void*)tile_frame_kernel<1, true, false>;
+    if (fast_) return (const void*)tile_frame_kernel<1, false, true>;
+    return lanes_ == 1 ? (const void*)tile_frame_kernel<1, false, false>
+           : lanes_ == 2 ? (const void*)tile_frame_kernel<2, false, false> : (const void*)tile_frame_kernel<4, false, false>;
   }
   pbd_options opts_;
   int device_;
+  ulonglong2* posT_ = nullptr;   // tagged hand-over: positions as {value, tag} pairs
+  unsigned* abortHost_ = nullptr;      // mapped host word + its device alias
+  unsigned* abortHostDev_ = nullptr;
+  long long spinLimit_ = 0;
+  bool tagged_ = false;
+  bool fast_ = false;            // PBD_FLAG_FAST_ARITH
   unsigned char* blob_ = nullptr;
   TileCopy* copies_ = nullptr;
   PhaseDesc* phases_ = nullptr;

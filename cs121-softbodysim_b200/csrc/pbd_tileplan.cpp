@@ -400,6 +400,7 @@ struct TileBuild {
   std::vector<uint32_t> verts;               // gathered tiles: slots, ascending
   TypeList ty[2];                            // 0 = edges, 1 = tets
   bool mixed = false;                        // both lists share ONE colouring: colour s of either type = step s of the visit
+  bool presetVerts = false;                  // verts holds the whole partition cell (tagged hand-over: every phase rewrites every vertex)
 };
 
 // Try to empty the highest colour classes: move each of their constraints to a lower colour that
@@ -996,13 +997,15 @@ void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& local
     nLocal = tb.rangeCount;
     for (uint32_t i = 0; i < tb.rangeCount; ++i) localOf[tb.rangeBegin + i] = i;
   } else {
-    std::vector<uint32_t> used;
-    for (int ty = 0; ty < 2; ++ty)
-      for (uint32_t k : tb.ty[ty].cons)
-        for (uint32_t j = 0; j < sets[ty].arity; ++j) used.push_back(sets[ty].at(k)[j]);
-    std::sort(used.begin(), used.end());
-    used.erase(std::unique(used.begin(), used.end()), used.end());
-    tb.verts.swap(used);
+    if (!tb.presetVerts) {
+      std::vector<uint32_t> used;
+      for (int ty = 0; ty < 2; ++ty)
+        for (uint32_t k : tb.ty[ty].cons)
+          for (uint32_t j = 0; j < sets[ty].arity; ++j) used.push_back(sets[ty].at(k)[j]);
+      std::sort(used.begin(), used.end());
+      used.erase(std::unique(used.begin(), used.end()), used.end());
+      tb.verts.swap(used);
+    }
     nLocal = (uint32_t)tb.verts.size();
     for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.verts[i]] = i;
   }
@@ -1560,6 +1563,13 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       PBD_PLAN_STAGE("  peak repair");
       if (!mixedThreads) finish_type(ty);
     }
+    // tagged hand-over (experimental): a shifted tile carries every vertex of its partition cell, touched
+    // by a constraint of this phase or not, so that every phase rewrites every vertex
+    if (opts.flags & PBD_FLAG_TAGGED_HANDOVER)
+      for (uint32_t p = 1; p < K; ++p) {
+        for (auto& tb : mainPh[p]) { tb.presetVerts = true; tb.verts.clear(); }
+        for (uint32_t sl = 0; sl < m.V; ++sl) mainPh[p][tileOfS[p][sl]].verts.push_back(sl);   // ascending
+      }
     if (mixedThreads) {
       joint_repair();
       PBD_PLAN_STAGE("  joint repair");

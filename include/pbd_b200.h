@@ -87,7 +87,17 @@ enum { PBD_BACKEND_AUTO = 0, PBD_BACKEND_STREAM = 1, PBD_BACKEND_TILE = 2 };
 enum { PBD_ORDER_STRICT = 0, PBD_ORDER_INTERLEAVED = 1 };
 enum {
   PBD_FLAG_STAGE_TIMING = 1u << 0, /* stream backend: no CUDA graph, CUDA events per stage   */
-  PBD_FLAG_NO_GRAPH = 1u << 1      /* stream backend: plain launches (debug / compute-sanitizer) */
+  PBD_FLAG_NO_GRAPH = 1u << 1,     /* stream backend: plain launches (debug / compute-sanitizer) */
+  PBD_FLAG_TAGGED_HANDOVER = 1u << 2, /* tile backend, EXPERIMENTAL: positions travel between
+                                      tiles as 64-bit {value, tag} pairs, no release fence / done flags.
+                                      Used only when every phase covers every vertex and the body is on
+                                      one GPU; otherwise ignored.                                          */
+  PBD_FLAG_FAST_ARITH = 1u << 3    /* tile and batch backends: the projections use FFMA, folded 1/6 factors and
+                                      the SFU reciprocal / rsqrt instead of the reference's SSE2 rounding
+                                      sequence (csrc/pbd_math.cuh: *_delta_fast).  Same constraints, same
+                                      schedule, results equal to the exact mode up to rounding: validated by
+                                      tolerance (RMS <= 1e-4 of the bounding-box diagonal after 10 frames,
+                                      residuals after 1000 frames), not bit for bit.                          */
 };
 
 typedef struct pbd_options {
