@@ -338,7 +338,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--backend", default="auto", choices=["auto", "stream", "tile"])
-    ap.add_argument("--order", default="interleaved", choices=["strict", "interleaved"],
+    ap.add_argument("--order", default="interleaved", choices=["strict", "interleaved", "riding"],
                     help="interleaved (default): a tile visit projects its edges then its tets, bit-exact vs the "
                          "oracle's sequence sweep; strict: all edges then all tets per iteration, bit-exact vs the "
                          "unmodified reference run on the permuted arrays")
@@ -394,7 +394,7 @@ def main():
     S, I = w["substeps"], w["iterations"]
     prm = capi.SolverParams.default(substeps=S, iterations=I)
     opt = capi.Options(backend={"auto": 0, "stream": 1, "tile": 2}[args.backend],
-                       order_mode=1 if args.order == "interleaved" else 0,
+                       order_mode={"strict": 0, "interleaved": 1, "riding": 2}[args.order],
                        block_threads=args.block_threads, tile_vertices=args.tile_vertices,
                        lanes_per_tet=args.lanes, partitions=args.partitions, tiles_per_sm=args.tiles_per_sm,
                        flags=(capi.FLAG_FAST_ARITH if args.fast else 0) | (capi.FLAG_TAGGED_HANDOVER if args.tagged else 0))

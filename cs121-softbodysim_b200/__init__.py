@@ -12,6 +12,8 @@ Contents (only what the hot path needs):
   meshgen.py deterministic inputs (Kuhn tet grids, edge builder, placement)
   shard.py   which bodies a rank owns + the max-over-ranks timing reduction (multi-GPU batches)
   build.py   the nvcc command line (``-gencode arch=compute_100a,code=sm_100a -lineinfo``)
+  wire.py    the PBD1 wire protocol, client side (what ``PBDRemoteWorld.cs`` speaks); the server side
+             is ``csrc/pbd_server.cpp`` -> ``pbd_server``, a native binary on top of the C ABI
 
 There is no CPU fallback: every solver call goes through ``libpbd_b200.so`` and raises if
 the library or a CUDA device is missing.
@@ -23,7 +25,7 @@ __all__ = ["meshgen"]
 
 def __getattr__(name):
     # capi/build are imported lazily so that meshgen stays usable before the library is built
-    if name in ("capi", "build", "shard"):
+    if name in ("capi", "build", "shard", "wire"):
         import importlib
 
         return importlib.import_module(f"{__name__}.{name}")

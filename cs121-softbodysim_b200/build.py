@@ -9,6 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpbd_b200.so")
+# (pbd_server.cpp is not part of the library: build_server links it against the library)
 SOURCES = ["pbd_plan.cpp", "pbd_tileplan.cpp", "pbd_stream.cu", "pbd_tile.cu", "pbd_batch.cu", "pbd_capi.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "pbd_b200.h")]
 
@@ -37,9 +38,29 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+SERVER = os.path.join(HERE, "pbd_server")
+SERVER_SRC = os.path.join(CSRC, "pbd_server.cpp")
+
+
+def build_server(force: bool = False) -> str:
+    """The PBD1 wire server (csrc/pbd_server.cpp) linked against the in-tree library."""
+    if not force and os.path.exists(SERVER) and os.path.getmtime(SERVER) >= max(os.path.getmtime(SERVER_SRC), os.path.getmtime(LIB)):
+        return SERVER
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-Wpedantic", "-Werror", SERVER_SRC, "-L", HERE, "-lpbd_b200",
+           "-Wl,-rpath,$ORIGIN", "-o", SERVER]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building pbd_server failed")
+    return SERVER
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source into cs121-softbodysim_b200/libpbd_b200.so; returns its path."""
+    """Compile every CUDA source into cs121-softbodysim_b200/libpbd_b200.so (and the wire server
+    cs121-softbodysim_b200/pbd_server on top of it); returns the library's path."""
     if not force and not stale():
+        build_server()
         return LIB
     cmd = [nvcc_path()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -50,6 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed (see {log})")
+    build_server(force=True)
     return LIB
 
 

@@ -33,7 +33,7 @@ LIB_PATH = os.environ.get("PBD_B200_LIB") or os.path.join(HERE, "libpbd_b200.so"
 
 PBD_OK, PBD_ERR_INVALID, PBD_ERR_INDEX, PBD_ERR_NO_DEVICE, PBD_ERR_CUDA, PBD_ERR_OOM, PBD_ERR_UNSUPPORTED = range(7)
 BACKEND_AUTO, BACKEND_STREAM, BACKEND_TILE = 0, 1, 2
-ORDER_STRICT, ORDER_INTERLEAVED = 0, 1
+ORDER_STRICT, ORDER_INTERLEAVED, ORDER_RIDING = 0, 1, 2
 FLAG_STAGE_TIMING, FLAG_NO_GRAPH, FLAG_TAGGED_HANDOVER, FLAG_FAST_ARITH = 1, 2, 4, 8
 ARRAY_INV_MASS, ARRAY_EDGE_REST, ARRAY_TET_REST, ARRAY_EDGE_LAMBDA, ARRAY_TET_LAMBDA, ARRAY_VELOCITY, ARRAY_XSTAR = range(7)
 

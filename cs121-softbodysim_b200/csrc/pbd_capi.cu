@@ -406,17 +406,28 @@ static int plan_sequence(const Plan& p, uint32_t* items) {
   for (const Phase& ph : p.phases)
     for (uint32_t t = ph.tileBegin; t < ph.tileBegin + ph.tileCount; ++t) {
       const Tile& tl = p.tiles[t];
+      // a tet, then its riders (PBD_ORDER_RIDING): the tet's thread projects them right after it
+      auto tet_unit = [&](uint32_t q) {
+        items[n++] = 0x80000000u | q;
+        if (tl.ride)
+          for (uint32_t sl = 0; sl < 2; ++sl)
+            if (p.tetRide[2 * (size_t)q + sl] != 0xffffffffu) items[n++] = p.tetRide[2 * (size_t)q + sl];
+      };
       if (tl.mixed) {   // colour step s = edge group s, then tet group s (vertex-disjoint: any order inside a step is the same)
         for (uint32_t g = 0; g < tl.edgeGroupCount; ++g) {
           const Group& ge = p.groups[tl.edgeGroupBegin + g];
           const Group& gt = p.groups[tl.tetGroupBegin + g];
           for (uint32_t j = 0; j < ge.count; ++j) items[n++] = ge.begin + j;
-          for (uint32_t j = 0; j < gt.count; ++j) items[n++] = 0x80000000u | (gt.begin + j);
+          for (uint32_t j = 0; j < gt.count; ++j) tet_unit(gt.begin + j);
         }
         continue;
       }
-      for (uint32_t j = 0; j < tl.edgeCount; ++j) items[n++] = tl.edgeBegin + j;
-      for (uint32_t j = 0; j < tl.tetCount; ++j) items[n++] = 0x80000000u | (tl.tetBegin + j);
+      // the tile's free edges (its colour groups cover exactly those), then its tets
+      uint32_t nFree = 0;
+      for (uint32_t g = 0; g < tl.edgeGroupCount; ++g) nFree += p.groups[tl.edgeGroupBegin + g].count;
+      if (!tl.ride) nFree = tl.edgeCount;
+      for (uint32_t j = 0; j < nFree; ++j) items[n++] = tl.edgeBegin + j;
+      for (uint32_t j = 0; j < tl.tetCount; ++j) tet_unit(tl.tetBegin + j);
     }
   return PBD_OK;
 }

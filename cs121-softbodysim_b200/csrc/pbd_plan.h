@@ -49,6 +49,9 @@ struct Tile {
   uint32_t tetGroupBegin = 0, tetGroupCount = 0;
   uint32_t edgeDevBegin = 0, tetDevBegin = 0;       // first device index (16-byte aligned ranges)
   uint32_t mixed = 0;       // 1: edge group s and tet group s form colour step s of the visit (same group count, vertex-disjoint)
+  uint32_t ride = 0;        // 1: PBD_ORDER_RIDING -- the tile's edge list ends with RIDERS (edges projected by the thread of
+                            //    their host tet right after it, no colour group of their own); its record block carries a
+                            //    u32 per tet = tile-local edge positions of the (at most two) riders, 0xffff = none
 };
 
 struct Phase {
@@ -88,6 +91,10 @@ struct Plan {
   uint32_t blockThreads = 0;
   uint32_t edgePhases = 0, tetPhases = 0;
   uint32_t edgeColorSum = 0, tetColorSum = 0;  // sum over phases of the max local colour count
+  // PBD_ORDER_RIDING: per tet schedule position, the schedule positions of its riders (2 entries,
+  // 0xffffffff = none); empty otherwise.  riders = number of edges that ride.
+  std::vector<uint32_t> tetRide;
+  uint32_t riders = 0;
 
   // introspection, caller indexing
   std::vector<uint32_t> edgePhase, edgeTile, edgeColor;
@@ -124,14 +131,15 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
 //   | edge lambda f32[nE] | tet lambda f32[nT]            (the last two come from the lambda arrays)
 inline uint32_t pad4(uint32_t n) { return (n + 3u) & ~3u; }
 constexpr uint32_t kMaxPreds = 32;   // tiles of the previous phase a tile can depend on (point-to-point sync)
+// (`ride`: one more u32 per tet, right after the tet rest values)
 inline uint32_t tile_static_bytes(uint32_t nVertGather, uint32_t nEdgeGroups, uint32_t nTetGroups, uint32_t nE,
-                                  uint32_t nT) {
+                                  uint32_t nT, bool ride = false) {
   return 64u + 4u * kMaxPreds + 4u * pad4(nVertGather) + 8u * (pad4(nEdgeGroups * 2) / 2) + 8u * (pad4(nTetGroups * 2) / 2) +
-         8u * pad4(nE) + 8u * (pad4(nT * 2) / 2) + 4u * pad4(nT);
+         8u * pad4(nE) + 8u * (pad4(nT * 2) / 2) + 4u * pad4(nT) + (ride ? 4u * pad4(nT) : 0u);
 }
 inline uint32_t tile_record_bytes(uint32_t nVertGather, uint32_t nEdgeGroups, uint32_t nTetGroups, uint32_t nE,
-                                  uint32_t nT) {
-  return tile_static_bytes(nVertGather, nEdgeGroups, nTetGroups, nE, nT) + 4u * pad4(nE) + 4u * pad4(nT);
+                                  uint32_t nT, bool ride = false) {
+  return tile_static_bytes(nVertGather, nEdgeGroups, nTetGroups, nE, nT, ride) + 4u * pad4(nE) + 4u * pad4(nT);
 }
 
 // Reference init helpers restated for the host (bit-exact, caller's constraint order):

@@ -31,7 +31,7 @@ namespace pbd {
 
 // first 64 bytes of a tile's record block (shared memory); offsets in bytes from the block start
 struct TileHdr {
-  uint32_t vertCount, flags, vertBegin, nEdgeGroups;   // flags: bit 0 = contiguous slot range, bit 1 = system-scope sync, bit 2 = mixed steps, bits 8..15 = predecessor count
+  uint32_t vertCount, flags, vertBegin, nEdgeGroups;   // flags: bit 0 = contiguous slot range, bit 1 = system-scope sync, bit 2 = mixed steps, bit 3 = riders (u32 per tet behind the tet rest values), bits 8..15 = predecessor count
   uint32_t nTetGroups, nEdges, nTets, offVertIdx;
   uint32_t offEdgeGroups, offTetGroups, offEdgeIdx, offEdgeRest;
   uint32_t offTetIdx, offTetRest, offEdgeLam, offTetLam;
@@ -108,6 +108,57 @@ PBD_DEV void project_tet_at(uint32_t sv, uint32_t idA, uint32_t restA, uint32_t 
   project_tet_rec<FAST>(sv, id, r, l, lamA, alpha);
 }
 
+// PBD_ORDER_RIDING: the (at most two) edges that ride on the tet at `o4` = 4 * its position are
+// projected by the tet's own thread right after the tet, on the vertices it has just written (same
+// thread, same addresses: program order, no barrier).  rideA = address of the tile's ride array,
+// eIdx/eRest/eLam = addresses of entry 0 of the tile's edge arrays.
+template <bool FAST>
+PBD_DEV void project_riders(uint32_t sv, uint32_t rideA, uint32_t o4, uint32_t eIdx, uint32_t eRest, uint32_t eLam, float alphaE) {
+  const uint32_t rp = lds_u32(rideA + o4);
+  const uint32_t p0 = (rp & 0xffffu) << 2, p1 = (rp >> 16) << 2;
+  if (p0 != (0xffffu << 2)) project_edge_at<FAST>(sv, eIdx + p0, eRest + p0, eLam + p0, alphaE);
+  if (p1 != (0xffffu << 2)) project_edge_at<FAST>(sv, eIdx + p1, eRest + p1, eLam + p1, alphaE);
+}
+
+#ifdef PBD_NO_REG_RIDERS   // A/B switch (tools/build_variant.sh): fast riders through shared memory like the exact ones
+constexpr bool kRegRiders = false;
+#else
+constexpr bool kRegRiders = true;
+#endif
+// Fast arithmetic + riders: the whole unit on registers.  The upload relabelled the tet (even
+// permutation) so that rider 0 is the edge (a, b) and rider 1 the edge (c, d); the riders are
+// projected on the tet's freshly updated registers and the four vertices are stored once.
+PBD_DEV void project_tet_unit_fast(uint32_t sv, uint32_t idA, uint32_t restA, uint32_t lamA, float alphaT, uint32_t rideWordA,
+                                   uint32_t eRest, uint32_t eLam, float alphaE) {
+  const uint2 id = lds_v2(idA);
+  const float r = lds_f32(restA), l = lds_f32(lamA);
+  const uint32_t rp = lds_u32(rideWordA);
+  const uint32_t a = sv + ((id.x & 0xffffu) << 4), b = sv + ((id.x >> 16) << 4);
+  const uint32_t c = sv + ((id.y & 0xffffu) << 4), d = sv + ((id.y >> 16) << 4);
+  float4 pa = lds_v4(a), pb = lds_v4(b), pc = lds_v4(c), pd = lds_v4(d);
+  const uint32_t p0 = (rp & 0xffffu) << 2, p1 = (rp >> 16) << 2;
+  const bool has0 = p0 != (0xffffu << 2), has1 = p1 != (0xffffu << 2);
+  float r0 = 0.f, l0 = 0.f, r1 = 0.f, l1 = 0.f;
+  if (has0) { r0 = lds_f32(eRest + p0); l0 = lds_f32(eLam + p0); }
+  if (has1) { r1 = lds_f32(eRest + p1); l1 = lds_f32(eLam + p1); }
+  {
+    float4 qa = pa, qb = pb, qc = pc, qd = pd;
+    float nl;
+    if (tet_delta_fast(qa, qb, qc, qd, r, l, alphaT, nl)) { pa = qa; pb = qb; pc = qc; pd = qd; sts_f32(lamA, nl); }
+  }
+  if (has0) {
+    float4 q0, q1;
+    float nl;
+    if (edge_delta_fast(pa, pb, r0, l0, alphaE, q0, q1, nl)) { pa = q0; pb = q1; sts_f32(eLam + p0, nl); }
+  }
+  if (has1) {
+    float4 q0, q1;
+    float nl;
+    if (edge_delta_fast(pc, pd, r1, l1, alphaE, q0, q1, nl)) { pc = q0; pd = q1; sts_f32(eLam + p1, nl); }
+  }
+  sts_v4(a, pa); sts_v4(b, pb); sts_v4(c, pc); sts_v4(d, pd);
+}
+
 // ---------------------------------------------------------------- sweeps (shared memory only)
 //
 // Everything a colour step touches lives in shared memory: `rec` / `svOff` are byte offsets into
@@ -145,7 +196,7 @@ PBD_SWEEP_INLINE void sweep_edges(const TileHdr& h, uint32_t rec, uint32_t svOff
 // exchanged with quad shuffles and summed in the reference's order, which keeps the result
 // bit-identical while shortening the dependent instruction stream of a colour step.
 template <int LANES, bool FAST>
-PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff, float alpha, long long* ft) {
+PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff, float alpha, long long* ft, float alphaE = 0.0f) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t n = h.nTetGroups;
   if (n == 0) return;
@@ -160,11 +211,19 @@ PBD_SWEEP_INLINE void sweep_tets(const TileHdr& h, uint32_t rec, uint32_t svOff,
     uint32_t grp = base + rec + h.offTetGroups;
     const uint32_t idA = base + rec + h.offTetIdx + 8u * tid, restA = base + rec + h.offTetRest + 4u * tid,
                    lamA = base + rec + h.offTetLam + 4u * tid;
+    const bool ride = (h.flags & 8u) != 0u;
+    const uint32_t rideA = restA + 4u * ((h.nTets + 3u) & ~3u);   // the ride array follows the rest values
+    const uint32_t eIdx = base + rec + h.offEdgeIdx, eRest = base + rec + h.offEdgeRest, eLam = base + rec + h.offEdgeLam;
     for (uint32_t g = 0; g < n; ++g, grp += 8u) {
       const uint2 gd = lds_v2(grp);
       if (tid < gd.y) {
         const uint32_t o = gd.x << 2;
-        project_tet_at<FAST>(svA, idA + 2u * o, restA + o, lamA + o, alpha);
+        if (FAST && ride && kRegRiders) {
+          project_tet_unit_fast(svA, idA + 2u * o, restA + o, lamA + o, alpha, rideA + o, eRest, eLam, alphaE);
+        } else {
+          project_tet_at<FAST>(svA, idA + 2u * o, restA + o, lamA + o, alpha);
+          if (ride) project_riders<FAST>(svA, rideA, o, eIdx, eRest, eLam, alphaE);
+        }
       }
       __syncthreads();
       PBD_STEP_TRACE(ft, g, gd.y);
@@ -338,6 +397,9 @@ PBD_SWEEP_INLINE void sweep_mixed(const TileHdr& h, uint32_t rec, uint32_t svOff
                  eLamA = base + rec + h.offEdgeLam + 4u * tid;
   const uint32_t tIdA = base + rec + h.offTetIdx + 8u * rtid, tRestA = base + rec + h.offTetRest + 4u * rtid,
                  tLamA = base + rec + h.offTetLam + 4u * rtid;
+  const bool ride = (h.flags & 8u) != 0u;
+  const uint32_t rideA = tRestA + 4u * ((h.nTets + 3u) & ~3u);   // the ride array follows the tet rest values
+  const uint32_t eIdx0 = base + rec + h.offEdgeIdx, eRest0 = base + rec + h.offEdgeRest, eLam0 = base + rec + h.offEdgeLam;
 #ifdef PBD_SWEEP_PREFETCH
   // The record of a thread's NEXT constraint (group entry, indices, rest value, lambda -- none of
   // which another constraint ever writes) is fetched before the block barrier, so that after the
@@ -394,7 +456,12 @@ PBD_SWEEP_INLINE void sweep_mixed(const TileHdr& h, uint32_t rec, uint32_t svOff
       project_edge_at<FAST>(sv, eIdA + o, eRestA + o, eLamA + o, alphaE);
     } else if (rtid < gt.y) {
       const uint32_t o = gt.x << 2;
-      project_tet_at<FAST>(sv, tIdA + 2u * o, tRestA + o, tLamA + o, alphaT);
+      if (FAST && ride && kRegRiders) {
+        project_tet_unit_fast(sv, tIdA + 2u * o, tRestA + o, tLamA + o, alphaT, rideA + o, eRest0, eLam0, alphaE);
+      } else {
+        project_tet_at<FAST>(sv, tIdA + 2u * o, tRestA + o, tLamA + o, alphaT);
+        if (ride) project_riders<FAST>(sv, rideA, o, eIdx0, eRest0, eLam0, alphaE);
+      }
     }
     __syncthreads();
     PBD_STEP_TRACE(ft, g, ge.y + (gt.y << 16));

@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           } else {
             sweep_edges<FAST>(h, recOff, svOff, k.alphaEdge, ft);
             if (ft) ft[3] = clock64();
-            sweep_tets<LANES, FAST>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr);
+            sweep_tets<LANES, FAST>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr, k.alphaEdge);
           }
           if (ft) ft[4] = clock64();
           // ---- write back
@@ -616,7 +616,7 @@ class TileBackend final : public Backend {
       const uint32_t nVG = t.contiguous ? 0u : t.vertCount;
       TileHdr h{};
       const uint32_t nPred = useFlags_ ? (uint32_t)preds[ti].size() : 0u;
-      h.vertCount = t.vertCount; h.flags = (t.contiguous ? 1u : 0u) | (remote[ti] ? 2u : 0u) | (t.mixed ? 4u : 0u) | (nPred << 8); h.vertBegin = t.contiguous ? t.vertBegin : 0u;
+      h.vertCount = t.vertCount; h.flags = (t.contiguous ? 1u : 0u) | (remote[ti] ? 2u : 0u) | (t.mixed ? 4u : 0u) | (t.ride ? 8u : 0u) | (nPred << 8); h.vertBegin = t.contiguous ? t.vertBegin : 0u;
       h.nEdgeGroups = t.edgeGroupCount; h.nTetGroups = t.tetGroupCount; h.nEdges = t.edgeCount; h.nTets = t.tetCount;
       // planner invariants the sweeps rely on (pbd_sweep.cuh projects a colour group in ONE pass of the
       // block and would silently drop the rest): fail loudly instead
@@ -636,10 +636,13 @@ class TileBackend final : public Backend {
       h.offEdgeRest = off; off += 4u * pad4(t.edgeCount);
       h.offTetIdx = off; off += 8u * (pad4(t.tetCount * 2) / 2);
       h.offTetRest = off; off += 4u * pad4(t.tetCount);
+      const uint32_t offTetRide = off;   // PBD_ORDER_RIDING: u32 per tet, right behind the rest values (the kernel derives the offset)
+      if (t.ride) off += 4u * pad4(t.tetCount);
       const uint32_t staticBytes = off;
       h.offEdgeLam = off; off += 4u * pad4(t.edgeCount);
       h.offTetLam = off; off += 4u * pad4(t.tetCount);
-      if (staticBytes != tile_static_bytes(nVG, t.edgeGroupCount, t.tetGroupCount, t.edgeCount, t.tetCount)) return cudaErrorUnknown;
+      if (staticBytes != tile_static_bytes(nVG, t.edgeGroupCount, t.tetGroupCount, t.edgeCount, t.tetCount, t.ride != 0)) return cudaErrorUnknown;
+      if (t.ride && (t.edgeCount >= 0xffffu || plan.tetRide.size() != 2 * (size_t)plan.T)) return cudaErrorInvalidConfiguration;
       recMax = std::max(recMax, off);
 
       const size_t base = blob.size();
@@ -675,10 +678,42 @@ class TileBackend final : public Backend {
       float* trs = reinterpret_cast<float*>(b + h.offTetRest);
       for (uint32_t q = 0; q < t.tetCount; ++q) {
         const size_t kk = (size_t)t.tetBegin + q;
-        const uint16_t* l = &plan.tetLocal[4 * kk];
+        uint16_t l[4] = {plan.tetLocal[4 * kk], plan.tetLocal[4 * kk + 1], plan.tetLocal[4 * kk + 2], plan.tetLocal[4 * kk + 3]};
+        if (fast_ && kRegRiders && t.ride && plan.tetRide[2 * kk] != 0xffffffffu) {
+          // fast arithmetic keeps a tet's riders in registers: relabel the tet's vertices by an EVEN
+          // permutation (same signed volume, same rest value / lambda) so that rider 0 is the edge
+          // (v0, v1) and rider 1 -- the opposite edge, if there is one -- is (v2, v3).  The edge's
+          // own orientation does not matter (its correction is antisymmetric).  Exact arithmetic never
+          // relabels: the reference's rounding sequence depends on the caller's vertex order.
+          const size_t ek = plan.tetRide[2 * kk];
+          const uint16_t a = plan.edgeLocal[2 * ek], b = plan.edgeLocal[2 * ek + 1];
+          int ia = -1, ib = -1;
+          for (int j = 0; j < 4; ++j) { if (l[j] == a && ia < 0) ia = j; else if (l[j] == b && ib < 0) ib = j; }
+          if (ia < 0 || ib < 0) return cudaErrorInvalidConfiguration;   // a rider's vertices are its host's
+          int rest2[2], nr = 0;
+          for (int j = 0; j < 4; ++j) if (j != ia && j != ib) rest2[nr++] = j;
+          int perm[4] = {ia, ib, rest2[0], rest2[1]};
+          int inv = 0;
+          for (int x = 0; x < 4; ++x) for (int y = x + 1; y < 4; ++y) inv += perm[x] > perm[y];
+          if (inv & 1) std::swap(perm[2], perm[3]);
+          const uint16_t o4[4] = {l[0], l[1], l[2], l[3]};
+          for (int j = 0; j < 4; ++j) l[j] = o4[perm[j]];
+        }
         tix[2 * q] = (uint32_t)l[0] | ((uint32_t)l[1] << 16);
         tix[2 * q + 1] = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
         trs[q] = tRest[plan.tetDev[kk]];
+      }
+      if (t.ride) {
+        uint32_t* rd = reinterpret_cast<uint32_t*>(b + offTetRide);
+        for (uint32_t q = 0; q < t.tetCount; ++q) {
+          uint32_t pos[2];
+          for (uint32_t sl = 0; sl < 2; ++sl) {
+            const uint32_t gp = plan.tetRide[2 * ((size_t)t.tetBegin + q) + sl];   // schedule position of the rider
+            if (gp != 0xffffffffu && (gp < t.edgeBegin || gp - t.edgeBegin >= t.edgeCount)) return cudaErrorInvalidConfiguration;
+            pos[sl] = gp == 0xffffffffu ? 0xffffu : gp - t.edgeBegin;
+          }
+          rd[q] = pos[0] | (pos[1] << 16);
+        }
       }
       TileCopy& c = copies[ti];
       c.blobOff = base;

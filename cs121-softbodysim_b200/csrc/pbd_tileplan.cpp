@@ -401,6 +401,7 @@ struct TileBuild {
   TypeList ty[2];                            // 0 = edges, 1 = tets
   bool mixed = false;                        // both lists share ONE colouring: colour s of either type = step s of the visit
   bool presetVerts = false;                  // verts holds the whole partition cell (tagged hand-over: every phase rewrites every vertex)
+  uint32_t nRiders = 0;                      // PBD_ORDER_RIDING: edges that ride on this tile's tets (not in ty[0].cons)
 };
 
 // Try to empty the highest colour classes: move each of their constraints to a lower colour that
@@ -1022,10 +1023,10 @@ void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& local
   }
 }
 
-uint32_t tile_bytes(const TileBuild& tb) {
+uint32_t tile_bytes(const TileBuild& tb, bool ride = false) {
   const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
   const uint32_t rec = tile_record_bytes(tb.contiguous ? 0u : nv, tb.ty[0].nColours, tb.ty[1].nColours,
-                                         (uint32_t)tb.ty[0].cons.size(), (uint32_t)tb.ty[1].cons.size());
+                                         (uint32_t)tb.ty[0].cons.size() + tb.nRiders, (uint32_t)tb.ty[1].cons.size(), ride);
   return 16u * nv + 2u * rec;   // vertices + double-buffered record block
 }
 
@@ -1122,14 +1123,16 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   plan.V = m.V; plan.E = m.E; plan.T = m.T;
   plan.backend = PBD_BACKEND_TILE;
   plan.orderMode = opts.order_mode;
-  if (opts.order_mode != PBD_ORDER_STRICT && opts.order_mode != PBD_ORDER_INTERLEAVED) { err = "unknown order_mode"; return false; }
-  const bool fused = opts.order_mode == PBD_ORDER_INTERLEAVED;
+  if (opts.order_mode != PBD_ORDER_STRICT && opts.order_mode != PBD_ORDER_INTERLEAVED && opts.order_mode != PBD_ORDER_RIDING) { err = "unknown order_mode"; return false; }
+  const bool riding = opts.order_mode == PBD_ORDER_RIDING;
+  if (riding && opts.lanes_per_tet > 1) { err = "PBD_ORDER_RIDING needs one thread per tet (lanes_per_tet <= 1)"; return false; }
+  const bool fused = opts.order_mode == PBD_ORDER_INTERLEAVED || riding;
   const uint32_t blockThreads = opts.block_threads ? opts.block_threads : (opts.tiles_per_sm >= 2 ? 256u : 512u);
   if (blockThreads % 32 || blockThreads > 512) { err = "block_threads must be a multiple of 32, <= 512"; return false; }
   plan.blockThreads = blockThreads;
   // interleaved order, one thread per tet: edges and tets of a tile visit share the colour steps
   const bool noMixed = !knobs().mixed;   // debug: A/B against separate sweeps
-  const uint32_t mixedThreads = (fused && opts.lanes_per_tet <= 1 && !noMixed) ? blockThreads : 0u;
+  const uint32_t mixedThreads = (fused && opts.lanes_per_tet <= 1 && (!noMixed || riding)) ? blockThreads : 0u;
   // most constraints of one type a colour step can take: one block pass
   const uint32_t caps[2] = {blockThreads, std::max(1u, blockThreads / std::max(1u, opts.lanes_per_tet))};
   if (opts.partitions > kMaxPartitions) { err = "partitions must be <= 8"; return false; }
@@ -1388,11 +1391,14 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
         if (above > (size_t)K * nTilesMax) break;
       }
     };
-    for (int ty = 0; ty < 2; ++ty) {
+    // PBD_ORDER_RIDING: riderOf[2 * tet + slot] = edge riding on that tet (NONE = free slot),
+    // hostOf[edge] = its host tet (NONE = a free edge, scheduled like any edge of the interleaved order)
+    std::vector<uint32_t> riderOf, hostOf;
+    auto assign_type = [&](int ty, bool onTop) {
       const CSet& cs = sets[ty];
-      // mixed steps: a visit's step count follows the JOINT load of a vertex, so the tets are
-      // balanced on top of the edge loads already placed
-      if (!(mixedThreads && ty == 1 && knobs().jointLoad)) std::fill(load.begin(), load.end(), (uint16_t)0);
+      // mixed steps: a visit's step count follows the JOINT load of a vertex, so the second type is
+      // balanced on top of the loads the first one already placed
+      if (!onTop) std::fill(load.begin(), load.end(), (uint16_t)0);
       std::vector<uint8_t>& mask = maskA[ty];
       std::vector<uint8_t>& phaseOf = phaseA[ty];
       mask.assign(cs.n, 0);
@@ -1407,6 +1413,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           for (uint32_t j = 1; j < cs.arity; ++j) same &= tileOfS[p][id[j]] == t;
           if (same) mk |= (uint8_t)(1u << p);
         }
+        if (ty == 0 && riding && hostOf[k] != NONE) { mask[k] = 0; continue; }   // a rider: it goes where its host tet goes
         mask[k] = mk;
         bucket[__builtin_popcount(mk)].push_back(k);
       }
@@ -1562,6 +1569,66 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       }
       PBD_PLAN_STAGE("  peak repair");
       if (!mixedThreads) finish_type(ty);
+    };
+    if (!riding) {
+      assign_type(0, false);
+      assign_type(1, mixedThreads && knobs().jointLoad);
+    } else {
+      // tets first; then every edge looks for a host among the tets that contain it (a tet that is
+      // admissible in some partition: wherever the planner puts it, all its vertices -- hence the
+      // edge's -- lie in one tile there).  A tet takes at most two riders, and two only if they are
+      // opposite edges of it (vertex-disjoint), which is what the kernel's register-resident form
+      // needs.  Edges without a host stay free and are balanced on top of the tet loads.
+      assign_type(1, false);
+      riderOf.assign((size_t)m.T * 2, NONE);
+      hostOf.assign(m.E, NONE);
+      {
+        // (vertex pair) -> tets containing it: sorted list of (lo << 32 | hi, tet * 8 + pair code)
+        static const uint8_t pr[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};   // code c and 5 - c are opposite
+        std::vector<std::pair<uint64_t, uint32_t>> inc;
+        inc.reserve((size_t)m.T * 6);
+        for (uint32_t t = 0; t < m.T; ++t) {
+          if (maskA[1][t] == 0) continue;   // residual tets do not host
+          const uint32_t* id = sets[1].at(t);
+          for (uint32_t c = 0; c < 6; ++c) {
+            const uint32_t a = id[pr[c][0]], b = id[pr[c][1]];
+            if (a == b) continue;
+            inc.emplace_back(((uint64_t)std::min(a, b) << 32) | std::max(a, b), t * 8u + c);
+          }
+        }
+        std::sort(inc.begin(), inc.end());
+        auto range_of = [&](uint32_t e, size_t& lo, size_t& hi) {
+          const uint32_t a = sets[0].at(e)[0], b = sets[0].at(e)[1];
+          const uint64_t key = ((uint64_t)std::min(a, b) << 32) | std::max(a, b);
+          lo = std::lower_bound(inc.begin(), inc.end(), std::make_pair(key, 0u)) - inc.begin();
+          hi = lo;
+          while (hi < inc.size() && inc[hi].first == key) ++hi;
+        };
+        // passes 0, 1: a host without a rider yet (edges with <= 2 candidates first, then the rest);
+        // pass 2: a host whose rider is the opposite edge
+        std::vector<uint8_t> codeOf((size_t)m.T * 2, 0);
+        for (int pass = 0; pass < 3; ++pass)
+          for (uint32_t e = 0; e < m.E; ++e) {
+            if (hostOf[e] != NONE || sets[0].at(e)[0] == sets[0].at(e)[1]) continue;
+            size_t lo, hi;
+            range_of(e, lo, hi);
+            if (pass == 0 && hi - lo > 2) continue;
+            for (size_t i = lo; i < hi && hostOf[e] == NONE; ++i) {
+              const uint32_t t = inc[i].second >> 3, c = inc[i].second & 7u;
+              if (pass < 2) {
+                if (riderOf[2 * (size_t)t] == NONE) { riderOf[2 * (size_t)t] = e; codeOf[2 * (size_t)t] = (uint8_t)c; hostOf[e] = t; }
+              } else if (riderOf[2 * (size_t)t] != NONE && riderOf[2 * (size_t)t + 1] == NONE && codeOf[2 * (size_t)t] + c == 5u) {
+                riderOf[2 * (size_t)t + 1] = e; codeOf[2 * (size_t)t + 1] = (uint8_t)c; hostOf[e] = t;
+              }
+            }
+          }
+        uint32_t nRide = 0;
+        for (uint32_t e = 0; e < m.E; ++e) nRide += hostOf[e] != NONE;
+        plan.riders = nRide;
+        if (knobs().debug) fprintf(stderr, "[plan] riding: %u of %u edges ride on a tet, %u stay free\n", nRide, m.E, m.E - nRide);
+      }
+      PBD_PLAN_STAGE("  riders");
+      assign_type(0, true);
     }
     // tagged hand-over (experimental): a shifted tile carries every vertex of its partition cell, touched
     // by a constraint of this phase or not, so that every phase rewrites every vertex
@@ -1575,6 +1642,12 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       PBD_PLAN_STAGE("  joint repair");
       finish_type(0);
       finish_type(1);
+      if (riding)
+        for (uint32_t p = 0; p < K; ++p)
+          for (auto& tb : mainPh[p]) {
+            tb.nRiders = 0;
+            for (uint32_t k : tb.ty[1].cons) tb.nRiders += (riderOf[2 * (size_t)k] != NONE) + (riderOf[2 * (size_t)k + 1] != NONE);
+          }
       PBD_PLAN_STAGE("  tile balance");
     }
     PBD_PLAN_STAGE("assignment");
@@ -1606,8 +1679,8 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
                 }
           }
           ++tileId;
-          const uint32_t nE = (uint32_t)tb.ty[0].cons.size(), nT = (uint32_t)tb.ty[1].cons.size();
-          const uint32_t rec = tile_record_bytes(tb.contiguous ? 0u : nv, nE ? 1u : 0u, nT ? 1u : 0u, nE, nT);
+          const uint32_t nE = (uint32_t)tb.ty[0].cons.size() + tb.nRiders, nT = (uint32_t)tb.ty[1].cons.size();
+          const uint32_t rec = tile_record_bytes(tb.contiguous ? 0u : nv, nE ? 1u : 0u, nT ? 1u : 0u, nE, nT, riding);
           if (nv > 65535u || 16u * nv + 2u * rec > smemBytes) { fits = false; break; }
         }
     }
@@ -1623,7 +1696,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
           TileBuild& tb = *work[i];
           finish_tile(sets, tb, lo, sc, caps, mixedThreads);
           const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
-          if (nv > 65535u || tile_bytes(tb) > smemBytes) ok = false;
+          if (nv > 65535u || tile_bytes(tb, riding) > smemBytes) ok = false;
         }
       };
       const unsigned nThreads = (m.T + m.E < 200000u) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -1720,7 +1793,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
         build_residual_phases(sets, ty, resid[ty], m.V, resCap, resPh[ty], localOf, scratch, caps);
         for (auto& ph : resPh[ty])
           for (auto& tb : ph)
-            if (tile_bytes(tb) > smemBytes) ok = false;
+            if (tile_bytes(tb, riding) > smemBytes) ok = false;
       }
       if (ok) break;
       if (resCap <= 16) { err = "a residual tile does not fit in shared memory"; return false; }
@@ -1760,6 +1833,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     plan.tetPhase.assign(m.T, 0); plan.tetTile.assign(m.T, 0); plan.tetColor.assign(m.T, 0);
     for (uint32_t t = 0; t < nTile0; ++t) plan.tileVertexCapacity = std::max(plan.tileVertexCapacity, tile0Begin[t + 1] - tile0Begin[t]);
     uint32_t devCur[2] = {0, 0};
+    std::vector<uint32_t> ridePos(riding ? m.E : 0u, NONE);   // rider edge -> its schedule position
     for (size_t pi = 0; pi < seq.size(); ++pi) {
       const PhaseRef& pr = seq[pi];
       Phase P;
@@ -1768,12 +1842,14 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       bool anyE = false, anyT = false;
       for (size_t ti = 0; ti < pr.tiles->size(); ++ti) {
         TileBuild& tb = (*pr.tiles)[ti];
-        const bool hasE = pr.useE && !tb.ty[0].cons.empty(), hasT = pr.useT && !tb.ty[1].cons.empty();
+        const bool hasT = pr.useT && !tb.ty[1].cons.empty();
+        const bool hasE = pr.useE && (!tb.ty[0].cons.empty() || (hasT && tb.nRiders != 0));
         const bool isHome = pr.home && pi == 0;   // the very first phase covers every slot (vertex stages are fused into it)
         if (!hasE && !hasT && !(isHome && tb.contiguous)) continue;
         Tile tl;
         tl.contiguous = tb.contiguous ? 1u : 0u;
         tl.mixed = (tb.mixed && hasE && hasT) ? 1u : 0u;
+        tl.ride = (riding && hasT) ? 1u : 0u;
         uint32_t nLocal;
         if (tb.contiguous) {
           tl.vertBegin = tb.rangeBegin;
@@ -1852,14 +1928,35 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
             }
             i = j;
           }
-          count = (uint32_t)order.size() - begin;
           gCount = (uint32_t)plan.groups.size() - gBegin;
+          if (ty == 0 && tl.ride && tb.nRiders) {
+            // riders: behind the tile's free edges, in the order of their host tets; no colour group
+            for (size_t q = 0; q < tb.ty[1].cons.size(); ++q)
+              for (uint32_t sl = 0; sl < 2; ++sl) {
+                const uint32_t c = riderOf[2 * (size_t)tb.ty[1].cons[q] + sl];
+                if (c == NONE) continue;
+                cPhase[c] = (uint32_t)plan.phases.size();
+                cTile[c] = (uint32_t)plan.tiles.size();
+                cCol[c] = tb.ty[1].colour.empty() ? 0u : tb.ty[1].colour[q];
+                for (uint32_t a = 0; a < 2; ++a) local.push_back((uint16_t)localOf[cs.at(c)[a]]);
+                ridePos[c] = (uint32_t)order.size();
+                order.push_back(c);
+                dev.push_back(devCur[ty]++);
+              }
+          }
+          if (ty == 1 && riding)
+            for (uint32_t q = begin; q < (uint32_t)order.size(); ++q)
+              for (uint32_t sl = 0; sl < 2; ++sl) {
+                const uint32_t c = tl.ride ? riderOf[2 * (size_t)order[q] + sl] : NONE;
+                plan.tetRide.push_back(c == NONE ? NONE : ridePos[c]);
+              }
+          count = (uint32_t)order.size() - begin;
           mxCol[ty] = std::max(mxCol[ty], gCount);
           (ty ? anyT : anyE) = true;
         }
         plan.tileRecordBytes = std::max(plan.tileRecordBytes,
                                         tile_record_bytes(tl.contiguous ? 0u : tl.vertCount, tl.edgeGroupCount,
-                                                          tl.tetGroupCount, tl.edgeCount, tl.tetCount));
+                                                          tl.tetGroupCount, tl.edgeCount, tl.tetCount, tl.ride != 0));
         plan.tiles.push_back(tl);
       }
       P.tileCount = (uint32_t)plan.tiles.size() - P.tileBegin;

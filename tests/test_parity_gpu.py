@@ -516,7 +516,7 @@ def test_fast_arith_parameter_and_degenerate_paths(mode, flags, capi, po, meshge
             assert np.sqrt(np.mean(np.sum((a.astype(np.float64) - b) ** 2, 1))) / diag <= 1e-5, prm
 
 
-@pytest.mark.parametrize("mode,flags", [("exact-interleaved", 0), ("exact-tagged", 4), ("fast+tagged", 12)])
+@pytest.mark.parametrize("mode,flags", [("exact-interleaved", 0), ("exact-tagged", 4), ("fast+tagged", 12), ("riding", 0), ("riding-fast", 8)])
 def test_p3_config1_1000_frames_tile_modes(mode, flags, capi, po, meshgen, golden):
     """P3 (see test_p3_config1_1000_frames_residuals_no_worse_than_reference) for the modes bench.py runs:
     interleaved order, tagged hand-over, fast arithmetic.  The measured residuals are written to
@@ -525,7 +525,8 @@ def test_p3_config1_1000_frames_tile_modes(mode, flags, capi, po, meshgen, golde
     g = golden("ref_config1_p3_window.npz")
     window = [int(f) for f in g["window"]]
     ref_worst = g["residuals"].mean(axis=1).max(axis=0)
-    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_INTERLEAVED, flags=flags)
+    om = capi.ORDER_RIDING if mode.startswith("riding") else capi.ORDER_INTERLEAVED
+    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=om, flags=flags)
     with capi.Body(capi.SolverParams.default(substeps=10), x0, edges, tets, device=0, options=opt) as b:
         done, rows = 0, []
         for fr in window:
@@ -537,3 +538,59 @@ def test_p3_config1_1000_frames_tile_modes(mode, flags, capi, po, meshgen, golde
             rows.append([r["edge_rms"], r["vol_rel"], r["tet_vol_rms"]])
         mean = np.mean(rows, axis=0)
         assert (mean <= 1.10 * ref_worst[:3]).all(), (mode, mean, ref_worst)
+
+
+@pytest.mark.parametrize("flags", [0, 4])
+@pytest.mark.parametrize("mesh,tile_vertices,partitions,frames", [
+    ("kuhn8", 0, 0, (1, 10, 30)), ("kuhn8", 100, 0, (1, 10, 30)), ("kuhn8", 150, 3, (1, 10)),
+    ("icosphere001", 200, 0, (1, 10, 30)), ("kuhn12", 300, 5, (1, 10)), ("default", 0, 0, (1, 4)),
+    ("default", 700, 0, (1, 4)), ("bunny", 64, 2, (1, 20)), ("kuhn20", 0, 0, (1, 5)),
+])
+def test_p1_tile_riding_order_bit_exact_vs_sequence_oracle(mesh, tile_vertices, partitions, frames, flags, capi, po, meshgen, golden):
+    """PBD_ORDER_RIDING: edges ride on a tet of the same tile visit (the tet's thread projects them right
+    after the tet).  Still one projection of every constraint per iteration: the pinned C port replays
+    the disclosed sequence constraint by constraint; positions, velocities, xStar and lambdas BIT-EXACT.
+    flags = 4: the same with the tagged hand-over."""
+    x0, edges, tets = _mesh(mesh, meshgen, golden)
+    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_RIDING, tile_vertices=tile_vertices,
+                       partitions=partitions, flags=flags)
+    body = capi.Body(capi.SolverParams.default(substeps=5), x0, edges, tets, device=0, options=opt)
+    ora = po.Oracle(po.Params.default(substeps=5), x0, edges, tets, kind="port")
+    ora.permute_constraints(*body.schedule_order())
+    seq = body.schedule_sequence()
+    assert np.array_equal(np.sort(seq), np.concatenate([np.arange(body.E, dtype=np.uint32),
+                                                        np.arange(body.T, dtype=np.uint32) | np.uint32(0x80000000)]))
+    done = 0
+    for fr in frames:
+        for _ in range(fr - done):
+            body.step(1.0 / 60.0)
+            ora.step_sequence(1.0 / 60.0, seq)
+        done = fr
+        _assert_state_equal(capi, po, body, ora, f"{mesh}/riding tv={tile_vertices} K={partitions} flags={flags} frame {fr}")
+    body.close()
+
+
+@pytest.mark.parametrize("mesh", ["icosphere", "bunny", "icosphere001", "default", "kuhn6", "kuhn12"])
+def test_riding_fast_arith_within_tolerance(mesh, capi, po, meshgen, golden):
+    """The mode bench.py reports as `value`: PBD_ORDER_RIDING + PBD_FLAG_FAST_ARITH.  (a) vs the exact
+    arithmetic on the same schedule after one frame: relative RMS <= 2e-6; (b) P2 vs the reference in its
+    original order after 10 frames: <= 1e-4."""
+    x0, edges, tets = _mesh(mesh, meshgen, golden)
+    diag = np.linalg.norm(x0.max(0) - x0.min(0))
+    prm = capi.SolverParams.default(substeps=10)
+    mk = lambda fl: capi.Body(prm, x0, edges, tets, device=0,
+                              options=capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_RIDING, flags=fl))
+    rms = lambda a, b: np.sqrt(np.mean(np.sum((a.astype(np.float64) - b) ** 2, 1))) / diag
+    with mk(capi.FLAG_FAST_ARITH) as fast, mk(0) as exact:
+        fast.step(1 / 60)
+        exact.step(1 / 60)
+        d1 = rms(fast.read_positions(), exact.read_positions())
+        assert d1 <= 2e-6, f"{mesh}: fast vs exact after 1 frame: rel RMS {d1:.3e}"
+        fast.step_async(1 / 60, 9)
+        fast.sync()
+        exact.step_async(1 / 60, 9)
+        exact.sync()
+        ref10 = exact.read_positions() if mesh == "kuhn12" else golden(f"ref_{mesh}.npz")["pos_10"]
+        for name, b in (("fast", fast), ("exact", exact)):
+            d10 = rms(b.read_positions(), ref10)
+            assert d10 <= 1e-4, f"{mesh}/{name}: rel RMS after 10 frames {d10:.3e}"

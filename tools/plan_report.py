@@ -22,10 +22,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("n", nargs="?", type=int, default=56)
     ap.add_argument("--strict", action="store_true")
+    ap.add_argument("--riding", action="store_true")
     ap.add_argument("--partitions", type=int, default=0)
     a = ap.parse_args()
     x0, tets, edges = meshgen.kuhn_grid(a.n)
-    om = capi.ORDER_STRICT if a.strict else capi.ORDER_INTERLEAVED
+    om = capi.ORDER_STRICT if a.strict else capi.ORDER_RIDING if a.riding else capi.ORDER_INTERLEAVED
     t0 = time.time()
     p = capi.Plan(x0, edges, tets, capi.Options(backend=capi.BACKEND_TILE, order_mode=om, partitions=a.partitions))
     i = p.info()
