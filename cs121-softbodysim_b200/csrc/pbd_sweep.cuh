@@ -69,7 +69,13 @@ PBD_DEV void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1
 PBD_DEV void sts_v4(uint32_t a, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-PBD_DEV uint32_t smem_window(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// (the volatile move keeps the window address in a register: the compiler otherwise rematerialises
+// it -- S2UR SR_CgaCtaId + ULEA -- inside every colour step)
+PBD_DEV uint32_t smem_window(const void* p) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+  return r;
+}
 
 // one edge / one tet whose record sits at the given shared addresses; sv = address of the tile's vertex 0
 template <bool FAST>

@@ -59,7 +59,8 @@ constexpr uint32_t kMaxRanks = 8;     // GPUs one body can be spread over (one n
 
 struct TileParams {
   float4* pos;
-  ulonglong2* posT;             // tagged hand-over (experimental): 2 x {value|tag<<32, value|tag<<32} per vertex, else null
+  uint4* posT;                  // tagged hand-over: {x, y, z, tag} per vertex (one 128-bit word), else null
+  const float* invMass;         // ... and the inverse masses (static), slot order
   float4* prev;
   float4* vel;
   const unsigned char* blob;
@@ -127,49 +128,40 @@ __device__ __forceinline__ void grid_barrier(const TileParams& P, unsigned* coun
   __syncthreads();
 }
 
-// ---- tagged hand-over (EXPERIMENTAL, PBD_FLAG_TAGGED_HANDOVER) ----------------------
-// A position is four 64-bit {value, tag} pairs (x, y, z, invMass), read and written as two 128-bit
-// accesses of two b64 elements each.  A 64-bit element is single-copy atomic, so a reader that finds
-// the expected tag in all four pairs holds the values written WITH that tag -- no release fence on the
-// writer, no done flag, no separate poll round trip.  Tags: a tile visit with sequence number
+// ---- tagged hand-over (PBD_FLAG_TAGGED_HANDOVER) ------------------------------------------------
+// A position travels between tiles as ONE 128-bit word {x, y, z, tag}, written and read with scalar
+// 128-bit accesses (st/ld.relaxed.gpu.b128 -> STG/LDG.E.128.STRONG.GPU): a naturally aligned scalar
+// access is a single memory operation, so a reader that finds the expected tag holds the x, y, z
+// written WITH that tag -- no release fence on the writer (MEMBAR.GPU + L1 invalidate, ~1.3 k cycles
+// per tile visit), no done flag, no separate poll round trip.  The inverse mass never changes and
+// lives in its own read-only array (P.invMass, slot order).  Tags: a tile visit with sequence number
 // seq = iteration * nPhases + phase (iterations counted across frames) writes 2*seq + 2 and, every
 // phase covering every vertex exactly once, expects 2*seq (the visit before it); the commit pass at
 // the end of a frame writes 2*seqEnd + 1, which is what the first visit of the next frame expects.
-__device__ __forceinline__ void ld_pairs(const ulonglong2* p, ulonglong2& v) {
-  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+// Tags are compared for equality only, so the 32-bit wrap is harmless.
+__device__ __forceinline__ uint4 ld_tagged(const uint4* p) {
+  unsigned __int128 v;
+  asm volatile("ld.relaxed.gpu.global.b128 %0, [%1];" : "=q"(v) : "l"(p) : "memory");
+  return make_uint4((uint32_t)v, (uint32_t)(v >> 32), (uint32_t)(v >> 64), (uint32_t)(v >> 96));
 }
-__device__ __forceinline__ void st_pairs(ulonglong2* p, ulonglong2 v) {
-  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+__device__ __forceinline__ void st_tagged(uint4* p, float4 q, uint32_t tag) {
+  const unsigned __int128 v = (unsigned __int128)__float_as_uint(q.x) | ((unsigned __int128)__float_as_uint(q.y) << 32) |
+                              ((unsigned __int128)__float_as_uint(q.z) << 64) | ((unsigned __int128)tag << 96);
+  asm volatile("st.relaxed.gpu.global.b128 [%0], %1;" ::"l"(p), "q"(v) : "memory");
 }
-__device__ __forceinline__ bool tagged_unpack(ulonglong2 a, ulonglong2 b, uint32_t expect, float4& out) {
-  out = make_float4(__uint_as_float((uint32_t)a.x), __uint_as_float((uint32_t)a.y), __uint_as_float((uint32_t)b.x),
-                    __uint_as_float((uint32_t)b.y));
-  return (uint32_t)(a.x >> 32) == expect && (uint32_t)(a.y >> 32) == expect && (uint32_t)(b.x >> 32) == expect &&
-         (uint32_t)(b.y >> 32) == expect;
+__device__ __forceinline__ float4 tagged_value(uint4 r, float w) {
+  return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), w);
 }
-__device__ __forceinline__ float4 tagged_wait_load(const TileParams& P, uint32_t s, uint32_t expect) {
-  float4 out;
-  ulonglong2 a, b;
+__device__ __forceinline__ float4 tagged_wait_load(const TileParams& P, uint32_t s, uint32_t expect, float w) {
   SpinGuard g;
-  do {
-    ld_pairs(P.posT + 2 * (size_t)s, a);
-    ld_pairs(P.posT + 2 * (size_t)s + 1, b);
-  } while (!tagged_unpack(a, b, expect, out) && !spin_expired(g, P));
-  return out;
+  uint4 r;
+  do { r = ld_tagged(P.posT + s); } while (r.w != expect && !spin_expired(g, P));
+  return tagged_value(r, w);
 }
-__device__ __forceinline__ float4 tagged_load_any(const ulonglong2* posT, uint32_t s) {   // own earlier write: no wait
-  float4 out;
-  ulonglong2 a, b;
-  ld_pairs(posT + 2 * (size_t)s, a);
-  ld_pairs(posT + 2 * (size_t)s + 1, b);
-  tagged_unpack(a, b, 0u, out);
-  return out;
+__device__ __forceinline__ float4 tagged_load_any(const TileParams& P, uint32_t s) {   // own earlier write: no wait
+  return tagged_value(ld_tagged(P.posT + s), __ldg(P.invMass + s));
 }
-__device__ __forceinline__ void tagged_store(ulonglong2* posT, uint32_t s, float4 p, uint32_t tag) {
-  const unsigned long long t = (unsigned long long)tag << 32;
-  st_pairs(posT + 2 * (size_t)s, make_ulonglong2(t | __float_as_uint(p.x), t | __float_as_uint(p.y)));
-  st_pairs(posT + 2 * (size_t)s + 1, make_ulonglong2(t | __float_as_uint(p.z), t | __float_as_uint(p.w)));
-}
+__device__ __forceinline__ void tagged_store(uint4* posT, uint32_t s, float4 p, uint32_t tag) { st_tagged(posT + s, p, tag); }
 
 // vertex-only pass over the phase-0 partition (no constraints): used when there is nothing to
 // sweep and for the final commit.  finalCommit: ground (if clamp) + commit, no predict.
@@ -184,7 +176,7 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
     for (uint32_t s = b + threadIdx.x; s < e; s += blockDim.x) {
       if (finalCommit) {
         float4 p, x = __ldcg(P.prev + s), v;
-        if (TAGGED) p = waitTag ? tagged_wait_load(P, s, waitTag) : tagged_load_any(P.posT, s);
+        if (TAGGED) p = waitTag ? tagged_wait_load(P, s, waitTag, __ldg(P.invMass + s)) : tagged_load_any(P, s);
         else p = __ldcg(P.pos + s);
         if (clamp) ground_vertex(p, k);
         commit_vertex(p, x, v, k);
@@ -194,7 +186,7 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
         if (TAGGED) tagged_store(P.posT, s, p, writeTag); else __stcg(P.pos + s, p);
       } else if (TAGGED) {
         VertexIn in;
-        in.p = tagged_load_any(P.posT, s);
+        in.p = tagged_load_any(P, s);
         in.x = in.v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (mode == LOAD_PREDICT || mode == LOAD_COMMIT_PREDICT) in.x = __ldcg(P.prev + s);
         if (mode == LOAD_PREDICT) in.v = __ldcg(P.vel + s);
@@ -346,7 +338,8 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             // the vertices whose tag is not there yet
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
             for (uint32_t base = 0; base < h.vertCount; base += 3u * nth) {
-              ulonglong2 ta[3], tb[3];
+              uint4 raw[3];
+              float w[3];
               VertexIn in[3];
               uint32_t slot[3];
 #pragma unroll
@@ -354,8 +347,8 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
                 const uint32_t i = base + u * nth + tid;
                 if (i < h.vertCount) {
                   slot[u] = contiguous ? h.vertBegin + i : (vidx[i] & 0x0fffffffu);
-                  ld_pairs(P.posT + 2 * (size_t)slot[u], ta[u]);
-                  ld_pairs(P.posT + 2 * (size_t)slot[u] + 1, tb[u]);
+                  raw[u] = ld_tagged(P.posT + slot[u]);
+                  w[u] = __ldg(P.invMass + slot[u]);
                   in[u].x = in[u].v = make_float4(0.f, 0.f, 0.f, 0.f);
                   if (mode == LOAD_PREDICT || mode == LOAD_COMMIT_PREDICT) in[u].x = __ldcg(P.prev + slot[u]);
                   if (mode == LOAD_PREDICT) in[u].v = __ldcg(P.vel + slot[u]);
@@ -365,7 +358,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
               for (int u = 0; u < 3; ++u) {
                 const uint32_t i = base + u * nth + tid;
                 if (i < h.vertCount) {
-                  if (!tagged_unpack(ta[u], tb[u], expectTag, in[u].p)) in[u].p = tagged_wait_load(P, slot[u], expectTag);
+                  in[u].p = raw[u].w == expectTag ? tagged_value(raw[u], w[u]) : tagged_wait_load(P, slot[u], expectTag, w[u]);
                   sv[i] = finish_vertex(P, k, slot[u], mode, true, in[u]);   // (mode != LOAD_PLAIN only on contiguous home tiles)
                 }
               }
@@ -490,14 +483,14 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   vertex_pass<false>(P, k, LOAD_PLAIN, clamp, true);
 }
 
-// float4 positions <-> tagged pairs (upload / host reads only)
-__global__ void to_tagged_kernel(const float4* pos, ulonglong2* posT, uint32_t n, uint32_t tag) {
+// float4 positions <-> tagged words (upload / host reads only)
+__global__ void to_tagged_kernel(const float4* pos, uint4* posT, float* invMass, uint32_t n, uint32_t tag) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) tagged_store(posT, i, pos[i], tag);
+  if (i < n) { const float4 p = pos[i]; st_tagged(posT + i, p, tag); invMass[i] = p.w; }
 }
-__global__ void from_tagged_kernel(const ulonglong2* posT, float4* pos, uint32_t n) {
+__global__ void from_tagged_kernel(const uint4* posT, float4* pos, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) pos[i] = tagged_load_any(posT, i);
+  if (i < n) pos[i] = tagged_value(ld_tagged(posT + i), pos[i].w);   // pos keeps the inverse mass it was uploaded with
 }
 
 class TileBackend final : public Backend {
@@ -507,7 +500,7 @@ class TileBackend final : public Backend {
     for (void* q : ipcOpened_) cudaIpcCloseMemHandle(q);
     cudaFree(done_); cudaFree(tileList_); cudaFree(homeList_);
     cudaFree(blob_); cudaFree(copies_); cudaFree(phases_); cudaFree(tile0Begin_); cudaFree(barrier_);
-    cudaFree(trace_); cudaFree(ftrace_); cudaFree(posT_);
+    cudaFree(trace_); cudaFree(ftrace_); cudaFree(posT_); cudaFree(invMass_);
     if (abortHost_) cudaFreeHost(abortHost_);
   }
   const char* name() const override {
@@ -828,9 +821,10 @@ class TileBackend final : public Backend {
       tagged_ = full;
     }
     if (tagged_) {
-      if ((err = cudaMalloc((void**)&posT_, sizeof(ulonglong2) * 2 * ((size_t)plan.V + 1))) != cudaSuccess) return err;
-      bytes_ += sizeof(ulonglong2) * 2 * (size_t)plan.V;
-      to_tagged_kernel<<<(plan.V + 255) / 256, 256>>>(d.pos, posT_, plan.V, 2u * (iterBase_ * nPhases_) + 1u);   // the frame-start tag
+      if ((err = cudaMalloc((void**)&posT_, sizeof(uint4) * ((size_t)plan.V + 1))) != cudaSuccess) return err;
+      if ((err = cudaMalloc((void**)&invMass_, sizeof(float) * ((size_t)plan.V + 1))) != cudaSuccess) return err;
+      bytes_ += (sizeof(uint4) + sizeof(float)) * (size_t)plan.V;
+      to_tagged_kernel<<<(plan.V + 255) / 256, 256>>>(d.pos, posT_, invMass_, plan.V, 2u * (iterBase_ * nPhases_) + 1u);   // the frame-start tag
       if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
 
@@ -852,7 +846,7 @@ class TileBackend final : public Backend {
 
   cudaError_t enqueue_frame(const DeviceArrays& d, const FrameShape& f, cudaStream_t s) override {
     TileParams P{};
-    P.pos = d.pos; P.posT = tagged_ ? posT_ : nullptr; P.prev = d.prev; P.vel = d.vel;
+    P.pos = d.pos; P.posT = tagged_ ? posT_ : nullptr; P.invMass = invMass_; P.prev = d.prev; P.vel = d.vel;
     P.blob = blob_; P.copies = copies_; P.edgeLam = d.edgeLam; P.tetLam = d.tetLam;
     P.phases = phases_; P.tile0Begin = tile0Begin_; P.consts = d.consts; P.barrier = barrier_;
     P.trace = trace_; P.ftrace = ftrace_;
@@ -979,7 +973,8 @@ class TileBackend final : public Backend {
   }
   pbd_options opts_;
   int device_;
-  ulonglong2* posT_ = nullptr;   // tagged hand-over: positions as {value, tag} pairs
+  uint4* posT_ = nullptr;        // tagged hand-over: positions as {x, y, z, tag} words
+  float* invMass_ = nullptr;     // ... and the inverse masses
   unsigned* abortHost_ = nullptr;      // mapped host word + its device alias
   unsigned* abortHostDev_ = nullptr;
   long long spinLimit_ = 0;

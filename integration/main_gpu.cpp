@@ -23,6 +23,7 @@ int main(int argc, char** argv) {
     else if (a == "--help" || a == "-h") { std::printf("Usage: %s --port 7777 [--mode gpu] [--device N] [--order strict|interleaved] [--fast]\n", argv[0]); return 0; }
     else { std::fprintf(stderr, "Unknown arg: %s\n", a.c_str()); return 1; }
   }
+  std::setvbuf(stdout, nullptr, _IOLBF, 0);   // the reference printf()s without flushing: keep a piped log line-by-line
   sockets_init();
   CudaStepper gpu(device, &opts);
   Shared sh;

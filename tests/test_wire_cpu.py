@@ -12,11 +12,23 @@ import numpy as np
 import pytest
 
 
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
 class Server:
+    """pbd_server (asks the OS for a port with --port 0 and prints it) or, with `exe`, the reference's
+    server loop, which prints the port it was GIVEN (Net.cpp:88): that one gets a port chosen here."""
+
     def __init__(self, pkg, *extra, exe=None):
         pkg.build.build()
+        port = "0" if exe is None else str(_free_port())
         exe = exe or pkg.build.SERVER
-        self.proc = subprocess.Popen([exe, "--port", "0", *extra], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        self.proc = subprocess.Popen([exe, "--port", port, *extra], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         self.port = None
         self.lines = []
         t0 = time.time()
