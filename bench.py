@@ -67,15 +67,23 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload: str, backend: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the frame kernel, from the committed
-    `ncu --set full` capture of this workload (profiles/traffic.json); None if never captured."""
+def ncu_profile(workload: str, backend: str) -> dict:
+    """Per-launch figures of the frame kernel from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json: dram_bytes = dram__bytes_read.sum + dram__bytes_write.sum, warp_instructions =
+    smsp__inst_executed.sum, smem_wavefronts = l1tex__data_pipe_lsu_wavefronts_mem_shared.sum); {} if never captured."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(f"{workload}:{backend}")
+            v = json.load(f).get(f"{workload}:{backend}")
     except Exception:
-        return None
+        return {}
+    if v is None:
+        return {}
+    return v if isinstance(v, dict) else {"dram_bytes": v}
+
+
+def ncu_traffic(workload: str, backend: str):
+    return ncu_profile(workload, backend).get("dram_bytes")
 
 
 def make_workload(name, mg):
@@ -195,32 +203,56 @@ def run_reference_arm(args):
     return 0
 
 
-def run_batch(args):
+def run_batch(args, ctx=None, emit_line=True):
     """--workload batch4096 (BASELINE configs[3]): 4096 independent 6k-tet bodies, sharded across the
-    ranks (bodies b with b % world == rank), one kernel per frame per GPU, no collective on the data
-    path.  Total work is fixed -> "scaling": "strong".  A substep here = one substep of ALL bodies."""
-    import numpy as np
-    import torch
+    ranks (contiguous body ranges), one kernel per frame per GPU, no collective on the data
+    path.  Total work is fixed -> "scaling": "strong".  A substep here = one substep of ALL bodies.
+    `value` = fast arithmetic, the bit-exact mode under `alt` (--arith).  With `ctx` (called from main for
+    the N > 1 sub-record) the process group of the caller is used and the line is returned, not printed."""
+    if ctx is None:
+        import numpy as np
+        import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import __graft_entry__ as ge
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(local)
+        dist = None
+        if world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import __graft_entry__ as ge
+        if rank == 0:
+            ge.build()
+        if dist:
+            dist.barrier()
+        pkg = ge.package()
+    else:
+        np, torch, dist, rank, world, local, pkg = (ctx[k] for k in ("np", "torch", "dist", "rank", "world", "local", "pkg"))
+    arith = ["fast", "exact"] if args.arith == "both" else [args.arith]
+    lines = [_run_batch_mode(args, np, torch, dist, rank, world, local, pkg, m, cpu_baseline=(i == 0 and ctx is None))
+             for i, m in enumerate(arith)]
+    line = lines[0]
     if rank == 0:
-        ge.build()
-    if dist:
-        dist.barrier()
-    pkg = ge.package()
+        line["config"]["arithmetic"] = ARITH_DOC[arith[0]]
+        if len(lines) > 1:
+            o = lines[1]
+            line["alt"] = {arith[1]: {"value": o["value"], "unit": o["unit"], "ms_per_step": o["ms_per_step"],
+                                      "roofline_frac": o["roofline"]["frac"], "e2e": o["e2e"]["value"],
+                                      "arithmetic": ARITH_DOC[arith[1]], "sane": o["sane"]}}
+        if emit_line:
+            emit(line)
+    if dist and ctx is None:
+        dist.destroy_process_group()
+    return line if ctx is not None else 0
+
+
+def _run_batch_mode(args, np, torch, dist, rank, world, local, pkg, mode, cpu_baseline):
     capi, mg = pkg.capi, pkg.meshgen
-    w = WORKLOADS[args.workload]
+    w = WORKLOADS["batch4096"]
     nb, S, I = w["bodies"], w["substeps"], w["iterations"]
     local_xyz, tets, edges = mg.kuhn_grid(w["kuhn"], rot=np.eye(3), lowest_y=None)
     mine = pkg.shard.body_slice(nb, world, rank)
@@ -230,7 +262,8 @@ def run_batch(args):
         bodies.append((mg.place_body(local_xyz, rot=rot, lowest_y=0.25 + 0.001 * (b % 13)), edges, tets))
     V, E, T = len(local_xyz), len(edges), len(tets)
     t0 = time.perf_counter()
-    batch = capi.Batch(capi.SolverParams.default(substeps=S, iterations=I), bodies, device=local)
+    bopt = capi.Options(flags=capi.FLAG_FAST_ARITH if mode == "fast" else 0, lanes_per_tet=args.lanes)
+    batch = capi.Batch(capi.SolverParams.default(substeps=S, iterations=I), bodies, device=local, options=bopt)
     init_ms = (time.perf_counter() - t0) * 1e3
     info = batch.info()
     host_pos = torch.empty(3 * V * len(mine), dtype=torch.float32).pin_memory()
@@ -241,6 +274,9 @@ def run_batch(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if args.preroll:                                  # untimed: past free fall and first contact
+        batch.step_async(DT, args.preroll)
+        batch.sync()
     for _ in range(args.warmup):
         batch.step_async(DT, 1)
         batch.sync()
@@ -263,26 +299,28 @@ def run_batch(args):
     assert sum(pkg.shard.gather_counts(len(mine), dist, "cuda")) == nb
     pos = host_pos.numpy().reshape(-1, 3)
     sane = bool(np.isfinite(pos).all() and pos[:, 1].min() >= -1e-5)
+    batch.close()
     if rank != 0:
-        if dist:
-            dist.destroy_process_group()
-        return 0
+        return None
     frame_ms = total_ms / args.steps
     value = args.steps * S / (total_ms * 1e-3)                      # substeps of the WHOLE batch per second
     bytes_sub = nb * (104 * V + I * (20 * E + 28 * T + 84 * V))
     achieved = bytes_sub * S / (frame_ms * 1e-3) / 1e9
     peak, peak_src = load_peaks()
+    name = "b200-batch-fast" if mode == "fast" else "b200-batch"
     line = {
         "metric": METRIC, "value": value, "unit": "batch-" + UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "bodies": nb, "bodies_per_gpu": len(mine), "V": V, "E": E, "T": T,
-                   "substeps_per_frame": S, "iterations": I, "dt": DT, "backend": "b200-batch",
+                   "substeps_per_frame": S, "iterations": I, "dt": DT, "backend": name,
                    "order_mode": "strict", "parallelism": f"{world} GPU(s), bodies sharded, no collective",
+                   "preroll_frames": args.preroll,
                    "l2": "not flushed: per-GPU working set %.2f GB >> L2" % (info["device_bytes"] / 1e9)},
         "body_substeps_per_s": value * nb, "tet_constraints_per_s": value * nb * T * I,
+        "frame_ms": {"min": min(dev_ms), "median": statistics.median(dev_ms), "max": max(dev_ms), "n": len(dev_ms)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
-                     "frac": achieved / (peak * world), "traffic": ncu_traffic(args.workload, "b200-batch"),
+                     "frac": achieved / (peak * world), "traffic": ncu_traffic("batch4096", name),
                      "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
                      "kernel": "batch_frame_kernel, 1 launch per frame per GPU",
                      "algorithmic_bytes_per_substep": bytes_sub},
@@ -290,20 +328,16 @@ def run_batch(args):
                 "d2h_bytes_per_step": 12 * V * len(mine), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "pbd_batch_step + pbd_batch_read_positions -> pinned host buffer"},
         "gpu_launches": args.steps * world, "clocks": clocks, "init_ms": init_ms, "plan_ms": info["plan_ms"],
-        "schedule": {k: info[k] for k in ("edge_colors", "tet_colors", "tiles", "grid_blocks", "block_threads")},
+        "schedule": {k: info[k] for k in ("edge_colors", "tet_colors", "tiles", "grid_blocks", "block_threads", "lanes_per_tet")},
         "sane": sane,
     }
-    if not args.no_cpu_baseline and world == 1:
+    if cpu_baseline and not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(bodies[0][0], edges, tets, w, S, 8, 1, threads=0)   # 8 frames of ONE body
         per_body = r["substeps"] / r["seconds"]
         line["cpu_baseline"] = {"value": per_body / nb, "unit": "batch-" + UNIT, "cores": 1, "kind": r["kind"],
                                 "sample": f"8 frames x {S} substeps of ONE body on 1 of {os.cpu_count()} host cores "
                                           f"({per_body:.1f} body-substeps/s), divided by {nb} bodies"}
-    emit(line)
-    if dist:
-        dist.destroy_process_group()
-    batch.close()
-    return 0
+    return line
 
 
 _JSON_FD = None
@@ -350,16 +384,24 @@ def main():
     ap.add_argument("--shard", action="store_true",
                     help="with --gpus N > 1: ONE body of the workload spread over the N GPUs (tiles of other ranks' "
                          "vertices are read/written in place over NVLink; strong scaling) instead of one body per GPU")
-    ap.add_argument("--fast", action="store_true",
-                    help="PBD_FLAG_FAST_ARITH: FFMA / SFU forms of the projections (tolerance-validated, not bit-exact)")
-    ap.add_argument("--tagged", action="store_true",
-                    help="PBD_FLAG_TAGGED_HANDOVER: positions travel between tiles as {value, tag} pairs")
+    ap.add_argument("--fast", action="store_true", help="shorthand for --arith fast")
+    ap.add_argument("--tagged", action="store_true", help="(default now; kept for older scripts)")
+    ap.add_argument("--arith", default="both", choices=["both", "fast", "exact"],
+                    help="both (default): `value` = fast arithmetic (tolerance-validated), the bit-exact mode under `alt`")
+    ap.add_argument("--no-tagged", action="store_true", help="release/acquire done counters instead of the tagged hand-over")
+    ap.add_argument("--preroll", type=int, default=30, help="untimed frames before warm-up (past first ground contact)")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-splits", action="store_true", help="N > 1: skip the batch4096 / sharded-body sub-records")
+    ap.add_argument("--split-body", default="big8m", choices=["big8m", "big32m"],
+                    help="N > 1: the body of the sharded sub-record (big32m = BASELINE configs[4]; planning it takes minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
     args = ap.parse_args()
     if args.backend == "stream":
         args.order = "strict"          # the per-colour stream backend only has the reference's edges-then-tets order
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.fast:
+        args.arith = "fast"
 
     if args.workload == "batch4096" and args.impl != "reference":
         return run_batch(args)
@@ -387,21 +429,74 @@ def main():
     if dist:
         dist.barrier()
     pkg = ge.package()
-    capi, mg = pkg.capi, pkg.meshgen
+    ctx = dict(np=np, torch=torch, dist=dist, rank=rank, world=world, local=local, pkg=pkg)
 
-    x0, edges, tets, w = make_workload(args.workload, mg)
+    sharded = args.shard and world > 1
+    arith = ["fast", "exact"] if args.arith == "both" else [args.arith]
+    if args.backend == "stream" or sharded:
+        arith = ["exact"] if args.arith == "both" else arith[:1]     # stream backend / sharded body: one mode
+    results = {}
+    for mode in arith:
+        results[mode] = measure_body(ctx, args, args.workload, mode, sharded, cpu_baseline=(mode == arith[0]))
+    line = None
+    if rank == 0:
+        line = results[arith[0]]
+        line["config"]["arithmetic"] = ARITH_DOC[arith[0]]
+        if len(arith) > 1:
+            o = results[arith[1]]
+            line["alt"] = {arith[1]: {"value": o["value"], "unit": o["unit"], "ms_per_step": o["ms_per_step"],
+                                      "roofline_frac": o["roofline"]["frac"], "e2e": o["e2e"]["value"], "backend": o["config"]["backend"],
+                                      "frame_ms": o["frame_ms"], "arithmetic": ARITH_DOC[arith[1]], "sane": o["sane"]}}
+    # ---- the two splits BASELINE.json's north_star names, measured in the same launch when N > 1
+    if world > 1 and not sharded and args.workload == "headline" and not args.no_splits:
+        sub = {}
+        try:
+            sub["batch4096"] = run_batch(args, ctx=ctx, emit_line=False)
+        except Exception as e:                                        # a sub-record must never take the headline line down
+            sub["batch4096"] = {"error": repr(e)}
+        try:
+            sub[args.split_body] = measure_body(ctx, args, args.split_body, "fast" if args.arith != "exact" else "exact", True,
+                                                cpu_baseline=False, steps=max(3, args.steps // 2), sustained=False, check_small=True)
+        except Exception as e:
+            sub[args.split_body] = {"error": repr(e)}
+        if rank == 0:
+            line["splits"] = sub
+    if rank == 0:
+        emit(line)
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+ARITH_DOC = {
+    "fast": "PBD_FLAG_FAST_ARITH: FFMA + SFU rcp/rsqrt forms of the projections, validated by tolerance (P2 <= 1e-4 rel. RMS after 10 "
+            "frames, P3 residuals after 1000 frames; tests/test_parity_gpu.py::test_fast_arith_*), not bit for bit",
+    "exact": "IEEE binary32 without FMA in the reference's evaluation order: BIT-EXACT against the oracle replaying the disclosed order",
+}
+
+
+def measure_body(ctx, args, workload, mode, sharded, cpu_baseline, steps=None, sustained=True, check_small=False):
+    """One body of `workload` per rank (or ONE body across all ranks when `sharded`): device-timed K frames,
+    the end-to-end leg through the stepper API, a sustained sample; returns the JSON line (rank 0) or None."""
+    np, torch, dist, rank, world, local, pkg = (ctx[k] for k in ("np", "torch", "dist", "rank", "world", "local", "pkg"))
+    capi, mg = pkg.capi, pkg.meshgen
+    steps = steps or args.steps
+    x0, edges, tets, w = make_workload(workload, mg)
     V, E, T = len(x0), len(edges), len(tets)
     S, I = w["substeps"], w["iterations"]
     prm = capi.SolverParams.default(substeps=S, iterations=I)
+    tagged = (not args.no_tagged) and not sharded and args.backend != "stream"
+    flags = (capi.FLAG_FAST_ARITH if mode == "fast" else 0) | (capi.FLAG_TAGGED_HANDOVER if tagged else 0)
     opt = capi.Options(backend={"auto": 0, "stream": 1, "tile": 2}[args.backend],
                        order_mode={"strict": 0, "interleaved": 1, "riding": 2}[args.order],
                        block_threads=args.block_threads, tile_vertices=args.tile_vertices,
-                       lanes_per_tet=args.lanes, partitions=args.partitions, tiles_per_sm=args.tiles_per_sm,
-                       flags=(capi.FLAG_FAST_ARITH if args.fast else 0) | (capi.FLAG_TAGGED_HANDOVER if args.tagged else 0))
+                       lanes_per_tet=args.lanes, partitions=args.partitions, tiles_per_sm=args.tiles_per_sm, flags=flags)
 
     t0 = time.perf_counter()
-    sharded = args.shard and world > 1
+    check = None
     if sharded:
+        if check_small:
+            check = shard_identity_check(ctx, opt)
         sb = capi.ShardedBody(prm, x0, edges, tets, rank, world, dist, device=local, options=opt)
         body, stepper, state = sb.body, None, None
     else:
@@ -420,16 +515,29 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-timed region: K frames, inputs resident in HBM, CUDA events on the launching stream
+    def max_over_ranks(v):
+        if not dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- pre-roll (untimed): past free fall and first contact, so that every timed frame is steady-state
+    # contact (the body starts 0.25 above the ground; the exact arithmetic has a fast path for exactly
+    # satisfied constraints that only free fall takes)
+    if args.preroll:
+        body.step_async(DT, args.preroll)
+        body.sync()
     for _ in range(args.warmup):
         body.step_async(DT, 1)
         body.sync()
+    # ---- device-timed region: K frames, inputs resident in HBM, CUDA events on the launching stream
     sampler = ClockSampler(local)
     sync_all()
     sampler.start()
     dev_ms = []
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         if flush is not None:
             flush.zero_()                            # evict L2 (126 MB) between timed frames; not timed
             torch.cuda.synchronize()
@@ -437,11 +545,7 @@ def main():
         dev_ms.append(body.sync())                   # ms between the library's events around the frame
     wall_ms = (time.perf_counter() - wall0) * 1e3
     sync_all()
-    total_ms = sum(dev_ms)
-    if dist:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = max_over_ranks(sum(dev_ms))
 
     # ---- end-to-end through the stepper API with host buffers (step + pack D2H into pinned memory)
     stats = capi.StepStats()
@@ -458,60 +562,95 @@ def main():
         e2e_step()
     sync_all()
     e0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
-    e2e_s = time.perf_counter() - e0
+    e2e_s = max_over_ranks(time.perf_counter() - e0)
     clocks = sampler.stop()
-    if dist:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    pos = host_pos.numpy().reshape(-1, 3)
-    sane = bool(np.isfinite(pos).all() and pos[:, 1].min() >= -1e-5)
 
+    # ---- sustained sample: >= 2 s of back-to-back frames (no flush, no host work in between), own clocks record
+    sus = None
+    if sustained and not args.no_sustained:
+        per = max(1, int(0.25 / max(1e-4, (total_ms / steps) * 1e-3)))       # ~0.25 s of frames per sync
+        s2 = ClockSampler(local)
+        sync_all()
+        s2.start()
+        ms_sum, frames, t_s = 0.0, 0, time.perf_counter()
+        while time.perf_counter() - t_s < 2.0:
+            body.step_async(DT, per)
+            ms_sum += body.sync()
+            frames += per
+        sus_clk = s2.stop()
+        ms_sum = max_over_ranks(ms_sum)
+        sus = {"seconds": ms_sum * 1e-3, "frames": frames, "ms_per_step": ms_sum / frames,
+               "value": (1 if sharded else world) * frames * S / (ms_sum * 1e-3), "clocks": sus_clk}
+    body.read_positions(out_ptr=host_pos.data_ptr())
+    pos = host_pos.numpy().reshape(-1, 3)
+    if sharded:
+        sane = bool(np.isfinite(pos[sb.owner == rank]).all() and pos[sb.owner == rank][:, 1].min() >= -1e-5)
+    else:
+        sane = bool(np.isfinite(pos).all() and pos[:, 1].min() >= -1e-5)
+    name = body.name()
+    if stepper:
+        stepper.close()
+    else:
+        sb.close()
     if rank != 0:
-        if dist:
-            dist.destroy_process_group()
-        return 0
+        return None
 
     bodies = 1 if sharded else world
-    substeps_total = bodies * args.steps * S
-    value = substeps_total / (total_ms * 1e-3)
+    value = bodies * steps * S / (total_ms * 1e-3)
     bytes_sub = info["algorithmic_bytes_per_substep"]
-    frame_ms = total_ms / args.steps
+    frame_ms = total_ms / steps
     achieved = bodies * bytes_sub * S / (frame_ms * 1e-3) / 1e9
     peak, peak_src = load_peaks()
     peak *= world
+    prof = ncu_profile(workload, name)
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
         "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "V": V, "E": E, "T": T, "substeps_per_frame": S, "iterations": I,
-                   "dt": DT, "backend": body.name(), "order_mode": args.order,
+                   "dt": DT, "backend": name, "order_mode": args.order, "hand_over": "tagged 128-bit {x,y,z,tag} words" if tagged else "release/acquire done counters",
                    "lanes_per_tet": info.get("lanes_per_tet"), "partitions": info.get("partitions"),
                    "parallelism": ("1 GPU" if world == 1 else
                                    f"ONE body across {world} GPUs: tiles read/write other ranks' vertices in place over NVLink "
                                    "(peer memory, CUDA IPC), per-tile release/acquire counters at system scope; no NCCL on the data path"
                                    if sharded else f"{world} independent bodies, one per GPU, no collective"),
                    "l2": "not flushed" if flush is None else "flushed between timed frames (256 MiB memset, untimed)",
-                   "working_set_bytes": info["device_bytes"]},
+                   "preroll_frames": args.preroll, "working_set_bytes": info["device_bytes"]},
         "tet_constraints_per_s": value * T * I,
         "substeps_per_s_per_gpu": value / world,
+        "frame_ms": {"min": min(dev_ms), "median": statistics.median(dev_ms), "max": max(dev_ms), "n": len(dev_ms),
+                     "note": "device ms of every timed frame on this rank (CUDA events on the library's stream)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args.workload, body.name()), "peak_source": peak_src,
-                     "kernel": "whole frame = %d launches of %s" % (info["launches_per_frame"], body.name()),
+                     "traffic": prof.get("dram_bytes"), "peak_source": peak_src,
+                     "kernel": "whole frame = %d launches of %s" % (info["launches_per_frame"], name),
                      "algorithmic_bytes_per_substep": bytes_sub, "frac_of_nominal_8TBs": achieved / 8000.0},
-        "e2e": {"value": bodies * args.steps * S / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 52,
-                "d2h_bytes_per_step": 12 * V, "ms_per_step": 1e3 * e2e_s / args.steps,
+        "e2e": {"value": bodies * steps * S / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 52,
+                "d2h_bytes_per_step": 12 * V, "ms_per_step": 1e3 * e2e_s / steps,
                 "api": "CudaStepper.step(state, dt) + pack_positions -> pinned host buffer (C ABI pbd_step + pbd_read_positions)"},
-        "gpu_launches": args.steps * info["launches_per_frame"],
+        "gpu_launches": steps * info["launches_per_frame"],
         "clocks": clocks,
         "init_ms": init_ms, "plan_ms": info["plan_ms"], "wall_ms_timed_region": wall_ms,
         "schedule": {k: info[k] for k in ("edge_colors", "tet_colors", "edge_phases", "tet_phases", "tiles", "partitions",
                                           "lanes_per_tet", "launches_per_frame", "grid_blocks", "block_threads")},
         "sane": sane,
     }
-    if not args.no_cpu_baseline and world == 1:
+    if prof.get("warp_instructions"):
+        # second roofline: issue slots.  warp-instructions per frame (ncu smsp__inst_executed.sum of the committed capture
+        # of this kernel) / (SMs that run a CTA x 4 schedulers x cycles of the frame at the sampled SM clock)
+        cyc = frame_ms * 1e-3 * sm_mhz * 1e6
+        line["roofline"]["issue_slot_frac"] = prof["warp_instructions"] / (info["grid_blocks"] * 4 * cyc)
+        line["roofline"]["issue_slot_source"] = prof.get("source")
+    if prof.get("smem_wavefronts"):
+        cyc = frame_ms * 1e-3 * sm_mhz * 1e6
+        line["roofline"]["smem_pipe_frac"] = prof["smem_wavefronts"] / (info["grid_blocks"] * cyc)
+    if sus:
+        line["sustained"] = sus
+    if check is not None:
+        line["bit_identity_check"] = check
+    if cpu_baseline and not args.no_cpu_baseline and world == 1:
         sample = 2 if T > 200000 else S
         frames = 3 if T > 200000 else max(1, int(2e8 / max(1, (20 * E + 45 * T) * I * sample)))
         r = cpu_reference_run(x0, edges, tets, w, sample, frames, 1, threads=0)
@@ -520,12 +659,38 @@ def main():
                                 "sample": f"{frames} x {sample} substeps (same mesh, same substep dt) after 1 warm-up; "
                                           f"SerialStepper on 1 of {os.cpu_count()} host cores",
                                 "solve_fraction": r["stats"]["solveMs"] / max(r["stats"]["totalMs"], 1e-9)}
-    emit(line)
+    return line
+
+
+def shard_identity_check(ctx, opt):
+    """Spot check run before a sharded measurement: a small body (Kuhn n=16) stepped 3 frames as ONE body
+    across the ranks must be bit-identical to rank 0's single-GPU run of the same plan (plan_sms)."""
+    np, torch, dist, rank, world, local, pkg = (ctx[k] for k in ("np", "torch", "dist", "rank", "world", "local", "pkg"))
+    capi, mg = pkg.capi, pkg.meshgen
+    import ctypes as C
+    x0, tets, edges = mg.kuhn_grid(16)
+    prm = capi.SolverParams.default(substeps=4)
+    o = capi.Options()
+    C.memmove(C.byref(o), C.byref(opt), C.sizeof(opt))
+    o.tile_vertices, o.plan_sms = 160, 16 * world
+    sb = capi.ShardedBody(prm, x0, edges, tets, rank, world, dist, device=local, options=o)
+    for _ in range(3):
+        sb.step_async(1 / 60)
+        sb.sync()
+    got = sb.read_positions()
+    sb.close()
+    same = None
+    if rank == 0:
+        o1 = capi.Options()
+        C.memmove(C.byref(o1), C.byref(o), C.sizeof(o))
+        o1.shard_world, o1.shard_rank = 0, 0
+        with capi.Body(prm, x0, edges, tets, device=local, options=o1) as b:
+            for _ in range(3):
+                b.step(1 / 60)
+            same = bool(np.array_equal(b.read_positions(), got))
     if dist:
-        dist.destroy_process_group()
-    if stepper:
-        stepper.close()
-    return 0
+        dist.barrier()
+    return {"body": "Kuhn n=16, 3 frames, ONE body across the ranks vs rank 0 alone on the same plan", "bit_identical": same}
 
 
 if __name__ == "__main__":

@@ -70,6 +70,9 @@ __device__ __forceinline__ void bulk_store(void* dstGlobal, const void* srcSmem,
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// ... until at most N of this thread's bulk async-groups are still pending
+template <int N>
+__device__ __forceinline__ void bulk_wait_pending() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (bulk copies)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   uint32_t buf = 0;
   uint32_t parityBits = 0;   // bit b: phase parity of mbar[b]
   bool needWait = true;
+  bool recReady = false;  // tagged path: the previous visit already waited for this visit's record block
   uint32_t j = 0;         // position in itemTile
 
   for (uint32_t sub = 0; sub < P.substeps; ++sub) {
@@ -293,13 +294,14 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
         for (uint32_t t = blockIdx.x; t < pd.tileCount; t += gridDim.x) {
           if (ft) ft[0] = clock64();
           // ---- record block
-          if (needWait) {
+          if (needWait && !recReady) {
             // one thread waits on the mbarrier, the block barrier releases the rest (16 warps
             // polling the same mbarrier serialise: ~45 cycles each)
             if (tid == 0) while (!mbar_try_wait(&mbar[buf], (parityBits >> buf) & 1u)) {}
             __syncthreads();
             parityBits ^= 1u << buf;
           }
+          recReady = false;
           const uint32_t recOff = buf * P.recStride;
           unsigned char* rec = smem + recOff;
           const TileHdr h = *reinterpret_cast<const TileHdr*>(rec);
@@ -312,10 +314,6 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           // ---- prefetch the next tile's block into the other buffer
           const uint32_t jn = (j + 1 == nItems) ? 0u : j + 1;
           const bool hasNext = item + 1 < totalItems;
-          if (tid == 0 && hasNext && nItems > 1) {
-            bulk_wait_all();   // the lambda write-back that last read the other buffer (and its global writes) is complete
-            fetch(jn, buf ^ 1u);
-          }
           // ---- vertices L2 -> shared memory (all of a thread's loads are issued before the first use)
           // ---- point-to-point sync: wait until the tiles that last wrote my vertices have stored them
           if (!TAGGED && P.done) {
@@ -395,6 +393,16 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           }
           __syncthreads();
           if (ft) ft[2] = clock64();
+          // ---- prefetch the next tile's record block into the other buffer.  Issued here, behind the
+          // barrier that ends the vertex load: every thread has finished the PREVIOUS visit's write-back
+          // (which reads that buffer's gathered-slot list) by then, and the lambda write-back that read
+          // it was issued a whole vertex load ago.  Its global writes need to be complete only before the
+          // same tile's lambdas are fetched again, nItems - 1 visits later.
+          if (tid == 0 && hasNext && nItems > 1) {
+            bulk_wait_read();
+            if (nItems >= 4) bulk_wait_pending<2>(); else if (nItems == 3) bulk_wait_pending<1>(); else bulk_wait_all();
+            fetch(jn, buf ^ 1u);
+          }
           // ---- sweeps
           if (stagger) {
             const long long t0 = clock64();
@@ -410,6 +418,32 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           }
           if (ft) ft[4] = clock64();
           // ---- write back
+          if (TAGGED && nItems > 1) {
+            // Tagged hand-over: nothing to publish after the stores, so the visit ends WITHOUT a block
+            // barrier.  One barrier right after the sweeps (a) makes the lambdas visible to the bulk
+            // store and (b) hands every thread the NEXT record block, which thread 0 waits for here --
+            // it was requested a whole sweep ago.  A thread writes back exactly the shared-memory
+            // entries (i = tid mod block size) that it overwrites itself when it loads the next tile.
+            fence_async_smem();
+            if (tid == 0 && hasNext) while (!mbar_try_wait(&mbar[buf ^ 1u], (parityBits >> (buf ^ 1u)) & 1u)) {}
+            __syncthreads();
+            if (hasNext) { parityBits ^= 1u << (buf ^ 1u); recReady = true; }
+            if (ft) ft[11] = ft[12] = ft[13] = clock64();
+            if (tid == 0) {
+              const TileCopy c = j < kItemCopySmem ? itemCopy[j] : P.copies[itemTile[j]];
+              if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
+              if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
+              bulk_commit();
+            }
+            const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
+            for (uint32_t i = tid; i < h.vertCount; i += nth)
+              tagged_store(P.posT, contiguous ? h.vertBegin + i : (vidx[i] & 0x0fffffffu), sv[i], writeTag);
+            buf ^= 1u;
+            j = jn;
+            ++item;
+            if (ft) { ft[5] = clock64(); ft[6] = h.nEdgeGroups; ft[7] = h.nTetGroups; ft[8] = h.vertCount; ft[9] = h.nEdges; ft[10] = h.nTets; }
+            continue;
+          }
           if (TAGGED) {
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
             for (uint32_t i = tid; i < h.vertCount; i += nth)
@@ -935,7 +969,8 @@ class TileBackend final : public Backend {
   cudaError_t shard_attach_pointers(uint32_t r, void* pos, void* done, int peerDevice) override {
     if (r >= world_) return cudaErrorInvalidValue;
     if (r != rank_) {
-      cudaError_t e = cudaDeviceEnablePeerAccess(peerDevice, 0);
+      cudaError_t e = cudaSuccess;
+      if (peerDevice != device_) e = cudaDeviceEnablePeerAccess(peerDevice, 0);   // (two ranks on one device: plain pointers)
       if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
       if (e != cudaSuccess) return e;
       posPeers_[r] = static_cast<float4*>(pos);
