@@ -217,24 +217,79 @@ def test_stepper_mirror_reinit_and_stats(backend, capi, po, meshgen):
     st.close()
 
 
-@pytest.mark.parametrize("backend", BACKENDS)
-def test_full_size_1m_tets_properties_and_one_frame_bit_exact(backend, capi, po, meshgen):
+FULL_SIZE_MODES = [
+    # (id, backend, order, flags)            what bench.py measures is "interleaved-tagged" (alt) and "interleaved-tagged-fast" (value)
+    ("stream", "stream", "strict", 0), ("tile-strict", "tile", "strict", 0), ("tile-interleaved", "tile", "interleaved", 0),
+    ("tile-interleaved-tagged", "tile", "interleaved", 4), ("tile-riding-tagged", "tile", "riding", 4),
+]
+
+
+@pytest.mark.parametrize("mode,backend,order,flags", FULL_SIZE_MODES, ids=[m[0] for m in FULL_SIZE_MODES])
+def test_full_size_1m_tets_properties_and_one_frame_bit_exact(mode, backend, order, flags, capi, po, meshgen):
     """BASELINE config 3 at full size (Kuhn n=56: V=185,193 E=1,257,704 T=1,053,696, 20 substeps x 6
-    iterations).  One frame is checked BIT-EXACT against the C port in the same order (~10 s of CPU);
+    iterations), in every order / hand-over mode -- including exactly the configuration bench.py
+    times (interleaved order, mixed colour steps, 144 tiles x 512 threads, tagged hand-over).  One
+    frame is checked BIT-EXACT against the C port replaying the disclosed sequence (~10 s of CPU);
     then 30 more frames must keep the size-independent invariants: finite, above ground, total volume
     within 1e-3, edge residual RMS small."""
     x0, tets, edges = meshgen.kuhn_grid(56)
     assert (len(x0), len(edges), len(tets)) == (185193, 1257704, 1053696)
-    body = capi.Body(capi.SolverParams.default(substeps=20), x0, edges, tets, device=0, options=_opt(capi, backend))
+    om = {"strict": capi.ORDER_STRICT, "interleaved": capi.ORDER_INTERLEAVED, "riding": capi.ORDER_RIDING}[order]
+    body = capi.Body(capi.SolverParams.default(substeps=20), x0, edges, tets, device=0, options=_opt(capi, backend, order_mode=om, flags=flags))
+    if flags & 4:
+        assert "tagged" in body.name()
     ora = po.Oracle(po.Params.default(substeps=20), x0, edges, tets, kind="port")
     ora.permute_constraints(*body.schedule_order())
+    seq = body.schedule_sequence()
     body.step(1 / 60)
-    ora.step(1 / 60)
+    ora.step_sequence(1 / 60, seq)
     assert np.array_equal(body.read_positions(), ora.positions())
+    assert np.array_equal(body.get_array(capi.ARRAY_VELOCITY), ora.get(po.GET_V))
     body.step_async(1 / 60, 30)
     body.sync()
     r = po.residuals(body.read_positions(), x0, edges, tets)
     assert r["finite"] and r["min_y_dynamic"] >= -1e-6 and r["vol_rel"] < 1e-3 and r["edge_rms"] < 1e-3, r
+    body.close()
+
+
+def test_full_size_1m_tets_fast_arith_vs_exact(capi, po, meshgen):
+    """The `value` configuration of bench.py (fast arithmetic, tagged hand-over, interleaved order) at full
+    size against the bit-exact mode on the SAME schedule: relative RMS <= 2e-6 after one frame (20 substeps),
+    <= 1e-4 after 10 frames, and the same invariants after 30 frames."""
+    x0, tets, edges = meshgen.kuhn_grid(56)
+    diag = np.linalg.norm(x0.max(0) - x0.min(0))
+    mk = lambda fl: capi.Body(capi.SolverParams.default(substeps=20), x0, edges, tets, device=0,
+                              options=capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_INTERLEAVED, flags=fl))
+    rms = lambda a, b: np.sqrt(np.mean(np.sum((a.astype(np.float64) - b) ** 2, 1))) / diag
+    with mk(12) as fast, mk(4) as exact:
+        for frames, tol in ((1, 2e-6), (10, 1e-4)):
+            n = frames - (0 if frames == 1 else 1)
+            fast.step_async(1 / 60, n); fast.sync()
+            exact.step_async(1 / 60, n); exact.sync()
+            d = rms(fast.read_positions(), exact.read_positions())
+            assert d <= tol, f"fast vs exact after {frames} frames: rel RMS {d:.3e}"
+        fast.step_async(1 / 60, 20)
+        fast.sync()
+        r = po.residuals(fast.read_positions(), x0, edges, tets)
+        assert r["finite"] and r["min_y_dynamic"] >= -1e-6 and r["vol_rel"] < 1e-3 and r["edge_rms"] < 1e-3, r
+
+
+@pytest.mark.parametrize("order,flags", [("strict", 0), ("interleaved", 4), ("riding", 4)])
+def test_p1_config2_kuhn26_bit_exact(order, flags, capi, po, meshgen):
+    """BASELINE config 2 (100k-tet cube, Kuhn n=26: V=19,683 E=129,194 T=105,456, 10 substeps x 6 iterations,
+    ground plane) at its own size: 5 frames bit-exact against the port replaying the disclosed sequence."""
+    x0, tets, edges = meshgen.kuhn_grid(26)
+    assert (len(x0), len(edges), len(tets)) == (19683, 129194, 105456)
+    om = {"strict": capi.ORDER_STRICT, "interleaved": capi.ORDER_INTERLEAVED, "riding": capi.ORDER_RIDING}[order]
+    body = capi.Body(capi.SolverParams.default(substeps=10), x0, edges, tets, device=0,
+                     options=capi.Options(backend=capi.BACKEND_TILE, order_mode=om, flags=flags))
+    ora = po.Oracle(po.Params.default(substeps=10), x0, edges, tets, kind="port")
+    ora.permute_constraints(*body.schedule_order())
+    seq = body.schedule_sequence()
+    for fr in range(5):
+        body.step(1 / 60)
+        ora.step_sequence(1 / 60, seq)
+    _assert_state_equal(capi, po, body, ora, f"kuhn26/{order}/flags={flags} frame 5")
     body.close()
 
 
@@ -594,3 +649,46 @@ def test_riding_fast_arith_within_tolerance(mesh, capi, po, meshgen, golden):
         for name, b in (("fast", fast), ("exact", exact)):
             d10 = rms(b.read_positions(), ref10)
             assert d10 <= 1e-4, f"{mesh}/{name}: rel RMS after 10 frames {d10:.3e}"
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_batch_config4_bodies_bit_exact(lanes, capi, po, meshgen):
+    """BASELINE config 4's body (Kuhn n=10: V=1,331 E=7,930 T=6,000, 16 edge + 27 tet colour steps per
+    iteration) with bench.py's per-body rotations and drop heights: 320 bodies (more than two waves of
+    CTAs), 10 substeps x 6 iterations, 3 frames; a sample of bodies BIT-EXACT against the reference run
+    on that body alone in the disclosed per-body order."""
+    local_xyz, tets, edges = meshgen.kuhn_grid(10, rot=np.eye(3), lowest_y=None)
+    nb = 320
+    bodies = [(meshgen.place_body(local_xyz, rot=meshgen.rotation_zx(7.0 * (b % 47), 3.0 * (b % 29)), lowest_y=0.25 + 0.001 * (b % 13)),
+               edges, tets) for b in range(nb)]
+    prm = dict(substeps=10, iterations=6)
+    with capi.Batch(capi.SolverParams.default(**prm), bodies, device=0, options=capi.Options(lanes_per_tet=lanes)) as batch:
+        info = batch.info()
+        assert info["tiles"] == nb and info["lanes_per_tet"] == lanes
+        batch.step_async(1 / 60, 3)
+        batch.sync()
+        pos = batch.read_positions()
+        assert np.isfinite(pos).all()
+        for b in (0, 1, 46, 147, 148, 295, 296, 319):
+            ora = po.Oracle(po.Params.default(**prm), bodies[b][0], edges, tets, kind=_oracle_kind(po))
+            ora.permute_constraints(*batch.schedule_order(b))
+            ora.step(1 / 60, 3)
+            assert np.array_equal(batch.body_positions(b, pos), ora.positions()), f"body {b}"
+
+
+def test_batch_fast_arith_within_tolerance(capi, po, meshgen):
+    """PBD_FLAG_FAST_ARITH on the batch backend: every body within 2e-6 (relative RMS) of the exact batch
+    after one frame and within 1e-4 after 10 frames."""
+    local_xyz, tets, edges = meshgen.kuhn_grid(10, rot=np.eye(3), lowest_y=None)
+    bodies = [(meshgen.place_body(local_xyz, rot=meshgen.rotation_zx(7.0 * b, 3.0 * b), lowest_y=0.25 + 0.001 * b), edges, tets) for b in range(12)]
+    prm = capi.SolverParams.default(substeps=10)
+    diag = np.linalg.norm(local_xyz.max(0) - local_xyz.min(0))
+    with capi.Batch(prm, bodies, device=0, options=capi.Options(flags=capi.FLAG_FAST_ARITH)) as fast, capi.Batch(prm, bodies, device=0) as exact:
+        for frames, tol in ((1, 2e-6), (10, 1e-4)):
+            n = frames - (0 if frames == 1 else 1)
+            fast.step_async(1 / 60, n); fast.sync()
+            exact.step_async(1 / 60, n); exact.sync()
+            pf, pe = fast.read_positions(), exact.read_positions()
+            for b in range(len(bodies)):
+                d = np.sqrt(np.mean(np.sum((fast.body_positions(b, pf).astype(np.float64) - exact.body_positions(b, pe)) ** 2, 1))) / diag
+                assert d <= tol, f"body {b} after {frames} frames: rel RMS {d:.3e}"
