@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "pbd_abi_version", "pbd_last_error", "pbd_device_count",
     "pbd_create", "pbd_create_from_init", "pbd_init_payload_size", "pbd_step", "pbd_step_async", "pbd_sync", "pbd_read_positions", "pbd_destroy",
     "pbd_backend_name", "pbd_get_info", "pbd_set_params", "pbd_get_schedule_order",
-    "pbd_get_schedule_sequence", "pbd_get_array",
+    "pbd_get_schedule_sequence", "pbd_get_array", "pbd_set_colliders",
     "pbd_shard_export", "pbd_shard_attach_ipc", "pbd_shard_attach_local", "pbd_shard_owner",
     "pbd_plan_create", "pbd_plan_get_info", "pbd_plan_get_order", "pbd_plan_get_sequence",
     "pbd_plan_get_edge_slots", "pbd_plan_get_tet_slots", "pbd_plan_destroy",
@@ -152,6 +152,7 @@ def lib() -> C.CDLL:
     L.pbd_get_schedule_order.argtypes = [vp, vp, vp]
     L.pbd_get_schedule_sequence.argtypes = [vp, vp]
     L.pbd_get_array.argtypes = [vp, C.c_int, vp]
+    L.pbd_set_colliders.argtypes = [vp, vp, u32, f32]
     L.pbd_shard_export.argtypes = [vp, vp]
     L.pbd_shard_attach_ipc.argtypes = [vp, vp]
     L.pbd_shard_attach_local.argtypes = [vp, u32]
@@ -271,6 +272,12 @@ class Body:
         self.params = params.copy()
         _check(lib().pbd_set_params(self.h, C.byref(self.params)))
 
+    def set_colliders(self, colliders, particle_radius: float = 0.0):
+        """Primitive colliders of the clamp stage (``pbd_set_colliders``); ``colliders`` as built by
+        ``colliders_array`` (an empty list removes them)."""
+        a = colliders_array(colliders) if not isinstance(colliders, np.ndarray) else np.ascontiguousarray(colliders)
+        _check(lib().pbd_set_colliders(self.h, a.ctypes.data_as(C.c_void_p) if a.size else None, a.size, C.c_float(particle_radius)))
+
     def info(self) -> dict:
         i = Info()
         _check(lib().pbd_get_info(self.h, C.byref(i)))
@@ -297,6 +304,27 @@ class Body:
         out = np.zeros(shape, dtype=np.float32)
         _check(lib().pbd_get_array(self.h, what, out.ctypes.data_as(C.c_void_p)))
         return out
+
+
+COLLIDER_SPHERE, COLLIDER_BOX, COLLIDER_CAPSULE = 0, 1, 2
+COLLIDER_DTYPE = np.dtype([("type", "<u4"), ("p", "<f4", 3), ("q", "<f4", 4), ("d", "<f4", 3)])   # pbd_collider, 44 bytes
+
+
+def colliders_array(items) -> np.ndarray:
+    """``pbd_collider`` rows from dicts / tuples ``(type, position, quaternion xyzw, data)``:
+    sphere data = (radius,), box = half extents, capsule = (radius, half height); the capsule axis is the
+    collider's local Y (SoftBodyPrimitiveCollider.PrimitiveColliderData, SoftBodyPrimitiveCollider.cs:8-14)."""
+    a = np.zeros(len(items), dtype=COLLIDER_DTYPE)
+    for i, it in enumerate(items):
+        if isinstance(it, dict):
+            it = (it["type"], it["position"], it.get("rotation", (0, 0, 0, 1)), it["data"])
+        t, p, q, d = it
+        a[i]["type"] = t
+        a[i]["p"] = p
+        a[i]["q"] = q
+        dd = list(d) + [0.0] * (3 - len(d))
+        a[i]["d"] = dd[:3]
+    return a
 
 
 SHARD_EXPORT_BYTES = 128

@@ -58,6 +58,8 @@ struct BatchParams {
   float* edgeLam;
   float* tetLam;
   const StepConsts* consts;
+  const ColliderSet* colliders;   // (batches carry no colliders: always null / 0; the shared vertex stages read them)
+  uint32_t nColliders;
   uint32_t nBodies, substeps, iterations;
   uint32_t recStride;
 };

@@ -31,6 +31,8 @@ struct DeviceArrays {
   uint32_t* slotOf = nullptr;   // [V] caller vertex -> slot (nullptr: identity)
   float* packed = nullptr;      // [3V] readback staging, caller order
   StepConsts* consts = nullptr; // device copy of the per-frame scalars
+  ColliderSet* colliders = nullptr;   // device copy of the primitive colliders (pbd_set_colliders)
+  uint32_t nColliders = 0;
   uint64_t bytes = 0;
 };
 
@@ -38,6 +40,7 @@ struct FrameShape {
   uint32_t substeps = 1;    // already clamped to >= 1
   uint32_t iterations = 0;
   int groundEnabled = 0;
+  uint32_t nColliders = 0;  // primitive colliders in the clamp stage (pbd_set_colliders)
 };
 
 class Backend {

@@ -6,6 +6,7 @@
 // becomes pbd_step; IStepper::pack_positions becomes pbd_read_positions.  No CPU fallback:
 // without a CUDA device every computing entry fails with PBD_ERR_NO_DEVICE.
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -68,7 +69,7 @@ cudaError_t dev_alloc(T** p, size_t n, uint64_t& bytes) {
 void free_arrays(DeviceArrays& d) {
   cudaFree(d.pos); cudaFree(d.prev); cudaFree(d.vel);
   cudaFree(d.edgeRest); cudaFree(d.edgeLam); cudaFree(d.tetRest); cudaFree(d.tetLam);
-  cudaFree(d.slotOf); cudaFree(d.packed); cudaFree(d.consts);
+  cudaFree(d.slotOf); cudaFree(d.packed); cudaFree(d.consts); cudaFree(d.colliders);
   d = DeviceArrays{};
 }
 
@@ -107,6 +108,7 @@ struct pbd_handle {
     f.substeps = params.substeps > 1u ? params.substeps : 1u;
     f.iterations = params.iterations;
     f.groundEnabled = params.groundEnabled ? 1 : 0;
+    f.nColliders = d.nColliders;
     return f;
   }
 };
@@ -220,6 +222,8 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
   if ((ce = dev_alloc(&d.tetLam, nT, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc tetLam");
   if ((ce = dev_alloc(&d.packed, (size_t)V * 3, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc packed");
   if ((ce = dev_alloc(&d.consts, 1, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc consts");
+  if ((ce = dev_alloc(&d.colliders, 1, d.bytes)) != cudaSuccess) return bail(ce, "cudaMalloc colliders");
+  if ((ce = cudaMemset(d.colliders, 0, sizeof(ColliderSet))) != cudaSuccess) return bail(ce, "memset colliders");
 
   bool identity = true;
   for (uint32_t i = 0; i < V && identity; ++i) identity = plan.vertexToSlot[i] == i;
@@ -372,6 +376,30 @@ int pbd_set_params(pbd_handle* h, const pbd_params* p) {
   CU(onDevice.err);
   CU(cudaStreamSynchronize(h->stream));
   h->params = *p;
+  h->be->invalidate();
+  return PBD_OK;
+}
+
+int pbd_set_colliders(pbd_handle* h, const pbd_collider* cols, uint32_t n, float particleRadius) {
+  if (!h || (n && !cols)) return fail(PBD_ERR_INVALID, "null argument");
+  if (n > PBD_MAX_COLLIDERS) return fail(PBD_ERR_INVALID, "at most PBD_MAX_COLLIDERS colliders");
+  static_assert(sizeof(pbd_collider) == sizeof(Collider) && sizeof(pbd_collider) == 44, "pbd_collider layout");
+  ColliderSet cs{};
+  cs.n = n;
+  cs.particleRadius = particleRadius;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (cols[i].type > PBD_COLLIDER_CAPSULE) return fail(PBD_ERR_INVALID, "unknown collider type");
+    const float* f = &cols[i].px;
+    for (int j = 0; j < 10; ++j)
+      if (!std::isfinite(f[j])) return fail(PBD_ERR_INVALID, "collider " + std::to_string(i) + " is not finite");
+    std::memcpy(&cs.c[i], &cols[i], sizeof(Collider));
+  }
+  if (!std::isfinite(particleRadius)) return fail(PBD_ERR_INVALID, "particleRadius is not finite");
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(h->d.colliders, &cs, sizeof(cs), cudaMemcpyHostToDevice));
+  h->d.nColliders = n;
   h->be->invalidate();
   return PBD_OK;
 }

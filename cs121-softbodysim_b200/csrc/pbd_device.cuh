@@ -100,13 +100,14 @@ __device__ __forceinline__ float4 finish_vertex(const Arrays& P, const StepConst
   float4 p = in.p;
   if (mode == LOAD_GROUND) {
     ground_vertex(p, k);
+    if (P.nColliders) collide_vertex(p, P.colliders, P.nColliders);
   } else if (mode == LOAD_PREDICT) {
     float4 v = in.v;
     p = predict_vertex(in.x, v, p.w, k);
     __stcg(P.vel + s, v);
   } else if (mode == LOAD_COMMIT_PREDICT) {
     float4 x = in.x, v;
-    if (clampFirst) ground_vertex(p, k);
+    if (clampFirst) { ground_vertex(p, k); if (P.nColliders) collide_vertex(p, P.colliders, P.nColliders); }
     commit_vertex(p, x, v, k);
     v.w = 0.0f;
     p = predict_vertex(x, v, p.w, k);

@@ -263,6 +263,91 @@ PBD_DEV void ground_vertex(float4& p, const StepConsts& k) {
   if (k.groundEnabled && p.w != 0.0f && p.y < k.groundY) p.y = k.groundY;
 }
 
+// ---- primitive colliders in the clamp stage ----------------------------------
+// Sphere / oriented box / capsule push-out of the reference's in-engine solver, restated from
+// Assets/Scripts/Softbody/SoftBodyCollisionMath.cs:8-110 (ComputePushOut, PushOutSphere :24-41,
+// PushOutBox :45-90, PushOutCapsule :93-110) and applied where that solver applies it
+// (SoftBodySolver.cs:554-561 == SoftBodyCompute.compute:410-430: after the ground plane, colliders in
+// order, `if (hit) p += push`).  float32, C# evaluation order, no FMA; the quaternion product is
+// Unity's `Quaternion * Vector3`.  Quaternion.Inverse is taken as the conjugate (unit rotations).
+// PBDServer itself has only the y-plane (Sim.cpp:187-195): with no collider set this is dead code.
+struct Collider {              // == pbd_collider (include/pbd_b200.h), 48 bytes
+  uint32_t type;               // 0 sphere, 1 box, 2 capsule (SoftBodyPrimitiveCollider.PrimitiveType)
+  float px, py, pz;            // positionW
+  float qx, qy, qz, qw;        // rotationW
+  float dx, dy, dz;            // sphere: radius | box: half extents | capsule: radius, half height
+};
+constexpr uint32_t kMaxColliders = 16;
+struct ColliderSet {
+  uint32_t n;
+  float particleRadius;
+  uint32_t pad[2];
+  Collider c[kMaxColliders];
+};
+
+PBD_DEV void quat_rotate(float qx, float qy, float qz, float qw, float vx, float vy, float vz, float& ox, float& oy, float& oz) {
+  const float x = fmul(qx, 2.0f), y = fmul(qy, 2.0f), z = fmul(qz, 2.0f);
+  const float xx = fmul(qx, x), yy = fmul(qy, y), zz = fmul(qz, z);
+  const float xy = fmul(qx, y), xz = fmul(qx, z), yz = fmul(qy, z);
+  const float wx = fmul(qw, x), wy = fmul(qw, y), wz = fmul(qw, z);
+  ox = fadd(fadd(fmul(fsub(1.0f, fadd(yy, zz)), vx), fmul(fsub(xy, wz), vy)), fmul(fadd(xz, wy), vz));
+  oy = fadd(fadd(fmul(fadd(xy, wz), vx), fmul(fsub(1.0f, fadd(xx, zz)), vy)), fmul(fsub(yz, wx), vz));
+  oz = fadd(fadd(fmul(fsub(xz, wy), vx), fmul(fadd(yz, wx), vy)), fmul(fsub(1.0f, fadd(xx, yy)), vz));
+}
+// SoftBodyCollisionMath.cs:24-41
+PBD_DEV bool push_out_sphere(float cx, float cy, float cz, float radius, float px, float py, float pz, float& ox, float& oy, float& oz) {
+  const float vx = fsub(px, cx), vy = fsub(py, cy), vz = fsub(pz, cz);
+  const float d2 = dot3(vx, vy, vz, vx, vy, vz);
+  const float r = fmaxf(1e-6f, radius);
+  if (d2 >= fmul(r, r)) return false;
+  const float d = __fsqrt_rn(fmaxf(d2, 1e-20f));
+  float nx = 0.0f, ny = 1.0f, nz = 0.0f;   // Vector3.up
+  if (d > 1e-10f) { nx = fdiv(vx, d); ny = fdiv(vy, d); nz = fdiv(vz, d); }
+  const float k = fsub(r, d);
+  ox = fmul(nx, k); oy = fmul(ny, k); oz = fmul(nz, k);
+  return true;
+}
+PBD_DEV bool push_out(const Collider& c, float pr, float px, float py, float pz, float& ox, float& oy, float& oz) {
+  if (c.type == 0u) return push_out_sphere(c.px, c.py, c.pz, fadd(c.dx, pr), px, py, pz, ox, oy, oz);
+  if (c.type == 1u) {   // SoftBodyCollisionMath.cs:45-90
+    float lx, ly, lz;
+    quat_rotate(-c.qx, -c.qy, -c.qz, c.qw, fsub(px, c.px), fsub(py, c.py), fsub(pz, c.pz), lx, ly, lz);
+    const float ex = fadd(c.dx, pr), ey = fadd(c.dy, pr), ez = fadd(c.dz, pr);
+    if (!(fabsf(lx) <= ex && fabsf(ly) <= ey && fabsf(lz) <= ez)) return false;
+    const float dx = fsub(ex, fabsf(lx)), dy = fsub(ey, fabsf(ly)), dz = fsub(ez, fabsf(lz));
+    float ux = 0.0f, uy = 0.0f, uz = 0.0f;
+    if (dx <= dy && dx <= dz) ux = fmul(dx, lx >= 0.0f ? 1.0f : -1.0f);
+    else if (dy <= dz) uy = fmul(dy, ly >= 0.0f ? 1.0f : -1.0f);
+    else uz = fmul(dz, lz >= 0.0f ? 1.0f : -1.0f);
+    quat_rotate(c.qx, c.qy, c.qz, c.qw, ux, uy, uz, ox, oy, oz);
+    return true;
+  }
+  // capsule, axis = local Y: SoftBodyCollisionMath.cs:93-110
+  const float r = fmaxf(1e-6f, fadd(c.dx, pr)), h = fmaxf(0.0f, c.dy);
+  float ux, uy, uz;
+  quat_rotate(c.qx, c.qy, c.qz, c.qw, 0.0f, 1.0f, 0.0f, ux, uy, uz);
+  const float ax = fsub(c.px, fmul(ux, h)), ay = fsub(c.py, fmul(uy, h)), az = fsub(c.pz, fmul(uz, h));
+  const float bx = fadd(c.px, fmul(ux, h)), by = fadd(c.py, fmul(uy, h)), bz = fadd(c.pz, fmul(uz, h));
+  const float abx = fsub(bx, ax), aby = fsub(by, ay), abz = fsub(bz, az);
+  const float ab2 = dot3(abx, aby, abz, abx, aby, abz);
+  float t = 0.0f;
+  if (ab2 > 1e-20f) {
+    t = fdiv(dot3(fsub(px, ax), fsub(py, ay), fsub(pz, az), abx, aby, abz), ab2);
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+  }
+  return push_out_sphere(fadd(ax, fmul(abx, t)), fadd(ay, fmul(aby, t)), fadd(az, fmul(abz, t)), r, px, py, pz, ox, oy, oz);
+}
+// every collider in order, on a vertex with mass (SoftBodyCompute.compute:396-397: invMass == 0 -> untouched)
+PBD_DEV void collide_vertex(float4& p, const ColliderSet* cs, uint32_t n) {
+  if (p.w == 0.0f) return;
+  const float pr = fmaxf(1e-6f, cs->particleRadius);   // SoftBodySolver.cs:546
+  for (uint32_t i = 0; i < n; ++i) {
+    const Collider c = cs->c[i];
+    float ox, oy, oz;
+    if (push_out(c, pr, p.x, p.y, p.z, ox, oy, oz)) { p.x = fadd(p.x, ox); p.y = fadd(p.y, oy); p.z = fadd(p.z, oz); }
+  }
+}
+
 // commit for one vertex (Sim.cpp:202-221).  p: xStar (+w); x: committed position, updated; v out.
 PBD_DEV void commit_vertex(float4& p, float4& x, float4& v, const StepConsts& k) {
   if (p.w == 0.0f) {

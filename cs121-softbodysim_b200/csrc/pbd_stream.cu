@@ -77,14 +77,15 @@ __global__ void __launch_bounds__(kBlock) tet_colour_kernel(float4* __restrict__
 }
 
 __global__ void __launch_bounds__(kBlock) ground_kernel(float4* __restrict__ pos, uint32_t V,
-                                                        const StepConsts* __restrict__ kc) {
+                                                        const StepConsts* __restrict__ kc, const ColliderSet* __restrict__ cs,
+                                                        uint32_t nColliders) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V) return;
   float4 p = pos[i];
-  if (p.w != 0.0f && p.y < kc->groundY) {
-    p.y = kc->groundY;
-    pos[i] = p;
-  }
+  const float4 q = p;
+  if (kc->groundEnabled && p.w != 0.0f && p.y < kc->groundY) p.y = kc->groundY;
+  if (nColliders) collide_vertex(p, cs, nColliders);
+  if (p.x != q.x || p.y != q.y || p.z != q.z) pos[i] = p;
 }
 
 __global__ void __launch_bounds__(kBlock) commit_kernel(float4* __restrict__ pos, float4* __restrict__ prev,
@@ -149,7 +150,7 @@ class StreamBackend final : public Backend {
 
   uint32_t launches_per_frame(const FrameShape& f) const override {
     const uint32_t nE = nonempty(edgeOff_), nT = nonempty(tetOff_);
-    return f.substeps * (2 + f.iterations * (nE + nT + (f.groundEnabled ? 1 : 0)));
+    return f.substeps * (2 + f.iterations * (nE + nT + ((f.groundEnabled || f.nColliders) ? 1 : 0)));
   }
   uint64_t device_bytes() const override { return bytes_; }
   void invalidate() override { drop_graph(); }
@@ -166,7 +167,7 @@ class StreamBackend final : public Backend {
     if (flags_ & PBD_FLAG_STAGE_TIMING) return record(d, f, s, true);
     if (flags_ & PBD_FLAG_NO_GRAPH) return record(d, f, s, false);
     if (!exec_ || !(f.substeps == shape_.substeps && f.iterations == shape_.iterations &&
-                    f.groundEnabled == shape_.groundEnabled)) {
+                    f.groundEnabled == shape_.groundEnabled && f.nColliders == shape_.nColliders)) {
       drop_graph();
       cudaError_t err = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
       if (err != cudaSuccess) return err;
@@ -231,7 +232,7 @@ class StreamBackend final : public Backend {
           const uint32_t n = tetOff_[c + 1] - tetOff_[c];
           if (n) tet_colour_kernel<<<blocks_for(n), kBlock, 0, s>>>(d.pos, tetIdx_, d.tetRest, d.tetLam, tetOff_[c], n, d.consts);
         }
-        if (f.groundEnabled && d.V) ground_kernel<<<vb, kBlock, 0, s>>>(d.pos, d.V, d.consts);
+        if ((f.groundEnabled || f.nColliders) && d.V) ground_kernel<<<vb, kBlock, 0, s>>>(d.pos, d.V, d.consts, d.colliders, f.nColliders);
       }
       if (timed) mark(2, s);
       if (d.V) commit_kernel<<<vb, kBlock, 0, s>>>(d.pos, d.prev, d.vel, d.V, d.consts);

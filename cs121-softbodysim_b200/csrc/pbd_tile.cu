@@ -70,6 +70,8 @@ struct TileParams {
   const PhaseDesc* phases;
   const uint32_t* tile0Begin;   // nTile0 + 1
   const StepConsts* consts;
+  const ColliderSet* colliders;  // primitive colliders of the clamp stage (nColliders == 0: none)
+  uint32_t nColliders;
   unsigned* barrier;
   unsigned* done;               // per tile: completed visits (point-to-point sync), or null: grid barrier per phase
   // one body across several GPUs: every rank steps the tiles it owns; a vertex / a done counter
@@ -178,7 +180,7 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
         float4 p, x = __ldcg(P.prev + s), v;
         if (TAGGED) p = waitTag ? tagged_wait_load(P, s, waitTag, __ldg(P.invMass + s)) : tagged_load_any(P, s);
         else p = __ldcg(P.pos + s);
-        if (clamp) ground_vertex(p, k);
+        if (clamp) { ground_vertex(p, k); if (P.nColliders) collide_vertex(p, P.colliders, P.nColliders); }
         commit_vertex(p, x, v, k);
         v.w = 0.0f;
         __stcg(P.prev + s, x);
@@ -883,6 +885,7 @@ class TileBackend final : public Backend {
     P.pos = d.pos; P.posT = tagged_ ? posT_ : nullptr; P.invMass = invMass_; P.prev = d.prev; P.vel = d.vel;
     P.blob = blob_; P.copies = copies_; P.edgeLam = d.edgeLam; P.tetLam = d.tetLam;
     P.phases = phases_; P.tile0Begin = tile0Begin_; P.consts = d.consts; P.barrier = barrier_;
+    P.colliders = d.colliders; P.nColliders = d.nColliders;
     P.trace = trace_; P.ftrace = ftrace_;
     P.nTile0 = nTile0_; P.nPhases = nPhases_; P.substeps = f.substeps; P.iterations = f.iterations;
     P.recStride = recStride_;

@@ -194,6 +194,23 @@ const char* pbd_backend_name(const pbd_handle* h);
 int pbd_get_info(const pbd_handle* h, pbd_info* out);
 int pbd_set_params(pbd_handle* h, const pbd_params* params); /* substeps/iterations/compliances/gravity/ground */
 
+/* Primitive colliders in the clamp stage (BASELINE.json north_star kernel (3) "ground and
+ * collision clamping").  PBDServer has only the y-plane (Sim.cpp:187-195); the sphere / oriented box / capsule
+ * push-out is the reference's in-engine solver's: Assets/Scripts/Softbody/SoftBodyCollisionMath.cs:8-110,
+ * collider data as SoftBodyPrimitiveCollider.PrimitiveColliderData (SoftBodyPrimitiveCollider.cs:8-14), applied
+ * like SoftBodySolver.cs:554-561 -- after the ground clamp of every iteration, colliders in order, on every vertex
+ * with mass: if it penetrates (within particleRadius), it is moved out along the minimal translation.
+ * n = 0 removes them.  Single bodies only (tile and stream backends). */
+enum { PBD_COLLIDER_SPHERE = 0, PBD_COLLIDER_BOX = 1, PBD_COLLIDER_CAPSULE = 2 };
+#define PBD_MAX_COLLIDERS 16
+typedef struct pbd_collider {
+  uint32_t type;          /* PBD_COLLIDER_*                                                    */
+  float px, py, pz;       /* positionW                                                         */
+  float qx, qy, qz, qw;   /* rotationW, unit quaternion (capsule axis = its local Y)           */
+  float dx, dy, dz;       /* sphere: radius | box: half extents | capsule: radius, half height */
+} pbd_collider;
+int pbd_set_colliders(pbd_handle* h, const pbd_collider* colliders, uint32_t n, float particleRadius);
+
 /* The projection order actually executed, as indices into the caller's arrays:
  * edgeOrder[k] = caller edge projected k-th inside an iteration's edge sweep (E entries),
  * tetOrder likewise (T entries).  Either pointer may be NULL. */

@@ -46,6 +46,10 @@ typedef struct pbdo_state {
   uint32_t *ta, *tb, *tc, *td; /* T                                                      */
   float *tRest, *tLam;      /* T                                                         */
   double ms_predict, ms_solve, ms_commit, ms_total; /* accumulated like perf::StepStats  */
+  /* primitive colliders of the clamp stage; 0 = PBDServer's behaviour */
+  uint32_t nColliders;
+  float particleRadius;
+  struct pbdo_collider { uint32_t type; float p[3]; float q[4]; float d[3]; } colliders[16];
 } pbdo_state;
 
 static double now_ms(void) {
@@ -190,6 +194,90 @@ static void ground(pbdo_state *s) {
   }
 }
 
+/* ---- primitive colliders.  Parity status of THIS part: UNPINNED -- the formulas
+ * live in the reference's Unity C# (Assets/Scripts/Softbody/SoftBodyCollisionMath.cs:8-110; HLSL twin
+ * Assets/Shaders/SoftBodyCompute.compute:108-204) and no C# / HLSL toolchain exists in this image, so
+ * this restatement cannot be run against them; it is checked against hand-computed known answers
+ * (tests/test_oracle_cpu.py) and is what the GPU clamp stage is compared with bit for bit.
+ * float32, C# evaluation order; Quaternion * Vector3 as Unity implements it; Quaternion.Inverse of a
+ * unit rotation = its conjugate. */
+static void quat_rotate(const float q[4], const float v[3], float o[3]) {
+  float x = q[0] * 2.0f, y = q[1] * 2.0f, z = q[2] * 2.0f;
+  float xx = q[0] * x, yy = q[1] * y, zz = q[2] * z;
+  float xy = q[0] * y, xz = q[0] * z, yz = q[1] * z;
+  float wx = q[3] * x, wy = q[3] * y, wz = q[3] * z;
+  o[0] = (1.0f - (yy + zz)) * v[0] + (xy - wz) * v[1] + (xz + wy) * v[2];
+  o[1] = (xy + wz) * v[0] + (1.0f - (xx + zz)) * v[1] + (yz - wx) * v[2];
+  o[2] = (xz - wy) * v[0] + (yz + wx) * v[1] + (1.0f - (xx + yy)) * v[2];
+}
+/* PushOutSphere, SoftBodyCollisionMath.cs:24-41 */
+static int push_out_sphere(const float c[3], float radius, const float p[3], float push[3]) {
+  float v[3] = {p[0] - c[0], p[1] - c[1], p[2] - c[2]};
+  float d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  float r = fmaxf(1e-6f, radius);
+  if (d2 >= r * r) return 0;
+  float d = sqrtf(fmaxf(d2, 1e-20f));
+  float n[3] = {0.0f, 1.0f, 0.0f};
+  if (d > 1e-10f) { n[0] = v[0] / d; n[1] = v[1] / d; n[2] = v[2] / d; }
+  float k = r - d;
+  push[0] = n[0] * k; push[1] = n[1] * k; push[2] = n[2] * k;
+  return 1;
+}
+/* ComputePushOut :8-21, PushOutBox :45-90, PushOutCapsule :93-110 */
+static int push_out(const struct pbdo_collider *c, float pr, const float p[3], float push[3]) {
+  if (c->type == 0u) return push_out_sphere(c->p, c->d[0] + pr, p, push);
+  if (c->type == 1u) {
+    float inv[4] = {-c->q[0], -c->q[1], -c->q[2], c->q[3]};
+    float rel[3] = {p[0] - c->p[0], p[1] - c->p[1], p[2] - c->p[2]}, l[3];
+    quat_rotate(inv, rel, l);
+    float ex = c->d[0] + pr, ey = c->d[1] + pr, ez = c->d[2] + pr;
+    if (!(fabsf(l[0]) <= ex && fabsf(l[1]) <= ey && fabsf(l[2]) <= ez)) return 0;
+    float dx = ex - fabsf(l[0]), dy = ey - fabsf(l[1]), dz = ez - fabsf(l[2]);
+    float u[3] = {0.0f, 0.0f, 0.0f};
+    if (dx <= dy && dx <= dz) u[0] = dx * (l[0] >= 0.0f ? 1.0f : -1.0f);
+    else if (dy <= dz) u[1] = dy * (l[1] >= 0.0f ? 1.0f : -1.0f);
+    else u[2] = dz * (l[2] >= 0.0f ? 1.0f : -1.0f);
+    quat_rotate(c->q, u, push);
+    return 1;
+  }
+  float r = fmaxf(1e-6f, c->d[0] + pr), h = fmaxf(0.0f, c->d[1]);
+  float yv[3] = {0.0f, 1.0f, 0.0f}, up[3];
+  quat_rotate(c->q, yv, up);
+  float a[3] = {c->p[0] - up[0] * h, c->p[1] - up[1] * h, c->p[2] - up[2] * h};
+  float b[3] = {c->p[0] + up[0] * h, c->p[1] + up[1] * h, c->p[2] + up[2] * h};
+  float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+  float ab2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+  float t = 0.0f;
+  if (ab2 > 1e-20f) {
+    t = ((p[0] - a[0]) * ab[0] + (p[1] - a[1]) * ab[1] + (p[2] - a[2]) * ab[2]) / ab2;
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+  }
+  float cc[3] = {a[0] + ab[0] * t, a[1] + ab[1] * t, a[2] + ab[2] * t};
+  return push_out_sphere(cc, r, p, push);
+}
+/* SoftBodySolver.cs:554-561: after the ground plane, every collider in order, `if (hit) p += push` */
+static void collide(pbdo_state *s) {
+  if (!s->nColliders) return;
+  float pr = fmaxf(1e-6f, s->particleRadius);
+  for (uint32_t i = 0; i < s->V; ++i) {
+    if (s->w[i] == 0.0f) continue;
+    float *p = s->xs + 3 * i;
+    for (uint32_t c = 0; c < s->nColliders; ++c) {
+      float push[3];
+      if (push_out(&s->colliders[c], pr, p, push)) { p[0] = p[0] + push[0]; p[1] = p[1] + push[1]; p[2] = p[2] + push[2]; }
+    }
+  }
+}
+void pbdo_set_colliders(pbdo_state *s, const void *cols, uint32_t n, float particleRadius) {
+  s->nColliders = n > 16u ? 16u : n;
+  s->particleRadius = particleRadius;
+  if (s->nColliders) memcpy(s->colliders, cols, sizeof(s->colliders[0]) * s->nColliders);
+}
+/* one point against one collider (known-answer tests) */
+int pbdo_push_out(const void *col, float particleRadius, const float *p, float *push) {
+  return push_out((const struct pbdo_collider *)col, fmaxf(1e-6f, particleRadius), p, push);
+}
+
 /* CProgram/src/Sim.cpp:197-222 */
 static void commit(pbdo_state *s, float dt) {
   float invDt = (dt > 1e-12f) ? (1.0f / dt) : 0.0f;
@@ -297,6 +385,7 @@ void pbdo_step(pbdo_state *s, float dt) {
       float aT = xpbd_alpha(s->prm.volumeCompliance, sdt);
       for (uint32_t t = 0; t < s->T; ++t) project_tet(s, t, aT);
       ground(s);
+      collide(s);
     }
     double t2 = now_ms();
     commit(s, sdt);
@@ -324,6 +413,7 @@ void pbdo_step_sequence(pbdo_state *s, float dt, const uint32_t *items, uint64_t
         else project_edge(s, id, aE);
       }
       ground(s);
+      collide(s);
     }
     commit(s, sdt);
   }

@@ -161,6 +161,17 @@ class Oracle:
         assert w.size == self.V
         self._f("set_inv_mass")(self.h, _ptr(w))
 
+    def set_colliders(self, colliders, particle_radius: float):
+        """colliders: float32/uint32-compatible structured rows (type, p[3], q[4], d[3]) = 44 bytes each, as
+        ``capi.colliders_array`` builds them (port only: PBDServer has no colliders)."""
+        assert self.kind == "port"
+        a = np.ascontiguousarray(colliders)
+        assert a.dtype.itemsize == 44
+        f = self._f("set_colliders")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float]
+        f.restype = None
+        f(self.h, a.ctypes.data_as(C.c_void_p) if a.size else None, a.size, C.c_float(particle_radius))
+
     def stats(self, reset: bool = True) -> dict:
         out = (C.c_double * 5)()
         self._f("stats")(self.h, out, 1 if reset else 0)
@@ -168,6 +179,21 @@ class Oracle:
 
     def name(self) -> str:
         return self._f("name")().decode()
+
+
+def push_out(collider, particle_radius: float, point):
+    """One point against one collider with the port's restatement of SoftBodyCollisionMath.ComputePushOut:
+    returns (hit, push[3])."""
+    lib, pre = _load("port")
+    a = np.ascontiguousarray(collider)
+    assert a.dtype.itemsize == 44 and a.size == 1
+    p = np.ascontiguousarray(point, dtype=np.float32)
+    out = np.zeros(3, dtype=np.float32)
+    f = getattr(lib, pre + "push_out")
+    f.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    f.restype = C.c_int
+    hit = f(a.ctypes.data_as(C.c_void_p), C.c_float(particle_radius), p.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return bool(hit), out
 
 
 # ---------------------------------------------------------------- residual metrics (P3)

@@ -692,3 +692,60 @@ def test_batch_fast_arith_within_tolerance(capi, po, meshgen):
             for b in range(len(bodies)):
                 d = np.sqrt(np.mean(np.sum((fast.body_positions(b, pf).astype(np.float64) - exact.body_positions(b, pe)) ** 2, 1))) / diag
                 assert d <= tol, f"body {b} after {frames} frames: rel RMS {d:.3e}"
+
+
+COLLIDER_SCENE = [
+    dict(type=0, position=(0.3, -0.6, 0.4), data=(1.0,)),                                                    # sphere under the body
+    dict(type=1, position=(1.6, 0.1, 0.5), rotation=(0.0, 0.0, 0.38268343, 0.92387953), data=(0.6, 0.15, 0.8)),   # tilted slab
+    dict(type=2, position=(-0.5, 0.3, 0.5), rotation=(0.70710678, 0.0, 0.0, 0.70710678), data=(0.2, 0.9)),      # capsule lying along z
+]
+
+
+@pytest.mark.parametrize("backend,order,flags", [("stream", "strict", 0), ("tile", "strict", 0), ("tile", "interleaved", 0),
+                                                 ("tile", "interleaved", 4), ("tile", "riding", 4)])
+def test_colliders_bit_exact_vs_oracle(backend, order, flags, capi, po, meshgen):
+    """pbd_set_colliders: sphere, oriented box and capsule push-out in the clamp stage, after
+    the ground clamp of every iteration.  The GPU must match the oracle's restatement of
+    SoftBodyCollisionMath.cs:8-110 BIT FOR BIT in every backend / order / hand-over mode; vertices end up
+    outside every collider; removing the colliders restores PBDServer's behaviour."""
+    x0, tets, edges = meshgen.kuhn_grid(8, lowest_y=0.9)
+    om = {"strict": capi.ORDER_STRICT, "interleaved": capi.ORDER_INTERLEAVED, "riding": capi.ORDER_RIDING}[order]
+    prm = dict(substeps=5)
+    body = capi.Body(capi.SolverParams.default(**prm), x0, edges, tets, device=0,
+                     options=_opt(capi, backend, order_mode=om, tile_vertices=150 if backend == "tile" else 0, flags=flags))
+    cols = capi.colliders_array(COLLIDER_SCENE)
+    body.set_colliders(cols, 0.02)
+    ora = po.Oracle(po.Params.default(**prm), x0, edges, tets, kind="port")
+    ora.permute_constraints(*body.schedule_order())
+    ora.set_colliders(cols, 0.02)
+    seq = body.schedule_sequence()
+    for fr in range(60):
+        body.step(1 / 60)
+        ora.step_sequence(1 / 60, seq)
+        if fr in (0, 9, 29, 59):
+            _assert_state_equal(capi, po, body, ora, f"colliders {backend}/{order}/flags={flags} frame {fr + 1}")
+    pos = body.read_positions()
+    assert np.isfinite(pos).all() and pos[:, 1].min() >= -1e-6
+    assert (np.linalg.norm(pos - np.array(COLLIDER_SCENE[0]["position"], np.float32), axis=1) >= 1.0 + 0.02 - 1e-3).all()
+    moved = np.abs(pos - x0).max()
+    assert moved > 0.05                                             # the scene did something
+    body.set_colliders([], 0.0)                                     # removed: back to the plain path
+    ora.set_colliders(capi.colliders_array([]), 0.0)
+    for _ in range(5):
+        body.step(1 / 60)
+        ora.step_sequence(1 / 60, seq)
+    _assert_state_equal(capi, po, body, ora, "after removing the colliders")
+    body.close()
+
+
+def test_set_colliders_validation(capi, meshgen):
+    x0, tets, edges = meshgen.kuhn_grid(3)
+    with capi.Body(capi.SolverParams.default(), x0, edges, tets, device=0) as b:
+        with pytest.raises(capi.PBDError):
+            b.set_colliders(capi.colliders_array([dict(type=7, position=(0, 0, 0), data=(1.0,))]), 0.0)
+        with pytest.raises(capi.PBDError):
+            b.set_colliders(capi.colliders_array([dict(type=0, position=(np.nan, 0, 0), data=(1.0,))]), 0.0)
+        with pytest.raises(capi.PBDError):
+            b.set_colliders(capi.colliders_array([dict(type=0, position=(0, 0, 0), data=(1.0,))] * 17), 0.0)
+        b.set_colliders(capi.colliders_array([dict(type=0, position=(0, -5, 0), data=(1.0,))] * 16), 0.0)
+        b.step(1 / 60)
