@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "pbd_abi_version", "pbd_last_error", "pbd_device_count",
     "pbd_create", "pbd_create_from_init", "pbd_init_payload_size", "pbd_step", "pbd_step_async", "pbd_sync", "pbd_read_positions", "pbd_destroy",
     "pbd_backend_name", "pbd_get_info", "pbd_set_params", "pbd_get_schedule_order",
-    "pbd_get_schedule_sequence", "pbd_get_array", "pbd_set_colliders",
+    "pbd_get_schedule_sequence", "pbd_get_array", "pbd_set_colliders", "pbd_set_surface", "pbd_read_normals",
     "pbd_shard_export", "pbd_shard_attach_ipc", "pbd_shard_attach_local", "pbd_shard_owner",
     "pbd_plan_create", "pbd_plan_get_info", "pbd_plan_get_order", "pbd_plan_get_sequence",
     "pbd_plan_get_edge_slots", "pbd_plan_get_tet_slots", "pbd_plan_destroy",
@@ -153,6 +153,8 @@ def lib() -> C.CDLL:
     L.pbd_get_schedule_sequence.argtypes = [vp, vp]
     L.pbd_get_array.argtypes = [vp, C.c_int, vp]
     L.pbd_set_colliders.argtypes = [vp, vp, u32, f32]
+    L.pbd_set_surface.argtypes = [vp, vp, u32]
+    L.pbd_read_normals.argtypes = [vp, vp]
     L.pbd_shard_export.argtypes = [vp, vp]
     L.pbd_shard_attach_ipc.argtypes = [vp, vp]
     L.pbd_shard_attach_local.argtypes = [vp, u32]
@@ -271,6 +273,17 @@ class Body:
     def set_params(self, params: SolverParams):
         self.params = params.copy()
         _check(lib().pbd_set_params(self.h, C.byref(self.params)))
+
+    def set_surface(self, surface_tris):
+        """``pbd_set_surface``: the boundary triangles (the asset's surfaceTriIds) normals are computed from."""
+        t = np.ascontiguousarray(surface_tris, dtype=np.uint32).reshape(-1, 3)
+        _check(lib().pbd_set_surface(self.h, _ptr(t), t.shape[0]))
+
+    def read_normals(self) -> np.ndarray:
+        """``pbd_read_normals``: float32 [V,3] area-weighted vertex normals of the committed positions."""
+        out = np.empty((self.V, 3), dtype=np.float32)
+        _check(lib().pbd_read_normals(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def set_colliders(self, colliders, particle_radius: float = 0.0):
         """Primitive colliders of the clamp stage (``pbd_set_colliders``); ``colliders`` as built by

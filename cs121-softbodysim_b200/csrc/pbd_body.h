@@ -77,6 +77,8 @@ Backend* make_tile_backend(const pbd_options& opts, int device);
 
 // shared vertex-stage kernels (pbd_stream.cu)
 cudaError_t launch_pack(const DeviceArrays& d, cudaStream_t s);
+// per-vertex normals of the surface triangles into d.packed (caller vertex order)
+cudaError_t launch_normals(const DeviceArrays& d, const uint32_t* tris, const uint32_t* adjOff, const uint32_t* adjTri, cudaStream_t s);
 
 StepConsts make_consts(const pbd_params& p, float dt);
 

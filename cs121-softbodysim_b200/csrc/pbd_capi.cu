@@ -95,10 +95,15 @@ struct pbd_handle {
   std::unique_ptr<Backend> be;
   double uploadMs = 0.0;
   bool pending = false;
+  uint32_t* surfTris = nullptr;   // pbd_set_surface: triangles + per-vertex adjacency (CSR), caller vertex order
+  uint32_t* surfAdjOff = nullptr;
+  uint32_t* surfAdjTri = nullptr;
+  uint32_t nSurfTris = 0;
 
   ~pbd_handle() {
     be.reset();
     free_arrays(d);
+    cudaFree(surfTris); cudaFree(surfAdjOff); cudaFree(surfAdjTri);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -367,6 +372,47 @@ int pbd_read_positions(pbd_handle* h, float* out, double* packMs) {
   if (h->d.V) CU(cudaMemcpyAsync(out, h->d.packed, sizeof(float) * 3 * (size_t)h->d.V, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   if (packMs) *packMs += wall_ms() - t0;
+  return PBD_OK;
+}
+
+int pbd_set_surface(pbd_handle* h, const uint32_t* tris, uint32_t nTris) {
+  if (!h || (nTris && !tris)) return fail(PBD_ERR_INVALID, "null argument");
+  const uint32_t V = h->d.V;
+  for (size_t i = 0; i < (size_t)nTris * 3; ++i)
+    if (tris[i] >= V) return fail(PBD_ERR_INDEX, "surface triangle index out of range (triangle " + std::to_string(i / 3) + ")");
+  // BuildTriAdjacency, SoftBodySolver.cs:1173-1213: per vertex the incident triangles in ascending triangle order
+  std::vector<uint32_t> off((size_t)V + 1, 0), adj((size_t)nTris * 3);
+  for (size_t i = 0; i < (size_t)nTris * 3; ++i) off[tris[i] + 1]++;
+  for (uint32_t v = 0; v < V; ++v) off[v + 1] += off[v];
+  {
+    std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+    for (uint32_t t = 0; t < nTris; ++t)
+      for (int j = 0; j < 3; ++j) adj[cur[tris[3 * (size_t)t + j]]++] = t;
+  }
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(h->surfTris); cudaFree(h->surfAdjOff); cudaFree(h->surfAdjTri);
+  h->surfTris = h->surfAdjOff = h->surfAdjTri = nullptr;
+  h->nSurfTris = 0;
+  CU(cudaMalloc((void**)&h->surfTris, sizeof(uint32_t) * (adj.size() + 1)));
+  CU(cudaMalloc((void**)&h->surfAdjOff, sizeof(uint32_t) * off.size()));
+  CU(cudaMalloc((void**)&h->surfAdjTri, sizeof(uint32_t) * (adj.size() + 1)));
+  if (nTris) CU(cudaMemcpy(h->surfTris, tris, sizeof(uint32_t) * 3 * (size_t)nTris, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->surfAdjOff, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice));
+  if (nTris) CU(cudaMemcpy(h->surfAdjTri, adj.data(), sizeof(uint32_t) * adj.size(), cudaMemcpyHostToDevice));
+  h->nSurfTris = nTris;
+  return PBD_OK;
+}
+
+int pbd_read_normals(pbd_handle* h, float* out) {
+  if (!h || !out) return fail(PBD_ERR_INVALID, "null argument");
+  if (!h->surfAdjOff) return fail(PBD_ERR_INVALID, "pbd_set_surface first");
+  DeviceScope onDevice(h->device);
+  CU(onDevice.err);
+  CU(launch_normals(h->d, h->surfTris, h->surfAdjOff, h->surfAdjTri, h->stream));
+  if (h->d.V) CU(cudaMemcpyAsync(out, h->d.packed, sizeof(float) * 3 * (size_t)h->d.V, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return PBD_OK;
 }
 

@@ -111,6 +111,30 @@ __global__ void __launch_bounds__(kBlock) pack_kernel(const float4* __restrict__
   out[3 * (size_t)i + 2] = x.z;
 }
 
+// Per-vertex normals for client-side lighting: K_UpdateNormals of the reference's compute
+// solver (Assets/Shaders/SoftBodyCompute.compute:459-491): sum of cross(pb - pa, pc - pa) over the surface
+// triangles incident to the vertex, in BuildTriAdjacency's order (SoftBodySolver.cs:1173-1213: ascending
+// triangle index), normalised; (0, 1, 0) when the sum vanishes.  Caller vertex order in and out.
+__global__ void __launch_bounds__(kBlock) normals_kernel(const float4* __restrict__ prev, const uint32_t* __restrict__ slotOf,
+                                                         const uint32_t* __restrict__ tris, const uint32_t* __restrict__ adjOff,
+                                                         const uint32_t* __restrict__ adjTri, float* __restrict__ out, uint32_t V) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+  for (uint32_t k = adjOff[i]; k < adjOff[i + 1]; ++k) {
+    const uint32_t t = adjTri[k];
+    const uint32_t a = tris[3 * t], b = tris[3 * t + 1], c = tris[3 * t + 2];
+    const float4 pa = prev[slotOf ? slotOf[a] : a], pb = prev[slotOf ? slotOf[b] : b], pc = prev[slotOf ? slotOf[c] : c];
+    const float ux = fsub(pb.x, pa.x), uy = fsub(pb.y, pa.y), uz = fsub(pb.z, pa.z);
+    const float vx = fsub(pc.x, pa.x), vy = fsub(pc.y, pa.y), vz = fsub(pc.z, pa.z);
+    sx = fadd(sx, cross_c(uy, vz, uz, vy)); sy = fadd(sy, cross_c(uz, vx, ux, vz)); sz = fadd(sz, cross_c(ux, vy, uy, vx));
+  }
+  const float n2 = dot3(sx, sy, sz, sx, sy, sz);
+  if (n2 < 1e-20f) { sx = 0.0f; sy = 1.0f; sz = 0.0f; }
+  else { const float r = fdiv(1.0f, __fsqrt_rn(n2)); sx = fmul(sx, r); sy = fmul(sy, r); sz = fmul(sz, r); }
+  out[3 * (size_t)i] = sx; out[3 * (size_t)i + 1] = sy; out[3 * (size_t)i + 2] = sz;
+}
+
 inline uint32_t blocks_for(uint32_t n) { return (n + kBlock - 1) / kBlock; }
 
 class StreamBackend final : public Backend {
@@ -258,6 +282,11 @@ Backend* make_stream_backend(uint32_t flags, uint32_t) { return new StreamBacken
 
 cudaError_t launch_pack(const DeviceArrays& d, cudaStream_t s) {
   if (d.V) pack_kernel<<<blocks_for(d.V), kBlock, 0, s>>>(d.prev, d.slotOf, d.packed, d.V);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_normals(const DeviceArrays& d, const uint32_t* tris, const uint32_t* adjOff, const uint32_t* adjTri, cudaStream_t s) {
+  if (d.V) normals_kernel<<<blocks_for(d.V), kBlock, 0, s>>>(d.prev, d.slotOf, tris, adjOff, adjTri, d.packed, d.V);
   return cudaGetLastError();
 }
 

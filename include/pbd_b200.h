@@ -194,6 +194,15 @@ const char* pbd_backend_name(const pbd_handle* h);
 int pbd_get_info(const pbd_handle* h, pbd_info* out);
 int pbd_set_params(pbd_handle* h, const pbd_params* params); /* substeps/iterations/compliances/gravity/ground */
 
+/* Per-vertex normals on the GPU, so that a client need not RecalculateNormals on the CPU
+ * (PBDRemoteSoftBody.cs:203-211): K_UpdateNormals of Assets/Shaders/SoftBodyCompute.compute:459-491 -- the
+ * normalised sum of cross(pb - pa, pc - pa) over the surface triangles incident to a vertex, in
+ * BuildTriAdjacency's order (SoftBodySolver.cs:1173-1213); (0, 1, 0) for vertices on no triangle.
+ * pbd_set_surface: nTris triangles (3 vertex indices each, caller's numbering; the asset's surfaceTriIds).
+ * pbd_read_normals: 3V floats, caller's vertex order, from the committed positions. */
+int pbd_set_surface(pbd_handle* h, const uint32_t* surfaceTriIds, uint32_t nTris);
+int pbd_read_normals(pbd_handle* h, float* out);
+
 /* Primitive colliders in the clamp stage (BASELINE.json north_star kernel (3) "ground and
  * collision clamping").  PBDServer has only the y-plane (Sim.cpp:187-195); the sphere / oriented box / capsule
  * push-out is the reference's in-engine solver's: Assets/Scripts/Softbody/SoftBodyCollisionMath.cs:8-110,

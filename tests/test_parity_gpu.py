@@ -749,3 +749,43 @@ def test_set_colliders_validation(capi, meshgen):
             b.set_colliders(capi.colliders_array([dict(type=0, position=(0, 0, 0), data=(1.0,))] * 17), 0.0)
         b.set_colliders(capi.colliders_array([dict(type=0, position=(0, -5, 0), data=(1.0,))] * 16), 0.0)
         b.step(1 / 60)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_gpu_vertex_normals_match_the_reference_formula(backend, capi, pkg, meshgen, golden):
+    """pbd_read_normals = K_UpdateNormals (SoftBodyCompute.compute:459-491) on the committed
+    positions: area-weighted sum of the incident surface triangles' normals, normalised, (0,1,0) for vertices on no
+    surface triangle.  Checked against a numpy restatement accumulating in the same (ascending triangle) order:
+    tolerance 2e-6 per component (float32 sums of ~6 terms); outward on the undeformed icosphere."""
+    import importlib
+    assets = importlib.import_module("cs121-softbodysim_b200.assets")
+    m = golden("mesh_icosphere001.npz")
+    x0 = meshgen.place_body(m["vertices"], lowest_y=0.6)
+    _, surf = assets.build_edges_and_surface(m["vertices"], m["tets"])
+    assert np.array_equal(surf, m["surface"])
+
+    def ref_normals(pos):
+        n = np.zeros((len(pos), 3), np.float32)
+        for a, b, c in surf:                                      # ascending triangle index per vertex = BuildTriAdjacency order
+            fn = np.cross((pos[b] - pos[a]).astype(np.float32), (pos[c] - pos[a]).astype(np.float32)).astype(np.float32)
+            n[a] += fn; n[b] += fn; n[c] += fn
+        n2 = np.einsum("ij,ij->i", n, n)
+        out = np.where((n2 < 1e-20)[:, None], np.array([0, 1, 0], np.float32), n / np.sqrt(np.maximum(n2, 1e-30))[:, None])
+        return out.astype(np.float32)
+
+    with capi.Body(capi.SolverParams.default(substeps=4), x0, m["edges"], m["tets"], device=0, options=_opt(capi, backend)) as b:
+        with pytest.raises(capi.PBDError):
+            b.read_normals()                                      # no surface set yet
+        b.set_surface(surf)
+        n0 = b.read_normals()
+        assert np.abs(n0 - ref_normals(x0)).max() <= 2e-6
+        on_surface = np.zeros(len(x0), bool); on_surface[surf.ravel()] = True
+        c = x0.mean(0)
+        assert (np.einsum("ij,ij->i", n0[on_surface], (x0 - c)[on_surface]) > 0).all()          # outward on the sphere
+        assert np.array_equal(n0[~on_surface], np.tile(np.array([0, 1, 0], np.float32), ((~on_surface).sum(), 1)))
+        for _ in range(40):                                       # squash it on the ground, normals follow the deformed surface
+            b.step(1 / 60)
+        assert np.abs(b.read_normals() - ref_normals(b.read_positions())).max() <= 2e-6
+        bad = surf.copy(); bad[0, 0] = len(x0)
+        with pytest.raises(capi.PBDError):
+            b.set_surface(bad)
