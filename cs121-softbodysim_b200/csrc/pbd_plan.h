@@ -89,6 +89,7 @@ struct Plan {
   uint32_t edgeDevCount = 0, tetDevCount = 0;
   std::vector<uint32_t> tile0Begin;    // K1+1 slot offsets of the phase-0 (RCB) tiles: a partition of all slots
   uint32_t blockThreads = 0;
+  uint32_t tilesPerSm = 1;             // resident tiles (CTAs) per SM the plan was sized for
   uint32_t edgePhases = 0, tetPhases = 0;
   uint32_t edgeColorSum = 0, tetColorSum = 0;  // sum over phases of the max local colour count
   // PBD_ORDER_RIDING: per tet schedule position, the schedule positions of its riders (2 entries,

@@ -549,6 +549,7 @@ class TileBackend final : public Backend {
     block_ = plan.blockThreads ? std::min(plan.blockThreads, 512u) : 512u;   // colour groups were cut to fit one pass of this block
     nPhases_ = (uint32_t)plan.phases.size();
     nTile0_ = (uint32_t)plan.tile0Begin.size() - 1;
+    tilesPerSm_ = std::max(1u, plan.tilesPerSm);
     lanes_ = opts_.lanes_per_tet == 2 ? 2u : opts_.lanes_per_tet == 4 ? 4u : 1u;   // auto: one thread per tet (fastest measured)
     fast_ = (opts_.flags & PBD_FLAG_FAST_ARITH) != 0u;
     if (fast_) lanes_ = 1;   // the fast forms exist for one thread per constraint
@@ -871,7 +872,7 @@ class TileBackend final : public Backend {
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, device_);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_);
     if (!coop || perSM < 1) return cudaErrorCooperativeLaunchTooLarge;
-    const uint32_t wantPerSm = std::max(1u, std::min(opts_.tiles_per_sm ? opts_.tiles_per_sm : 1u, (uint32_t)perSM));
+    const uint32_t wantPerSm = std::max(1u, std::min(opts_.tiles_per_sm ? opts_.tiles_per_sm : tilesPerSm_, (uint32_t)perSM));
     grid_ = std::max(1u, std::min(maxTilesPerPhase_, wantPerSm * (uint32_t)nSM));
     // every CTA's per-iteration tile list must fit the kernel's item table
     uint64_t items = 0;
@@ -1018,6 +1019,7 @@ class TileBackend final : public Backend {
   long long spinLimit_ = 0;
   bool tagged_ = false;
   bool fast_ = false;            // PBD_FLAG_FAST_ARITH
+  uint32_t tilesPerSm_ = 1;
   unsigned char* blob_ = nullptr;
   TileCopy* copies_ = nullptr;
   PhaseDesc* phases_ = nullptr;

@@ -1127,9 +1127,18 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   const bool riding = opts.order_mode == PBD_ORDER_RIDING;
   if (riding && opts.lanes_per_tet > 1) { err = "PBD_ORDER_RIDING needs one thread per tet (lanes_per_tet <= 1)"; return false; }
   const bool fused = opts.order_mode == PBD_ORDER_INTERLEAVED || riding;
-  const uint32_t blockThreads = opts.block_threads ? opts.block_threads : (opts.tiles_per_sm >= 2 ? 256u : 512u);
+  // tiles (CTAs) per SM.  auto: two half-size tiles of 256 threads with the tagged hand-over on a body that
+  // fills every SM (measured +4.6 % fast / +2.2 % exact on the 1M-tet body: one CTA's hand-over latencies
+  // overlap the other's sweep); one 512-thread tile otherwise (with done counters two CTAs measured -3 %:
+  // MEMBAR.GPU stalls the whole SM's memory pipeline)
+  if (nSMs == 0) nSMs = 148;
+  const uint32_t perSmPlan = opts.tiles_per_sm ? opts.tiles_per_sm
+                             : (((opts.flags & PBD_FLAG_TAGGED_HANDOVER) && opts.shard_world <= 1 && !opts.tile_vertices &&
+                                 (uint64_t)m.V >= (uint64_t)nSMs * 1024u) ? 2u : 1u);
+  const uint32_t blockThreads = opts.block_threads ? opts.block_threads : (perSmPlan >= 2 ? 256u : 512u);
   if (blockThreads % 32 || blockThreads > 512) { err = "block_threads must be a multiple of 32, <= 512"; return false; }
   plan.blockThreads = blockThreads;
+  plan.tilesPerSm = perSmPlan;
   // interleaved order, one thread per tet: edges and tets of a tile visit share the colour steps
   const bool noMixed = !knobs().mixed;   // debug: A/B against separate sweeps
   const uint32_t mixedThreads = (fused && opts.lanes_per_tet <= 1 && (!noMixed || riding)) ? blockThreads : 0u;
@@ -1171,7 +1180,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   if (opts.tile_vertices) {
     K1 = std::max(1u, (m.V + opts.tile_vertices - 1) / opts.tile_vertices);
   } else {
-    const uint32_t perSm = opts.tiles_per_sm ? opts.tiles_per_sm : 1u;
+    const uint32_t perSm = perSmPlan;
     const uint32_t minTile = 1024 / perSm;   // below this a tile is all interface: use fewer SMs instead
     K1 = std::max(1u, std::min(nSMs * perSm, m.V / std::max(1u, minTile)));
     // large bodies: enough tiles (whole waves) that a tile fits in shared memory, estimated from the
