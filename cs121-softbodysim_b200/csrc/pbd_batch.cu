@@ -21,6 +21,7 @@
 // for bit (tests/test_parity_gpu.py).
 #include <chrono>
 #include <cstddef>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -62,6 +63,28 @@ struct BatchParams {
   uint32_t nColliders;
   uint32_t nBodies, substeps, iterations;
   uint32_t recStride;
+  // work list (see BatchPiece): CTA c runs pieces [pieceBegin[c], pieceBegin[c + 1])
+  const struct BatchPiece* pieces;
+  const uint32_t* pieceBegin;
+  unsigned* pieceDone;      // per body: frame stamp set when the HEAD piece of a split body has been stored
+  uint32_t frameStamp;      // this frame's stamp (counts frames, wrap-safe compare)
+  long long spinLimit;      // bounded wait (cycles) of a tail piece for its head piece
+  unsigned* abortHost;      // mapped host word set when that wait gives up
+};
+
+// One unit of work of a CTA: substeps [subBegin, subEnd) of one body's frame.  Most pieces are whole
+// frames.  A frame is a sequential chain of `substeps` units, so dealing WHOLE bodies to the CTAs
+// quantises the kernel time to ceil(bodies / CTAs) body-frames (512 bodies on 148 SMs: 4 instead of
+// 3.46, i.e. 13.5 % idle -- what capped the strong scaling at 8 GPUs).  Instead the body-major
+// sequence of (body, substep) units is cut into one equal share per CTA; a body that straddles a cut
+// is stepped by two CTAs: the first runs its head substeps FIRST, stores the state (positions,
+// velocities, lambdas: exactly what a frame end stores) and stamps pieceDone[body]; the second runs its
+// tail substeps LAST, after polling the stamp -- by then the head has long been done, so nobody waits.
+// Results are bit-identical to stepping the frame in one piece (the state at a substep boundary is the
+// state the next frame would start from).
+struct BatchPiece {
+  uint32_t body, subBegin, subEnd;
+  uint32_t flags;   // bit 0: wait for pieceDone[body] before loading, bit 1: set it after storing
 };
 
 // LANES: threads cooperating on one tet (1, 2, 4: bit-identical results); FAST: PBD_FLAG_FAST_ARITH forms
@@ -81,8 +104,23 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
   }
   __syncthreads();
   uint32_t parity = 0;
-  for (uint32_t b = blockIdx.x; b < P.nBodies; b += gridDim.x) {
+  for (uint32_t pi = P.pieceBegin[blockIdx.x]; pi < P.pieceBegin[blockIdx.x + 1]; ++pi) {
+    const BatchPiece piece = P.pieces[pi];
+    const uint32_t b = piece.body;
     const BodyDesc c = P.bodies[b];
+    if (piece.flags & 1u) {   // tail piece: the head piece (another CTA) must have stored the body's state
+      if (tid == 0) {
+        uint32_t polls = 0;
+        long long t0 = 0;
+        while ((int)(ld_acquire(P.pieceDone + b) - P.frameStamp) < 0) {
+          if ((++polls & 1023u) == 0u) {
+            if (polls == 1024u) t0 = clock64();
+            else if (clock64() - t0 > P.spinLimit) { *reinterpret_cast<volatile unsigned*>(P.abortHost) = 1u; __threadfence_system(); break; }
+          }
+        }
+      }
+      __syncthreads();
+    }
     if (tid == 0) {
       mbar_expect_tx(&mbar, c.staticBytes + c.edgeLamBytes + c.tetLamBytes);
       bulk_load(smem, P.blob + c.blobOff, c.staticBytes, &mbar);
@@ -92,10 +130,10 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
     while (!mbar_try_wait(&mbar, parity)) {}
     parity ^= 1u;
     const TileHdr h = *reinterpret_cast<const TileHdr*>(smem);
-    // predict of the first substep while the vertices are loaded
+    // predict of the piece's first substep while the vertices are loaded
     for (uint32_t i = tid; i < h.vertCount; i += nth) sv[i] = load_transform(P, k, h.vertBegin + i, LOAD_PREDICT, false);
     __syncthreads();
-    for (uint32_t sub = 0; sub < P.substeps; ++sub) {
+    for (uint32_t sub = piece.subBegin; sub < piece.subEnd; ++sub) {
       for (uint32_t it = 0; it < P.iterations; ++it) {
         if (it != 0) {   // ground clamp that closes the previous iteration
           for (uint32_t i = tid; i < h.vertCount; i += nth) { float4 p = sv[i]; ground_vertex(p, k); sv[i] = p; }
@@ -104,7 +142,7 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
         sweep_edges<FAST>(h, 0, svOff, k.alphaEdge, nullptr);
         sweep_tets<LANES, FAST>(h, 0, svOff, k.alphaTet, nullptr);
       }
-      const bool last = sub + 1 == P.substeps;
+      const bool last = sub + 1 == piece.subEnd;
       for (uint32_t i = tid; i < h.vertCount; i += nth) {
         const uint32_t s = h.vertBegin + i;
         float4 p = sv[i], x = __ldcg(P.prev + s), v;
@@ -128,7 +166,13 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
       if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, smem + h.offEdgeLam, c.edgeLamBytes);
       if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, smem + h.offTetLam, c.tetLamBytes);
       bulk_commit();
-      bulk_wait_read();   // the buffer is overwritten by the next body
+      if (piece.flags & 2u) {   // head piece of a split body: everything it stored is visible before the stamp
+        bulk_wait_all();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        st_release(P.pieceDone + b, P.frameStamp);
+      } else {
+        bulk_wait_read();       // the buffer is overwritten by the next body
+      }
     }
     __syncthreads();
   }
@@ -165,6 +209,13 @@ struct pbd_batch {
   bool pending = false;
   uint32_t lanes = 1;
   bool fast = false;
+  BatchPiece* pieces = nullptr;        // the CTAs' work lists (see BatchPiece)
+  uint32_t* pieceBegin = nullptr;
+  unsigned* pieceDone = nullptr;
+  uint32_t frameStamp = 0, nSplit = 0;
+  unsigned* abortHost = nullptr;       // mapped host word + its device alias (bounded wait of a tail piece)
+  unsigned* abortHostDev = nullptr;
+  long long spinLimit = 0;
   const void* kernel() const {
     if (fast) return (const void*)batch_frame_kernel<1, true>;
     return lanes == 2 ? (const void*)batch_frame_kernel<2, false>
@@ -174,6 +225,8 @@ struct pbd_batch {
   ~pbd_batch() {
     cudaFree(d.pos); cudaFree(d.prev); cudaFree(d.vel); cudaFree(d.edgeLam); cudaFree(d.tetLam);
     cudaFree(d.packed); cudaFree(d.consts); cudaFree(blob); cudaFree(bodies);
+    cudaFree(pieces); cudaFree(pieceBegin); cudaFree(pieceDone);
+    if (abortHost) cudaFreeHost(abortHost);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -367,6 +420,39 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
   if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, B->kernel(), 512, B->smemBytes)) != cudaSuccess) return cbail(ce, "occupancy");
   if (perSM < 1) { bfail(PBD_ERR_UNSUPPORTED, "batch kernel does not fit on an SM", status); return nullptr; }
   B->grid = std::max(1u, std::min(nBodies, (uint32_t)(perSM * prop.multiProcessorCount)));
+  {
+    // work lists: the body-major sequence of (body, substep) units cut into one equal share per CTA (see BatchPiece)
+    const uint32_t S = params->substeps > 1u ? params->substeps : 1u, G = B->grid;
+    const uint64_t U = (uint64_t)nBodies * S;
+    std::vector<BatchPiece> pieces;
+    std::vector<uint32_t> begin(G + 1, 0);
+    const bool split = getenv("PBD_BATCH_NOSPLIT") == nullptr;   // debug switch: whole bodies, dealt round-robin
+    for (uint32_t c = 0; c < G; ++c) {
+      begin[c] = (uint32_t)pieces.size();
+      if (!split) {
+        for (uint32_t b = c; b < nBodies; b += G) pieces.push_back({b, 0u, S, 0u});
+        continue;
+      }
+      const uint64_t u0 = U * c / G, u1 = U * (c + 1) / G;
+      const uint32_t bFirst = (uint32_t)(u0 / S), sFirst = (uint32_t)(u0 % S);     // body the share starts in, at substep sFirst
+      const uint32_t bLast = (uint32_t)(u1 / S), sLast = (uint32_t)(u1 % S);       // body it ends in, before substep sLast
+      if (sLast != 0 && bLast < nBodies) { pieces.push_back({bLast, 0u, sLast, 2u}); ++B->nSplit; }   // head of a split body: first
+      for (uint32_t b = bFirst + (sFirst ? 1u : 0u); b < bLast; ++b) pieces.push_back({b, 0u, S, 0u});
+      if (sFirst != 0) pieces.push_back({bFirst, sFirst, S, 1u});                                      // tail of a split body: last
+    }
+    begin[G] = (uint32_t)pieces.size();
+    if ((ce = upload_vec(&B->pieces, pieces, B->bytes)) != cudaSuccess) return cbail(ce, "upload pieces");
+    if ((ce = upload_vec(&B->pieceBegin, begin, B->bytes)) != cudaSuccess) return cbail(ce, "upload pieceBegin");
+    if ((ce = cudaMalloc((void**)&B->pieceDone, sizeof(unsigned) * ((size_t)nBodies + 1))) != cudaSuccess) return cbail(ce, "cudaMalloc pieceDone");
+    if ((ce = cudaMemset(B->pieceDone, 0, sizeof(unsigned) * ((size_t)nBodies + 1))) != cudaSuccess) return cbail(ce, "memset pieceDone");
+    if ((ce = cudaHostAlloc((void**)&B->abortHost, 64, cudaHostAllocMapped)) != cudaSuccess) return cbail(ce, "cudaHostAlloc");
+    *B->abortHost = 0u;
+    if ((ce = cudaHostGetDevicePointer((void**)&B->abortHostDev, B->abortHost, 0)) != cudaSuccess) return cbail(ce, "cudaHostGetDevicePointer");
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    const char* e = getenv("PBD_SPIN_LIMIT_MS");
+    B->spinLimit = (long long)((e ? atof(e) : 10000.0) * (double)std::max(khz, 1000000));
+  }
   if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return cbail(ce, "cudaDeviceSynchronize");
   B->uploadMs = wall_ms() - tUp;
   return B.release();
@@ -383,8 +469,11 @@ int pbd_batch_step_async(pbd_batch* b, float dt, uint32_t frames) {
   P.edgeLam = b->d.edgeLam; P.tetLam = b->d.tetLam; P.consts = b->d.consts;
   P.nBodies = b->nBodies; P.substeps = b->params.substeps > 1u ? b->params.substeps : 1u; P.iterations = b->params.iterations;
   P.recStride = b->recStride;
+  P.pieces = b->pieces; P.pieceBegin = b->pieceBegin; P.pieceDone = b->pieceDone;
+  P.spinLimit = b->spinLimit; P.abortHost = b->abortHostDev;
   BCU(cudaEventRecord(b->ev0, b->stream));
   for (uint32_t f = 0; f < frames; ++f) {
+    P.frameStamp = ++b->frameStamp;
     if (b->nBodies) {
       void* args[] = {&P};
       BCU(cudaLaunchKernel(b->kernel(), dim3(b->grid), dim3(512), args, b->smemBytes, b->stream));
@@ -406,6 +495,10 @@ int pbd_batch_sync(pbd_batch* b, double* device_ms) {
     *device_ms = ms;
   }
   b->pending = false;
+  if (b->abortHost && *reinterpret_cast<volatile unsigned*>(b->abortHost) != 0u) {
+    *b->abortHost = 0u;
+    return bfail(PBD_ERR_CUDA, "a tail piece waited longer than PBD_SPIN_LIMIT_MS for the head piece of its body; the state is invalid");
+  }
   return PBD_OK;
 }
 

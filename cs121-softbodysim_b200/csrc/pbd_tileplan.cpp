@@ -58,6 +58,7 @@ struct PlanKnobs {
   int snapLevels;        // PBD_PLAN_NOSNAP=n         k-d levels whose cuts are NOT gap-snapped (default 4)
   int capMargin;         // PBD_PLAN_CAPM=n           tile balance: cap = p99 load - n (default 1)
   int tabu;              // PBD_PLAN_TABU=n           tabu-search iterations per class (-1: built-in budgets)
+  int minTile;           // PBD_PLAN_MINTILE=n        smallest tile (vertices) before fewer SMs are used instead (default 1024)
 };
 const PlanKnobs& knobs() {
   static const PlanKnobs k = [] {
@@ -74,6 +75,7 @@ const PlanKnobs& knobs() {
     q.snapLevels = num("PBD_PLAN_NOSNAP", 4);
     q.capMargin = num("PBD_PLAN_CAPM", 1);
     q.tabu = num("PBD_PLAN_TABU", -1);
+    q.minTile = std::max(32, num("PBD_PLAN_MINTILE", 1024));
     return q;
   }();
   return k;
@@ -1135,7 +1137,14 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   const uint32_t perSmPlan = opts.tiles_per_sm ? opts.tiles_per_sm
                              : (((opts.flags & PBD_FLAG_TAGGED_HANDOVER) && opts.shard_world <= 1 && !opts.tile_vertices &&
                                  (uint64_t)m.V >= (uint64_t)nSMs * 1024u) ? 2u : 1u);
-  const uint32_t blockThreads = opts.block_threads ? opts.block_threads : (perSmPlan >= 2 ? 256u : 512u);
+  // smallest tile before fewer SMs are used instead.  With done counters a tile below ~1024 vertices is all
+  // hand-over; the tagged hand-over is cheap enough that 256-vertex tiles on more SMs win (measured on the
+  // 100k-tet body: 6,280 -> 8,430 substeps/s, 19 -> 75 tiles per partition)
+  const uint32_t minTileAuto = getenv("PBD_PLAN_MINTILE") ? (uint32_t)knobs().minTile
+                               : ((opts.flags & PBD_FLAG_TAGGED_HANDOVER) && opts.shard_world <= 1 ? 256u : 1024u);
+  const bool smallTiles = !opts.tile_vertices && perSmPlan == 1 &&
+                          (uint64_t)m.V / std::max<uint64_t>(1, std::min<uint64_t>(nSMs, m.V / std::max(1u, minTileAuto))) < 640u;
+  const uint32_t blockThreads = opts.block_threads ? opts.block_threads : ((perSmPlan >= 2 || smallTiles) ? 256u : 512u);
   if (blockThreads % 32 || blockThreads > 512) { err = "block_threads must be a multiple of 32, <= 512"; return false; }
   plan.blockThreads = blockThreads;
   plan.tilesPerSm = perSmPlan;
@@ -1181,7 +1190,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     K1 = std::max(1u, (m.V + opts.tile_vertices - 1) / opts.tile_vertices);
   } else {
     const uint32_t perSm = perSmPlan;
-    const uint32_t minTile = 1024 / perSm;   // below this a tile is all interface: use fewer SMs instead
+    const uint32_t minTile = std::max(32u, minTileAuto / perSm);   // below this a tile is all interface: use fewer SMs instead
     K1 = std::max(1u, std::min(nSMs * perSm, m.V / std::max(1u, minTile)));
     // large bodies: enough tiles (whole waves) that a tile fits in shared memory, estimated from the
     // bytes a tile visit needs (16 B/vertex + double-buffered records, 12 B/edge and 16 B/tet, of
