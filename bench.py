@@ -485,7 +485,7 @@ def measure_body(ctx, args, workload, mode, sharded, cpu_baseline, steps=None, s
     V, E, T = len(x0), len(edges), len(tets)
     S, I = w["substeps"], w["iterations"]
     prm = capi.SolverParams.default(substeps=S, iterations=I)
-    tagged = (not args.no_tagged) and not sharded and args.backend != "stream"
+    tagged = (not args.no_tagged) and args.backend != "stream"
     flags = (capi.FLAG_FAST_ARITH if mode == "fast" else 0) | (capi.FLAG_TAGGED_HANDOVER if tagged else 0)
     opt = capi.Options(backend={"auto": 0, "stream": 1, "tile": 2}[args.backend],
                        order_mode={"strict": 0, "interleaved": 1, "riding": 2}[args.order],
@@ -611,11 +611,11 @@ def measure_body(ctx, args, workload, mode, sharded, cpu_baseline, steps=None, s
         "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "V": V, "E": E, "T": T, "substeps_per_frame": S, "iterations": I,
-                   "dt": DT, "backend": name, "order_mode": args.order, "hand_over": "tagged 128-bit {x,y,z,tag} words" if tagged else "release/acquire done counters",
+                   "dt": DT, "backend": name, "order_mode": args.order, "hand_over": "tagged 128-bit {x,y,z,tag} words" if "tagged" in name else "release/acquire done counters",
                    "lanes_per_tet": info.get("lanes_per_tet"), "partitions": info.get("partitions"),
                    "parallelism": ("1 GPU" if world == 1 else
                                    f"ONE body across {world} GPUs: tiles read/write other ranks' vertices in place over NVLink "
-                                   "(peer memory, CUDA IPC), per-tile release/acquire counters at system scope; no NCCL on the data path"
+                                   "(peer memory, CUDA IPC; system-scope tagged words or release/acquire counters); no NCCL on the data path"
                                    if sharded else f"{world} independent bodies, one per GPU, no collective"),
                    "l2": "not flushed" if flush is None else "flushed between timed frames (256 MiB memset, untimed)",
                    "preroll_frames": args.preroll, "working_set_bytes": info["device_bytes"]},

@@ -141,29 +141,34 @@ __device__ __forceinline__ void grid_barrier(const TileParams& P, unsigned* coun
 // phase covering every vertex exactly once, expects 2*seq (the visit before it); the commit pass at
 // the end of a frame writes 2*seqEnd + 1, which is what the first visit of the next frame expects.
 // Tags are compared for equality only, so the 32-bit wrap is harmless.
-__device__ __forceinline__ uint4 ld_tagged(const uint4* p) {
+// `sys`: the word may live on / be written from another GPU of the node (one body across several GPUs):
+// system scope, STG/LDG.E.128.STRONG.SYS over NVLink; one GPU: gpu scope.
+__device__ __forceinline__ uint4 ld_tagged(const uint4* p, bool sys) {
   unsigned __int128 v;
-  asm volatile("ld.relaxed.gpu.global.b128 %0, [%1];" : "=q"(v) : "l"(p) : "memory");
+  if (sys) asm volatile("ld.relaxed.sys.global.b128 %0, [%1];" : "=q"(v) : "l"(p) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.b128 %0, [%1];" : "=q"(v) : "l"(p) : "memory");
   return make_uint4((uint32_t)v, (uint32_t)(v >> 32), (uint32_t)(v >> 64), (uint32_t)(v >> 96));
 }
-__device__ __forceinline__ void st_tagged(uint4* p, float4 q, uint32_t tag) {
+__device__ __forceinline__ void st_tagged(uint4* p, float4 q, uint32_t tag, bool sys) {
   const unsigned __int128 v = (unsigned __int128)__float_as_uint(q.x) | ((unsigned __int128)__float_as_uint(q.y) << 32) |
                               ((unsigned __int128)__float_as_uint(q.z) << 64) | ((unsigned __int128)tag << 96);
-  asm volatile("st.relaxed.gpu.global.b128 [%0], %1;" ::"l"(p), "q"(v) : "memory");
+  if (sys) asm volatile("st.relaxed.sys.global.b128 [%0], %1;" ::"l"(p), "q"(v) : "memory");
+  else asm volatile("st.relaxed.gpu.global.b128 [%0], %1;" ::"l"(p), "q"(v) : "memory");
 }
 __device__ __forceinline__ float4 tagged_value(uint4 r, float w) {
   return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), w);
 }
-__device__ __forceinline__ float4 tagged_wait_load(const TileParams& P, uint32_t s, uint32_t expect, float w) {
+__device__ __forceinline__ float4 tagged_wait_load(const TileParams& P, const uint4* word, uint32_t expect, float w) {
   SpinGuard g;
   uint4 r;
-  do { r = ld_tagged(P.posT + s); } while (r.w != expect && !spin_expired(g, P));
+  const bool sys = P.world > 1;
+  do { r = ld_tagged(word, sys); } while (r.w != expect && !spin_expired(g, P));
   return tagged_value(r, w);
 }
 __device__ __forceinline__ float4 tagged_load_any(const TileParams& P, uint32_t s) {   // own earlier write: no wait
-  return tagged_value(ld_tagged(P.posT + s), __ldg(P.invMass + s));
+  return tagged_value(ld_tagged(P.posT + s, P.world > 1), __ldg(P.invMass + s));
 }
-__device__ __forceinline__ void tagged_store(uint4* posT, uint32_t s, float4 p, uint32_t tag) { st_tagged(posT + s, p, tag); }
+__device__ __forceinline__ void tagged_store(const TileParams& P, uint4* word, float4 p, uint32_t tag) { st_tagged(word, p, tag, P.world > 1); }
 
 // vertex-only pass over the phase-0 partition (no constraints): used when there is nothing to
 // sweep and for the final commit.  finalCommit: ground (if clamp) + commit, no predict.
@@ -178,21 +183,21 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
     for (uint32_t s = b + threadIdx.x; s < e; s += blockDim.x) {
       if (finalCommit) {
         float4 p, x = __ldcg(P.prev + s), v;
-        if (TAGGED) p = waitTag ? tagged_wait_load(P, s, waitTag, __ldg(P.invMass + s)) : tagged_load_any(P, s);
+        if (TAGGED) p = waitTag ? tagged_wait_load(P, P.posT + s, waitTag, __ldg(P.invMass + s)) : tagged_load_any(P, s);
         else p = __ldcg(P.pos + s);
         if (clamp) { ground_vertex(p, k); if (P.nColliders) collide_vertex(p, P.colliders, P.nColliders); }
         commit_vertex(p, x, v, k);
         v.w = 0.0f;
         __stcg(P.prev + s, x);
         __stcg(P.vel + s, v);
-        if (TAGGED) tagged_store(P.posT, s, p, writeTag); else __stcg(P.pos + s, p);
+        if (TAGGED) tagged_store(P, P.posT + s, p, writeTag); else __stcg(P.pos + s, p);
       } else if (TAGGED) {
         VertexIn in;
         in.p = tagged_load_any(P, s);
         in.x = in.v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (mode == LOAD_PREDICT || mode == LOAD_COMMIT_PREDICT) in.x = __ldcg(P.prev + s);
         if (mode == LOAD_PREDICT) in.v = __ldcg(P.vel + s);
-        tagged_store(P.posT, s, finish_vertex(P, k, s, mode, clamp, in), writeTag);
+        tagged_store(P, P.posT + s, finish_vertex(P, k, s, mode, clamp, in), writeTag);
       } else {
         const float4 p = load_transform(P, k, s, mode, clamp);
         __stcg(P.pos + s, p);
@@ -342,12 +347,16 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
               float w[3];
               VertexIn in[3];
               uint32_t slot[3];
+              const uint4* word[3];
 #pragma unroll
               for (int u = 0; u < 3; ++u) {
                 const uint32_t i = base + u * nth + tid;
                 if (i < h.vertCount) {
-                  slot[u] = contiguous ? h.vertBegin + i : (vidx[i] & 0x0fffffffu);
-                  raw[u] = ld_tagged(P.posT + slot[u]);
+                  // gathered tiles: the word lives on the rank that owns the vertex (entry bits 28..31), read in place
+                  const uint32_t e = contiguous ? 0u : vidx[i];
+                  slot[u] = contiguous ? h.vertBegin + i : (e & 0x0fffffffu);
+                  word[u] = (contiguous ? P.posT : reinterpret_cast<const uint4*>(posPeerS[e >> 28])) + slot[u];
+                  raw[u] = ld_tagged(word[u], multi);
                   w[u] = __ldg(P.invMass + slot[u]);
                   in[u].x = in[u].v = make_float4(0.f, 0.f, 0.f, 0.f);
                   if (mode == LOAD_PREDICT || mode == LOAD_COMMIT_PREDICT) in[u].x = __ldcg(P.prev + slot[u]);
@@ -358,7 +367,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
               for (int u = 0; u < 3; ++u) {
                 const uint32_t i = base + u * nth + tid;
                 if (i < h.vertCount) {
-                  in[u].p = raw[u].w == expectTag ? tagged_value(raw[u], w[u]) : tagged_wait_load(P, slot[u], expectTag, w[u]);
+                  in[u].p = raw[u].w == expectTag ? tagged_value(raw[u], w[u]) : tagged_wait_load(P, word[u], expectTag, w[u]);
                   sv[i] = finish_vertex(P, k, slot[u], mode, true, in[u]);   // (mode != LOAD_PLAIN only on contiguous home tiles)
                 }
               }
@@ -438,8 +447,10 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
               bulk_commit();
             }
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
-            for (uint32_t i = tid; i < h.vertCount; i += nth)
-              tagged_store(P.posT, contiguous ? h.vertBegin + i : (vidx[i] & 0x0fffffffu), sv[i], writeTag);
+            for (uint32_t i = tid; i < h.vertCount; i += nth) {
+              const uint32_t e = contiguous ? 0u : vidx[i];
+              tagged_store(P, (contiguous ? P.posT + h.vertBegin + i : reinterpret_cast<uint4*>(posPeerS[e >> 28]) + (e & 0x0fffffffu)), sv[i], writeTag);
+            }
             buf ^= 1u;
             j = jn;
             ++item;
@@ -448,8 +459,10 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           }
           if (TAGGED) {
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
-            for (uint32_t i = tid; i < h.vertCount; i += nth)
-              tagged_store(P.posT, contiguous ? h.vertBegin + i : (vidx[i] & 0x0fffffffu), sv[i], writeTag);
+            for (uint32_t i = tid; i < h.vertCount; i += nth) {
+              const uint32_t e = contiguous ? 0u : vidx[i];
+              tagged_store(P, (contiguous ? P.posT + h.vertBegin + i : reinterpret_cast<uint4*>(posPeerS[e >> 28]) + (e & 0x0fffffffu)), sv[i], writeTag);
+            }
           } else if (contiguous) {
             for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + h.vertBegin + i, sv[i]);
           } else {
@@ -522,11 +535,11 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
 // float4 positions <-> tagged words (upload / host reads only)
 __global__ void to_tagged_kernel(const float4* pos, uint4* posT, float* invMass, uint32_t n, uint32_t tag) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { const float4 p = pos[i]; st_tagged(posT + i, p, tag); invMass[i] = p.w; }
+  if (i < n) { const float4 p = pos[i]; st_tagged(posT + i, p, tag, false); invMass[i] = p.w; }
 }
 __global__ void from_tagged_kernel(const uint4* posT, float4* pos, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) pos[i] = tagged_value(ld_tagged(posT + i), pos[i].w);   // pos keeps the inverse mass it was uploaded with
+  if (i < n) pos[i] = tagged_value(ld_tagged(posT + i, true), pos[i].w);   // pos keeps the inverse mass it was uploaded with
 }
 
 class TileBackend final : public Backend {
@@ -848,7 +861,7 @@ class TileBackend final : public Backend {
     // ---- tagged hand-over (experimental): one GPU, one thread per tet, and every phase must cover
     // every vertex exactly once (then a vertex's previous writer is always the previous visit)
     tagged_ = false;
-    if ((opts_.flags & PBD_FLAG_TAGGED_HANDOVER) && world_ == 1 && lanes_ == 1 && !plan.phases.empty()) {
+    if ((opts_.flags & PBD_FLAG_TAGGED_HANDOVER) && lanes_ == 1 && !plan.phases.empty()) {
       bool full = true;
       for (const Phase& ph : plan.phases) {
         uint64_t covered = 0;
@@ -863,6 +876,7 @@ class TileBackend final : public Backend {
       bytes_ += (sizeof(uint4) + sizeof(float)) * (size_t)plan.V;
       to_tagged_kernel<<<(plan.V + 255) / 256, 256>>>(d.pos, posT_, invMass_, plan.V, 2u * (iterBase_ * nPhases_) + 1u);   // the frame-start tag
       if ((err = cudaGetLastError()) != cudaSuccess) return err;
+      posPeers_[rank_] = reinterpret_cast<float4*>(posT_);   // what peers map and address: the tagged words (same 16 B per vertex)
     }
 
     const void* fn = kernel();

@@ -1135,13 +1135,13 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   // MEMBAR.GPU stalls the whole SM's memory pipeline)
   if (nSMs == 0) nSMs = 148;
   const uint32_t perSmPlan = opts.tiles_per_sm ? opts.tiles_per_sm
-                             : (((opts.flags & PBD_FLAG_TAGGED_HANDOVER) && opts.shard_world <= 1 && !opts.tile_vertices &&
+                             : (((opts.flags & PBD_FLAG_TAGGED_HANDOVER) && !opts.tile_vertices &&
                                  (uint64_t)m.V >= (uint64_t)nSMs * 1024u) ? 2u : 1u);
   // smallest tile before fewer SMs are used instead.  With done counters a tile below ~1024 vertices is all
   // hand-over; the tagged hand-over is cheap enough that 256-vertex tiles on more SMs win (measured on the
   // 100k-tet body: 6,280 -> 8,430 substeps/s, 19 -> 75 tiles per partition)
   const uint32_t minTileAuto = getenv("PBD_PLAN_MINTILE") ? (uint32_t)knobs().minTile
-                               : ((opts.flags & PBD_FLAG_TAGGED_HANDOVER) && opts.shard_world <= 1 ? 256u : 1024u);
+                               : ((opts.flags & PBD_FLAG_TAGGED_HANDOVER) ? 256u : 1024u);   // (the same for every rank of a sharded body and for its single-GPU twin: plans must be identical)
   const bool smallTiles = !opts.tile_vertices && perSmPlan == 1 &&
                           (uint64_t)m.V / std::max<uint64_t>(1, std::min<uint64_t>(nSMs, m.V / std::max(1u, minTileAuto))) < 640u;
   const uint32_t blockThreads = opts.block_threads ? opts.block_threads : ((perSmPlan >= 2 || smallTiles) ? 256u : 512u);

@@ -50,8 +50,9 @@ def test_unlaunched_peer_rank_times_out_instead_of_hanging(capi, meshgen, monkey
         s.close()
 
 
+@pytest.mark.parametrize("flags", [0, 4], ids=["counters", "tagged"])
 @pytest.mark.parametrize("mesh,order", [("kuhn12", "interleaved"), ("kuhn12", "strict"), ("icosphere001", "riding")])
-def test_two_rank_shard_on_one_gpu_bit_exact(mesh, order, capi, po, meshgen, golden):
+def test_two_rank_shard_on_one_gpu_bit_exact(mesh, order, flags, capi, po, meshgen, golden):
     """The sharded-body path (tiles of rank r read / write vertices owned by rank 1-r in place, done
     counters at system scope) exercised on ONE GPU: both ranks' cooperative kernels are small enough to
     be co-resident on device 0 and are launched on their own streams.  Bit-identical to the single-handle
@@ -62,10 +63,12 @@ def test_two_rank_shard_on_one_gpu_bit_exact(mesh, order, capi, po, meshgen, gol
         m = golden(f"mesh_{mesh}.npz")
         x0, edges, tets = meshgen.place_body(m["vertices"], lowest_y=1.0), m["edges"], m["tets"]
     om = {"strict": capi.ORDER_STRICT, "interleaved": capi.ORDER_INTERLEAVED, "riding": capi.ORDER_RIDING}[order]
-    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=om, tile_vertices=150, plan_sms=8)
+    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=om, tile_vertices=0 if flags & 4 else 150, plan_sms=8, flags=flags)   # (the tagged hand-over needs the regular partitions: every phase covers every vertex)
     prm = capi.SolverParams.default(substeps=4)
     single = capi.Body(prm, x0, edges, tets, device=0, options=opt)
     shards = capi.sharded_bodies_one_process(prm, x0, edges, tets, devices=[0, 0], options=opt)
+    if flags & 4 and mesh.startswith("kuhn"):
+        assert "tagged" in shards[0].name() and "tagged" in single.name()   # (a plan with residual phases falls back to the counters)
     owner = capi.shard_owner(shards[0])
     assert set(np.unique(owner)) == {0, 1}
     ora = po.Oracle(po.Params.default(substeps=4), x0, edges, tets, kind="port")

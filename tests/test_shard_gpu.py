@@ -12,8 +12,9 @@ def _need_two(capi):
         pytest.skip("needs two GPUs")
 
 
+@pytest.mark.parametrize("flags", [0, 4], ids=["counters", "tagged"])
 @pytest.mark.parametrize("mesh,order", [("kuhn12", "interleaved"), ("kuhn12", "strict"), ("icosphere001", "interleaved")])
-def test_two_gpu_shard_bit_exact_vs_single_gpu_and_oracle(mesh, order, capi, po, meshgen, golden):
+def test_two_gpu_shard_bit_exact_vs_single_gpu_and_oracle(mesh, order, flags, capi, po, meshgen, golden):
     _need_two(capi)
     if mesh.startswith("kuhn"):
         x0, tets, edges = meshgen.kuhn_grid(int(mesh[4:]))
@@ -22,10 +23,12 @@ def test_two_gpu_shard_bit_exact_vs_single_gpu_and_oracle(mesh, order, capi, po,
         x0, edges, tets = meshgen.place_body(m["vertices"], lowest_y=1.0), m["edges"], m["tets"]
     om = capi.ORDER_INTERLEAVED if order == "interleaved" else capi.ORDER_STRICT
     # small tiles so that both GPUs own several tiles of every phase and many tiles straddle the cut
-    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=om, tile_vertices=150, plan_sms=8)
+    opt = capi.Options(backend=capi.BACKEND_TILE, order_mode=om, tile_vertices=0 if flags & 4 else 150, plan_sms=8, flags=flags)   # (the tagged hand-over needs the regular partitions: every phase covers every vertex)
     prm = capi.SolverParams.default(substeps=4)
     single = capi.Body(prm, x0, edges, tets, device=0, options=opt)
     shards = capi.sharded_bodies_one_process(prm, x0, edges, tets, devices=[0, 1], options=opt)
+    if flags & 4 and mesh.startswith("kuhn"):
+        assert "tagged" in shards[0].name() and "tagged" in single.name()
     owner = capi.shard_owner(shards[0])
     assert set(np.unique(owner)) == {0, 1}
     for a, b in zip(single.schedule_order(), shards[1].schedule_order()):
