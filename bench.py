@@ -394,6 +394,7 @@ def main():
     ap.add_argument("--no-splits", action="store_true", help="N > 1: skip the batch4096 / sharded-body sub-records")
     ap.add_argument("--split-body", default="big8m", choices=["big8m", "big32m"],
                     help="N > 1: the body of the sharded sub-record (big32m = BASELINE configs[4]; planning it takes minutes)")
+    ap.add_argument("--plan-sms", type=int, default=0, help="plan for this many SMs (0 = the device's SM count x ranks of a sharded body)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed frames")
     args = ap.parse_args()
@@ -490,7 +491,8 @@ def measure_body(ctx, args, workload, mode, sharded, cpu_baseline, steps=None, s
     opt = capi.Options(backend={"auto": 0, "stream": 1, "tile": 2}[args.backend],
                        order_mode={"strict": 0, "interleaved": 1, "riding": 2}[args.order],
                        block_threads=args.block_threads, tile_vertices=args.tile_vertices,
-                       lanes_per_tet=args.lanes, partitions=args.partitions, tiles_per_sm=args.tiles_per_sm, flags=flags)
+                       lanes_per_tet=args.lanes, partitions=args.partitions, tiles_per_sm=args.tiles_per_sm, flags=flags,
+                       plan_sms=args.plan_sms)
 
     t0 = time.perf_counter()
     check = None

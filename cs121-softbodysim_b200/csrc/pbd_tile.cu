@@ -158,17 +158,16 @@ __device__ __forceinline__ void st_tagged(uint4* p, float4 q, uint32_t tag, bool
 __device__ __forceinline__ float4 tagged_value(uint4 r, float w) {
   return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), w);
 }
-__device__ __forceinline__ float4 tagged_wait_load(const TileParams& P, const uint4* word, uint32_t expect, float w) {
+__device__ __forceinline__ float4 tagged_wait_load(const TileParams& P, const uint4* word, uint32_t expect, float w, bool sys) {
   SpinGuard g;
   uint4 r;
-  const bool sys = P.world > 1;
   do { r = ld_tagged(word, sys); } while (r.w != expect && !spin_expired(g, P));
   return tagged_value(r, w);
 }
 __device__ __forceinline__ float4 tagged_load_any(const TileParams& P, uint32_t s) {   // own earlier write: no wait
   return tagged_value(ld_tagged(P.posT + s, P.world > 1), __ldg(P.invMass + s));
 }
-__device__ __forceinline__ void tagged_store(const TileParams& P, uint4* word, float4 p, uint32_t tag) { st_tagged(word, p, tag, P.world > 1); }
+__device__ __forceinline__ void tagged_store(uint4* word, float4 p, uint32_t tag, bool sys) { st_tagged(word, p, tag, sys); }
 
 // vertex-only pass over the phase-0 partition (no constraints): used when there is nothing to
 // sweep and for the final commit.  finalCommit: ground (if clamp) + commit, no predict.
@@ -183,21 +182,21 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
     for (uint32_t s = b + threadIdx.x; s < e; s += blockDim.x) {
       if (finalCommit) {
         float4 p, x = __ldcg(P.prev + s), v;
-        if (TAGGED) p = waitTag ? tagged_wait_load(P, P.posT + s, waitTag, __ldg(P.invMass + s)) : tagged_load_any(P, s);
+        if (TAGGED) p = waitTag ? tagged_wait_load(P, P.posT + s, waitTag, __ldg(P.invMass + s), P.world > 1) : tagged_load_any(P, s);
         else p = __ldcg(P.pos + s);
         if (clamp) { ground_vertex(p, k); if (P.nColliders) collide_vertex(p, P.colliders, P.nColliders); }
         commit_vertex(p, x, v, k);
         v.w = 0.0f;
         __stcg(P.prev + s, x);
         __stcg(P.vel + s, v);
-        if (TAGGED) tagged_store(P, P.posT + s, p, writeTag); else __stcg(P.pos + s, p);
+        if (TAGGED) tagged_store(P.posT + s, p, writeTag, P.world > 1); else __stcg(P.pos + s, p);
       } else if (TAGGED) {
         VertexIn in;
         in.p = tagged_load_any(P, s);
         in.x = in.v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (mode == LOAD_PREDICT || mode == LOAD_COMMIT_PREDICT) in.x = __ldcg(P.prev + s);
         if (mode == LOAD_PREDICT) in.v = __ldcg(P.vel + s);
-        tagged_store(P, P.posT + s, finish_vertex(P, k, s, mode, clamp, in), writeTag);
+        tagged_store(P.posT + s, finish_vertex(P, k, s, mode, clamp, in), writeTag, P.world > 1);
       } else {
         const float4 p = load_transform(P, k, s, mode, clamp);
         __stcg(P.pos + s, p);
@@ -313,6 +312,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           unsigned char* rec = smem + recOff;
           const TileHdr h = *reinterpret_cast<const TileHdr*>(rec);
           const bool contiguous = (h.flags & 1u) != 0u;
+          const bool sysScope = multi && (h.flags & 2u) != 0u;   // this tile exchanges data with another GPU
           // tagged hand-over: what this visit expects in its vertices and what it leaves in them
           const uint32_t seq = (P.iterBase + sub * P.iterations + it) * P.nPhases + ph;
           const uint32_t expectTag = (sub == 0 && it == 0 && ph == 0) ? 2u * seq + 1u : 2u * seq;
@@ -352,11 +352,11 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
               for (int u = 0; u < 3; ++u) {
                 const uint32_t i = base + u * nth + tid;
                 if (i < h.vertCount) {
-                  // gathered tiles: the word lives on the rank that owns the vertex (entry bits 28..31), read in place
-                  const uint32_t e = contiguous ? 0u : vidx[i];
-                  slot[u] = contiguous ? h.vertBegin + i : (e & 0x0fffffffu);
-                  word[u] = (contiguous ? P.posT : reinterpret_cast<const uint4*>(posPeerS[e >> 28])) + slot[u];
-                  raw[u] = ld_tagged(word[u], multi);
+                  // every load is LOCAL: whoever wrote the vertex last stored it into this rank's array (push model;
+                  // the rank bits of a gathered-slot entry name the destination of this tile's own store)
+                  slot[u] = contiguous ? h.vertBegin + i : (vidx[i] & 0x0fffffffu);
+                  word[u] = P.posT + slot[u];
+                  raw[u] = ld_tagged(word[u], sysScope);
                   w[u] = __ldg(P.invMass + slot[u]);
                   in[u].x = in[u].v = make_float4(0.f, 0.f, 0.f, 0.f);
                   if (mode == LOAD_PREDICT || mode == LOAD_COMMIT_PREDICT) in[u].x = __ldcg(P.prev + slot[u]);
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
               for (int u = 0; u < 3; ++u) {
                 const uint32_t i = base + u * nth + tid;
                 if (i < h.vertCount) {
-                  in[u].p = raw[u].w == expectTag ? tagged_value(raw[u], w[u]) : tagged_wait_load(P, word[u], expectTag, w[u]);
+                  in[u].p = raw[u].w == expectTag ? tagged_value(raw[u], w[u]) : tagged_wait_load(P, word[u], expectTag, w[u], sysScope);
                   sv[i] = finish_vertex(P, k, slot[u], mode, true, in[u]);   // (mode != LOAD_PLAIN only on contiguous home tiles)
                 }
               }
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
             for (uint32_t i = tid; i < h.vertCount; i += nth) {
               const uint32_t e = contiguous ? 0u : vidx[i];
-              tagged_store(P, (contiguous ? P.posT + h.vertBegin + i : reinterpret_cast<uint4*>(posPeerS[e >> 28]) + (e & 0x0fffffffu)), sv[i], writeTag);
+              tagged_store((contiguous ? P.posT + h.vertBegin + i : reinterpret_cast<uint4*>(posPeerS[e >> 28]) + (e & 0x0fffffffu)), sv[i], writeTag, sysScope);
             }
             buf ^= 1u;
             j = jn;
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
             for (uint32_t i = tid; i < h.vertCount; i += nth) {
               const uint32_t e = contiguous ? 0u : vidx[i];
-              tagged_store(P, (contiguous ? P.posT + h.vertBegin + i : reinterpret_cast<uint4*>(posPeerS[e >> 28]) + (e & 0x0fffffffu)), sv[i], writeTag);
+              tagged_store((contiguous ? P.posT + h.vertBegin + i : reinterpret_cast<uint4*>(posPeerS[e >> 28]) + (e & 0x0fffffffu)), sv[i], writeTag, sysScope);
             }
           } else if (contiguous) {
             for (uint32_t i = tid; i < h.vertCount; i += nth) __stcg(P.pos + h.vertBegin + i, sv[i]);
@@ -567,6 +567,19 @@ class TileBackend final : public Backend {
     fast_ = (opts_.flags & PBD_FLAG_FAST_ARITH) != 0u;
     if (fast_) lanes_ = 1;   // the fast forms exist for one thread per constraint
 
+    // ---- tagged hand-over: one thread per tet, and every phase must cover every vertex exactly once
+    // (then a vertex's previous writer is always the previous visit)
+    tagged_ = false;
+    if ((opts_.flags & PBD_FLAG_TAGGED_HANDOVER) && lanes_ == 1 && !plan.phases.empty()) {
+      bool full = true;
+      for (const Phase& ph : plan.phases) {
+        uint64_t covered = 0;
+        for (uint32_t ti = ph.tileBegin; ti < ph.tileBegin + ph.tileCount; ++ti) covered += plan.tiles[ti].vertCount;
+        full &= covered == plan.V;   // tiles of one phase are vertex-disjoint
+      }
+      tagged_ = full;
+    }
+
     // rest values are already on the device at the plan's device indices (pbd_capi.cu)
     std::vector<float> eRest(plan.edgeDevCount), tRest(plan.tetDevCount);
     if (plan.edgeDevCount && (err = cudaMemcpy(eRest.data(), d.edgeRest, sizeof(float) * plan.edgeDevCount, cudaMemcpyDeviceToHost)) != cudaSuccess) return err;
@@ -654,12 +667,49 @@ class TileBackend final : public Backend {
     std::vector<TileCopy> copies(plan.tiles.size());
     std::vector<unsigned char> blob;
     uint32_t recMax = 64;
+    // Tagged hand-over across GPUs: PUSH model.  A tile stores each vertex into the memory of the rank
+    // that reads it NEXT (the owner of the tile that holds the vertex in the following phase), so every
+    // load -- and every retry while a tag is not there yet -- is local; only posted 16-byte stores cross
+    // NVLink (a remote load is a ~2 us round trip on the consumer's critical path, a remote store is not
+    // waited for by anyone).  The rank bits of a gathered-slot entry then name the DESTINATION rank of the
+    // store, and home tiles carry a slot list too (their vertices scatter to several ranks).
+    const bool pushModel = tagged_ && world_ > 1;
+    std::vector<uint8_t> destRank;   // [phase * V + slot]
+    if (pushModel) {
+      const size_t nPh = plan.phases.size();
+      std::vector<uint32_t> tileIn(nPh * (size_t)plan.V, 0);
+      for (size_t ph = 0; ph < nPh; ++ph)
+        for (uint32_t ti = plan.phases[ph].tileBegin; ti < plan.phases[ph].tileBegin + plan.phases[ph].tileCount; ++ti) {
+          const Tile& t = plan.tiles[ti];
+          for (uint32_t i = 0; i < t.vertCount; ++i)
+            tileIn[ph * plan.V + (t.contiguous ? t.vertBegin + i : plan.tileVerts[t.vertBegin + i])] = ti;
+        }
+      destRank.resize(nPh * (size_t)plan.V);
+      for (size_t ph = 0; ph < nPh; ++ph)
+        for (uint32_t sl = 0; sl < plan.V; ++sl) destRank[ph * plan.V + sl] = tileOwner[tileIn[((ph + 1) % nPh) * plan.V + sl]];
+      // system scope only for the tiles that exchange words with another GPU (flags bit 1): a tile whose
+      // vertices were last written by a tile of another rank, or that stores into another rank's memory
+      std::fill(remote.begin(), remote.end(), (uint8_t)0);
+      for (size_t ph = 0; ph < nPh; ++ph)
+        for (uint32_t ti = plan.phases[ph].tileBegin; ti < plan.phases[ph].tileBegin + plan.phases[ph].tileCount; ++ti) {
+          const Tile& t = plan.tiles[ti];
+          for (uint32_t i = 0; i < t.vertCount && !remote[ti]; ++i) {
+            const uint32_t sl = t.contiguous ? t.vertBegin + i : plan.tileVerts[t.vertBegin + i];
+            const uint32_t writer = tileIn[((ph + nPh - 1) % nPh) * plan.V + sl];
+            remote[ti] = tileOwner[writer] != tileOwner[ti] || destRank[ph * plan.V + sl] != tileOwner[ti];
+          }
+        }
+    }
+    std::vector<uint32_t> phaseOfTile(plan.tiles.size(), 0);
+    for (size_t ph = 0; ph < plan.phases.size(); ++ph)
+      for (uint32_t ti = plan.phases[ph].tileBegin; ti < plan.phases[ph].tileBegin + plan.phases[ph].tileCount; ++ti) phaseOfTile[ti] = (uint32_t)ph;
     for (size_t ti = 0; ti < plan.tiles.size(); ++ti) {
       const Tile& t = plan.tiles[ti];
-      const uint32_t nVG = t.contiguous ? 0u : t.vertCount;
+      const bool asRange = t.contiguous && !pushModel;   // the kernel walks the slot range [vertBegin, +vertCount) itself
+      const uint32_t nVG = asRange ? 0u : t.vertCount;
       TileHdr h{};
       const uint32_t nPred = useFlags_ ? (uint32_t)preds[ti].size() : 0u;
-      h.vertCount = t.vertCount; h.flags = (t.contiguous ? 1u : 0u) | (remote[ti] ? 2u : 0u) | (t.mixed ? 4u : 0u) | (t.ride ? 8u : 0u) | (nPred << 8); h.vertBegin = t.contiguous ? t.vertBegin : 0u;
+      h.vertCount = t.vertCount; h.flags = (asRange ? 1u : 0u) | (remote[ti] ? 2u : 0u) | (t.mixed ? 4u : 0u) | (t.ride ? 8u : 0u) | (nPred << 8); h.vertBegin = asRange ? t.vertBegin : 0u;
       h.nEdgeGroups = t.edgeGroupCount; h.nTetGroups = t.tetGroupCount; h.nEdges = t.edgeCount; h.nTets = t.tetCount;
       // planner invariants the sweeps rely on (pbd_sweep.cuh projects a colour group in ONE pass of the
       // block and would silently drop the rest): fail loudly instead
@@ -696,8 +746,8 @@ class TileBackend final : public Backend {
       if (nVG) {
         uint32_t* vi = reinterpret_cast<uint32_t*>(b + h.offVertIdx);
         for (uint32_t q = 0; q < nVG; ++q) {
-          const uint32_t sl = plan.tileVerts[t.vertBegin + q];
-          vi[q] = sl | (owner_of_slot(sl) << 28);
+          const uint32_t sl = t.contiguous ? t.vertBegin + q : plan.tileVerts[t.vertBegin + q];
+          vi[q] = sl | ((pushModel ? (uint32_t)destRank[(size_t)phaseOfTile[ti] * plan.V + sl] : owner_of_slot(sl)) << 28);
         }
       }
       uint32_t* eg = reinterpret_cast<uint32_t*>(b + h.offEdgeGroups);
@@ -858,18 +908,6 @@ class TileBackend final : public Backend {
       cudaMemset(ftrace_, 0, sizeof(long long) * 256 * (nPhases_ + 1));
     }
 
-    // ---- tagged hand-over (experimental): one GPU, one thread per tet, and every phase must cover
-    // every vertex exactly once (then a vertex's previous writer is always the previous visit)
-    tagged_ = false;
-    if ((opts_.flags & PBD_FLAG_TAGGED_HANDOVER) && lanes_ == 1 && !plan.phases.empty()) {
-      bool full = true;
-      for (const Phase& ph : plan.phases) {
-        uint64_t covered = 0;
-        for (uint32_t ti = ph.tileBegin; ti < ph.tileBegin + ph.tileCount; ++ti) covered += plan.tiles[ti].vertCount;
-        full &= covered == plan.V;   // tiles of one phase are vertex-disjoint
-      }
-      tagged_ = full;
-    }
     if (tagged_) {
       if ((err = cudaMalloc((void**)&posT_, sizeof(uint4) * ((size_t)plan.V + 1))) != cudaSuccess) return err;
       if ((err = cudaMalloc((void**)&invMass_, sizeof(float) * ((size_t)plan.V + 1))) != cudaSuccess) return err;

@@ -1199,6 +1199,14 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     const double need = 16.0 * m.V + 2.0 * (12.0 * m.E + 16.0 * m.T) / 4.0;
     const uint32_t byBytes = (uint32_t)std::ceil(1.25 * need / (double)smemBytes);
     if (byBytes > K1) K1 = ((byBytes + nSMs - 1) / nSMs) * nSMs;
+    // Two tiles per SM only pay while two record-block pairs fit an SM: bodies larger than one wave keep
+    // the tile size of the one-wave case (~640 vertices) and take more waves instead of growing the
+    // tiles until one barely fits (measured on the 8.4M-tet body, one GPU: 729 -> 775 substeps/s, and the
+    // plan for 2 x 148 SMs 572 -> what two GPUs need to scale)
+    if (perSm >= 2) {
+      const uint32_t wave = nSMs * perSm, bySize = (m.V + 639u) / 640u;
+      if (bySize > K1) K1 = ((bySize + wave - 1) / wave) * wave;
+    }
   }
 
   std::vector<uint32_t> localOf(m.V, NONE), scratch;

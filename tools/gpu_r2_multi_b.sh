@@ -6,6 +6,4 @@ run() { name=$1; shift
   python -c "import json; d=json.load(open('gpurun_out/q.json')); print('N=$N $name', d['config']['backend'], round(d['value'],1), 'frac', round(d['roofline']['frac'],4), 'sane', d['sane'])" || tail -5 gpurun_out/q.err
 }
 run big8m_tagged --workload big8m --arith fast
-run big8m_counters --workload big8m --arith fast --no-tagged
 run big8m_tagged_exact --workload big8m --arith exact
-run headline_tagged --arith fast
