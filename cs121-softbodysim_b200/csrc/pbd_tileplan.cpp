@@ -59,6 +59,7 @@ struct PlanKnobs {
   int capMargin;         // PBD_PLAN_CAPM=n           tile balance: cap = p99 load - n (default 1)
   int tabu;              // PBD_PLAN_TABU=n           tabu-search iterations per class (-1: built-in budgets)
   int minTile;           // PBD_PLAN_MINTILE=n        smallest tile (vertices) before fewer SMs are used instead (default 1024)
+  int riders;            // PBD_PLAN_RIDERS=n         PBD_ORDER_RIDING: most riders per tet (1 or 2, default 2)
 };
 const PlanKnobs& knobs() {
   static const PlanKnobs k = [] {
@@ -76,6 +77,7 @@ const PlanKnobs& knobs() {
     q.capMargin = num("PBD_PLAN_CAPM", 1);
     q.tabu = num("PBD_PLAN_TABU", -1);
     q.minTile = std::max(32, num("PBD_PLAN_MINTILE", 1024));
+    q.riders = num("PBD_PLAN_RIDERS", 2);
     return q;
   }();
   return k;
@@ -1633,7 +1635,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
         // passes 0, 1: a host without a rider yet (edges with <= 2 candidates first, then the rest);
         // pass 2: a host whose rider is the opposite edge
         std::vector<uint8_t> codeOf((size_t)m.T * 2, 0);
-        for (int pass = 0; pass < 3; ++pass)
+        for (int pass = 0; pass < (knobs().riders >= 2 ? 3 : 2); ++pass)
           for (uint32_t e = 0; e < m.E; ++e) {
             if (hostOf[e] != NONE || sets[0].at(e)[0] == sets[0].at(e)[1]) continue;
             size_t lo, hi;
