@@ -392,6 +392,7 @@ def main():
     ap.add_argument("--preroll", type=int, default=30, help="untimed frames before warm-up (past first ground contact)")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-splits", action="store_true", help="N > 1: skip the batch4096 / sharded-body sub-records")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the config1 / config2 sub-records")
     ap.add_argument("--split-body", default="big8m", choices=["big8m", "big32m"],
                     help="N > 1: the body of the sharded sub-record (big32m = BASELINE configs[4]; planning it takes minutes)")
     ap.add_argument("--plan-sms", type=int, default=0, help="plan for this many SMs (0 = the device's SM count x ranks of a sharded body)")
@@ -448,6 +449,18 @@ def main():
             line["alt"] = {arith[1]: {"value": o["value"], "unit": o["unit"], "ms_per_step": o["ms_per_step"],
                                       "roofline_frac": o["roofline"]["frac"], "e2e": o["e2e"]["value"], "backend": o["config"]["backend"],
                                       "frame_ms": o["frame_ms"], "arithmetic": ARITH_DOC[arith[1]], "sane": o["sane"]}}
+    # ---- the smaller BASELINE configs next to the headline (N = 1): configs[0] (default mesh) and configs[1] (100k tets)
+    if world == 1 and args.workload == "headline" and not args.no_extra and args.backend != "stream":
+        extra = {}
+        for wl in ("config1", "config2"):
+            try:
+                r = measure_body(ctx, args, wl, arith[0], False, cpu_baseline=False, steps=max(3, args.steps // 2), sustained=False)
+                extra[wl] = {"value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"], "roofline_frac": r["roofline"]["frac"],
+                             "e2e": r["e2e"]["value"], "backend": r["config"]["backend"], "workload": r["config"]["workload"],
+                             "schedule": r["schedule"], "sane": r["sane"], "arithmetic": arith[0]}
+            except Exception as e:
+                extra[wl] = {"error": repr(e)}
+        line["extra"] = extra
     # ---- the two splits BASELINE.json's north_star names, measured in the same launch when N > 1
     if world > 1 and not sharded and args.workload == "headline" and not args.no_splits:
         sub = {}

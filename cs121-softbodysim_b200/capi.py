@@ -32,7 +32,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PBD_B200_LIB") or os.path.join(HERE, "libpbd_b200.so")
 
 PBD_OK, PBD_ERR_INVALID, PBD_ERR_INDEX, PBD_ERR_NO_DEVICE, PBD_ERR_CUDA, PBD_ERR_OOM, PBD_ERR_UNSUPPORTED = range(7)
-BACKEND_AUTO, BACKEND_STREAM, BACKEND_TILE = 0, 1, 2
+BACKEND_AUTO, BACKEND_STREAM, BACKEND_TILE, BACKEND_JACOBI = 0, 1, 2, 3
 ORDER_STRICT, ORDER_INTERLEAVED, ORDER_RIDING = 0, 1, 2
 FLAG_STAGE_TIMING, FLAG_NO_GRAPH, FLAG_TAGGED_HANDOVER, FLAG_FAST_ARITH = 1, 2, 4, 8
 ARRAY_INV_MASS, ARRAY_EDGE_REST, ARRAY_TET_REST, ARRAY_EDGE_LAMBDA, ARRAY_TET_LAMBDA, ARRAY_VELOCITY, ARRAY_XSTAR = range(7)
@@ -91,7 +91,8 @@ class Options(C.Structure):
                 ("flags", C.c_uint32), ("tile_vertices", C.c_uint32), ("block_threads", C.c_uint32),
                 ("max_phases", C.c_uint32), ("partitions", C.c_uint32), ("lanes_per_tet", C.c_uint32),
                 ("tiles_per_sm", C.c_uint32), ("shard_world", C.c_uint32), ("shard_rank", C.c_uint32),
-                ("plan_sms", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("plan_sms", C.c_uint32), ("jacobi_edge_stiffness", C.c_float), ("jacobi_volume_stiffness", C.c_float),
+                ("reserved", C.c_uint32 * 1)]
 
     def __init__(self, **kw):
         super().__init__()

@@ -53,6 +53,7 @@ class Backend {
   virtual cudaError_t enqueue_frame(const DeviceArrays& d, const FrameShape& f, cudaStream_t s) = 0;
   virtual uint32_t launches_per_frame(const FrameShape& f) const = 0;
   virtual void invalidate() {}
+  virtual void set_omega(float) {}   // SOR factor (Jacobi comparison backend: pbd_params.omega)
   virtual void debug_dump() {}  // PBD_TILE_TRACE: per-phase timing of the last frame to stderr  // frame shape changed (set_params)
   virtual uint64_t device_bytes() const = 0;
   virtual void fill_info(pbd_info& info) const {}
@@ -74,6 +75,7 @@ class Backend {
 
 Backend* make_stream_backend(uint32_t flags, uint32_t blockThreads);
 Backend* make_tile_backend(const pbd_options& opts, int device);
+Backend* make_jacobi_backend(const pbd_options& opts);
 
 // shared vertex-stage kernels (pbd_stream.cu)
 cudaError_t launch_pack(const DeviceArrays& d, cudaStream_t s);

@@ -131,6 +131,21 @@ bool build_plan(const MeshView& m, const pbd_options& o, int nSMs, uint32_t smem
     return true;
   }
   if (backend == PBD_BACKEND_TILE) return build_tile_plan(m, o, (uint32_t)nSMs, smemBytes, plan, err);
+  if (backend == PBD_BACKEND_JACOBI) {
+    // no schedule: every vertex gathers its own constraints; caller's order throughout
+    plan = Plan();
+    plan.V = m.V; plan.E = m.E; plan.T = m.T;
+    plan.backend = PBD_BACKEND_JACOBI;
+    plan.edgeOrder.resize(m.E); plan.tetOrder.resize(m.T); plan.edgeDev.resize(m.E); plan.tetDev.resize(m.T);
+    for (uint32_t k = 0; k < m.E; ++k) plan.edgeOrder[k] = plan.edgeDev[k] = k;
+    for (uint32_t k = 0; k < m.T; ++k) plan.tetOrder[k] = plan.tetDev[k] = k;
+    plan.edgeDevCount = m.E; plan.tetDevCount = m.T;
+    plan.slotToVertex.resize(m.V); plan.vertexToSlot.resize(m.V);
+    for (uint32_t i = 0; i < m.V; ++i) plan.slotToVertex[i] = plan.vertexToSlot[i] = i;
+    plan.edgePhase.assign(m.E, 0); plan.edgeTile.assign(m.E, 0); plan.edgeColor.assign(m.E, 0);
+    plan.tetPhase.assign(m.T, 0); plan.tetTile.assign(m.T, 0); plan.tetColor.assign(m.T, 0);
+    return true;
+  }
   err = "unknown backend";
   return false;
 }
@@ -256,7 +271,9 @@ pbd_handle* pbd_create(const pbd_params* params, uint32_t V, uint32_t E, uint32_
     if ((ce = cudaMemset(d.tetLam, 0, sizeof(float) * (nT + 1))) != cudaSuccess) return bail(ce, "memset tetLam");
   }
   if (plan.backend == PBD_BACKEND_STREAM) h->be.reset(make_stream_backend(h->opts.flags, h->opts.block_threads));
+  else if (plan.backend == PBD_BACKEND_JACOBI) h->be.reset(make_jacobi_backend(h->opts));
   else h->be.reset(make_tile_backend(h->opts, device));
+  h->be->set_omega(h->params.omega);
   if (!h->be) { fail(PBD_ERR_UNSUPPORTED, "backend not available", status); return nullptr; }
   if ((ce = h->be->upload(plan, m, d)) != cudaSuccess) return bail(ce, "backend upload");
   if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return bail(ce, "cudaDeviceSynchronize");
@@ -422,6 +439,7 @@ int pbd_set_params(pbd_handle* h, const pbd_params* p) {
   CU(onDevice.err);
   CU(cudaStreamSynchronize(h->stream));
   h->params = *p;
+  h->be->set_omega(p->omega);
   h->be->invalidate();
   return PBD_OK;
 }

@@ -83,7 +83,11 @@ typedef struct pbd_step_stats {
   double predictMs, solveMs, commitMs, packMs, totalMs;
 } pbd_step_stats;
 
-enum { PBD_BACKEND_AUTO = 0, PBD_BACKEND_STREAM = 1, PBD_BACKEND_TILE = 2 };
+enum { PBD_BACKEND_AUTO = 0, PBD_BACKEND_STREAM = 1, PBD_BACKEND_TILE = 2,
+       PBD_BACKEND_JACOBI = 3 /* comparison schedule, NOT the PBDServer algorithm: the Jacobi + SOR gather solver of the
+                                 reference's in-engine path (SoftBodySolver.cs:379-527, SoftBodyCompute.compute:229-389):
+                                 two grid-wide phases per constraint type and iteration, stiffness in [0,1] instead of
+                                 XPBD compliance, SOR factor = pbd_params.omega (the reference default there is 1.4) */ };
 enum { PBD_ORDER_STRICT = 0, PBD_ORDER_INTERLEAVED = 1, PBD_ORDER_RIDING = 2 };
 enum {
   PBD_FLAG_STAGE_TIMING = 1u << 0, /* stream backend: no CUDA graph, CUDA events per stage   */
@@ -126,7 +130,9 @@ typedef struct pbd_options {
   uint32_t shard_world;    /* one body across several GPUs of a node: number of ranks (0/1 = off) */
   uint32_t shard_rank;     /* ... and which of them this handle is                               */
   uint32_t plan_sms;       /* plan for this many SMs, 0 = the device's SM count x shard_world     */
-  uint32_t reserved[3];
+  float jacobi_edge_stiffness;    /* PBD_BACKEND_JACOBI: edgeStiffness (0 = the reference default 0.9)    */
+  float jacobi_volume_stiffness;  /* PBD_BACKEND_JACOBI: volumeStiffness (0 = the reference default 0.98) */
+  uint32_t reserved[1];
 } pbd_options;
 
 typedef struct pbd_info {

@@ -223,3 +223,108 @@ def residuals(pos, x0, edges, tets, ground_y=0.0):
         "min_y_dynamic": float(pos[used, 1].min() - ground_y) if used.any() else 0.0,
         "finite": bool(np.isfinite(pos).all()),
     }
+
+
+# ---------------------------------------------------------------- Jacobi + SOR comparison schedule (test infrastructure)
+
+def jacobi_reference(params: "Params", x0, edges, tets, frames: int, dt: float, edge_k=0.9, tet_k=0.98, omega=None, pinned=None):
+    """numpy float32 restatement of the reference's in-engine gather solver (SoftBodySolver.cs:379-527 ==
+    SoftBodyCompute.compute:229-389) on top of the PBDServer integrator (predict / ground / commit, Sim.cpp:178-222)
+    and PBDServer's inverse masses: what PBD_BACKEND_JACOBI computes.  Every operation is a float32 numpy op in the
+    kernels' order (products rounded, sums left to right, per-vertex accumulation in ascending constraint order), so the
+    GPU result can be compared bit for bit.  Returns positions [V,3] float32."""
+    f = np.float32
+    x = np.ascontiguousarray(x0, dtype=np.float32).reshape(-1, 3).copy()
+    edges = np.ascontiguousarray(edges, dtype=np.int64).reshape(-1, 2)
+    tets = np.ascontiguousarray(tets, dtype=np.int64).reshape(-1, 4)
+    V = len(x)
+    ora = Oracle(params, x, edges.astype(np.uint32), tets.astype(np.uint32), pinned=pinned, kind="port")
+    w, e_rest, t_rest = ora.get(GET_W), ora.get(GET_EDGE_REST), ora.get(GET_TET_REST)
+    ora.close()
+    omega = f(params.omega if omega is None else omega)
+    ss = max(1, int(params.substeps))
+    sdt = f(f(dt) / f(ss))
+    inv_dt = f(1.0) / sdt if sdt > 1e-12 else f(0.0)
+    g = np.array([params.gx, params.gy, params.gz], np.float32) * sdt
+    fr = f(1.0) - f(min(max(params.friction, 0.0), 1.0))
+    v = np.zeros_like(x)
+    dyn = w != 0
+
+    def dot(a, b):
+        return (a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]) + a[:, 2] * b[:, 2]
+
+    def cross(a, b):
+        return np.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1], a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2], a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], 1)
+
+    def apply(p, vert, contrib, valid):
+        # per-vertex accumulation in ascending constraint order, then p += (omega / cnt) * sum
+        order = np.lexsort((np.arange(len(vert)), vert))
+        order = order[valid[order]]
+        s = np.zeros((V, 3), np.float32)
+        for k in range(3):
+            np.add.at(s[:, k], vert[order], contrib[order, k])
+        cnt = np.bincount(vert[order], minlength=V)
+        m = (cnt > 0) & dyn
+        fac = (omega / cnt[m].astype(np.float32)).astype(np.float32)
+        p[m] = p[m] + fac[:, None] * s[m]
+
+    for _ in range(frames):
+        for _ in range(ss):
+            v[dyn] = v[dyn] + g
+            p = x.copy()
+            p[dyn] = x[dyn] + v[dyn] * sdt
+            for _ in range(int(params.iterations)):
+                if len(edges):
+                    vert = np.concatenate([edges[:, 0], edges[:, 1]])           # constraint e seen from a, then from b
+                    other = np.concatenate([edges[:, 1], edges[:, 0]])
+                    eidx = np.concatenate([np.arange(len(edges))] * 2)
+                    wi, wj = w[vert], w[other]
+                    ws = wi + wj
+                    d = p[vert] - p[other]
+                    len2 = dot(d, d)
+                    valid = (wi != 0) & (ws != 0) & ~(len2 < 1e-18)
+                    with np.errstate(all="ignore"):
+                        ln = np.sqrt(len2)
+                        lam = f(-edge_k) * ((ln - e_rest[eidx]) / ws)
+                        contrib = (d / ln[:, None]) * (lam * wi)[:, None]
+                    order_key = eidx * 2                                           # adjacency order = ascending edge index
+                    o = np.lexsort((order_key, vert))
+                    apply_sorted = (vert[o], contrib[o], valid[o])
+                    apply(p, *apply_sorted)
+                if len(tets):
+                    pa, pb, pc, pd = (p[tets[:, k]] for k in range(4))
+                    wa, wb, wc, wd = (w[tets[:, k]] for k in range(4))
+                    six = f(6.0)
+                    ga = cross(pd - pb, pc - pb) / six
+                    gb = cross(pc - pa, pd - pa) / six
+                    gc = cross(pd - pa, pb - pa) / six
+                    n = cross(pb - pa, pc - pa)
+                    gd = n / six
+                    wsum = ((wa * dot(ga, ga) + wb * dot(gb, gb)) + wc * dot(gc, gc)) + wd * dot(gd, gd)
+                    massive = (((wa + wb) + wc) + wd) != 0
+                    ok = massive & ~(wsum < 1e-20)
+                    with np.errstate(all="ignore"):
+                        vol = dot(n, pd - pa) / six
+                        lam = f(-tet_k) * ((vol - t_rest) / wsum)
+                    vert = np.concatenate([tets[:, k] for k in range(4)])
+                    grads = np.concatenate([ga, gb, gc, gd])
+                    wrole = np.concatenate([wa, wb, wc, wd])
+                    lam4 = np.concatenate([lam] * 4)
+                    valid = np.concatenate([ok] * 4) & (wrole != 0) & (w[vert] != 0)
+                    contrib = grads * (lam4 * wrole)[:, None]
+                    tidx = np.concatenate([np.arange(len(tets))] * 4)
+                    o = np.lexsort((tidx, vert))
+                    apply(p, vert[o], contrib[o], valid[o])
+                if params.groundEnabled:
+                    low = dyn & (p[:, 1] < f(params.groundY))
+                    p[low, 1] = f(params.groundY)
+            vel = (p - x) * inv_dt
+            if params.groundEnabled:
+                c = dyn & (p[:, 1] <= f(params.groundY) + f(1e-6))
+                vel[c, 0] = vel[c, 0] * fr
+                vel[c, 2] = vel[c, 2] * fr
+                vel[c, 1] = np.maximum(vel[c, 1], f(0.0))
+            v[dyn] = vel[dyn]
+            v[~dyn] = 0
+            x[dyn] = p[dyn]
+    return x
