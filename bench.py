@@ -652,15 +652,20 @@ def measure_body(ctx, args, workload, mode, sharded, cpu_baseline, steps=None, s
                                           "lanes_per_tet", "launches_per_frame", "grid_blocks", "block_threads")},
         "sane": sane,
     }
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    per_sm = max(1, -(-info["grid_blocks"] // sm_count))                  # resident CTAs per SM
+    sms_used = max(1, info["grid_blocks"] // per_sm)
     if prof.get("warp_instructions"):
         # second roofline: issue slots.  warp-instructions per frame (ncu smsp__inst_executed.sum of the committed capture
-        # of this kernel) / (SMs that run a CTA x 4 schedulers x cycles of the frame at the sampled SM clock)
+        # of this kernel) / (SMs that run CTAs x 4 schedulers x cycles of the frame at the sampled SM clock)
         cyc = frame_ms * 1e-3 * sm_mhz * 1e6
-        line["roofline"]["issue_slot_frac"] = prof["warp_instructions"] / (info["grid_blocks"] * 4 * cyc)
+        line["roofline"]["issue_slot_frac"] = prof["warp_instructions"] / (sms_used * 4 * cyc)
         line["roofline"]["issue_slot_source"] = prof.get("source")
     if prof.get("smem_wavefronts"):
+        # third: the shared-memory data pipe, one wavefront per cycle and SM (what bounds the colour sweeps)
         cyc = frame_ms * 1e-3 * sm_mhz * 1e6
-        line["roofline"]["smem_pipe_frac"] = prof["smem_wavefronts"] / (info["grid_blocks"] * cyc)
+        line["roofline"]["smem_pipe_frac"] = prof["smem_wavefronts"] / (sms_used * cyc)
+        line["roofline"]["sms_used"] = sms_used
     if sus:
         line["sustained"] = sus
     if check is not None:
