@@ -70,6 +70,8 @@ struct BatchParams {
   uint32_t frameStamp;      // this frame's stamp (counts frames, wrap-safe compare)
   long long spinLimit;      // bounded wait (cycles) of a tail piece for its head piece
   unsigned* abortHost;      // mapped host word set when that wait gives up
+  uint32_t* stageHost;      // mapped host memory, 4 words per CTA: cycles of thread 0 in (predict loads, fused
+                            // commit+predict stages, final commit stages, the whole frame) -> pbd_step_stats
 };
 
 // One unit of work of a CTA: substeps [subBegin, subEnd) of one body's frame.  Most pieces are whole
@@ -104,6 +106,8 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
   }
   __syncthreads();
   uint32_t parity = 0;
+  __shared__ uint32_t stageS[4];   // per-stage cycle accounting (thread 0), see BatchParams::stageHost
+  if (tid == 0) { stageS[0] = stageS[1] = stageS[2] = 0u; stageS[3] = (uint32_t)clock64(); }
   for (uint32_t pi = P.pieceBegin[blockIdx.x]; pi < P.pieceBegin[blockIdx.x + 1]; ++pi) {
     const BatchPiece piece = P.pieces[pi];
     const uint32_t b = piece.body;
@@ -131,8 +135,10 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
     parity ^= 1u;
     const TileHdr h = *reinterpret_cast<const TileHdr*>(smem);
     // predict of the piece's first substep while the vertices are loaded
+    if (tid == 0) stageS[0] -= (uint32_t)clock64();
     for (uint32_t i = tid; i < h.vertCount; i += nth) sv[i] = load_transform(P, k, h.vertBegin + i, LOAD_PREDICT, false);
     __syncthreads();
+    if (tid == 0) stageS[0] += (uint32_t)clock64();
     for (uint32_t sub = piece.subBegin; sub < piece.subEnd; ++sub) {
       for (uint32_t it = 0; it < P.iterations; ++it) {
         if (it != 0) {   // ground clamp that closes the previous iteration
@@ -143,6 +149,7 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
         sweep_tets<LANES, FAST>(h, 0, svOff, k.alphaTet, nullptr);
       }
       const bool last = sub + 1 == piece.subEnd;
+      if (tid == 0) stageS[last ? 2 : 1] -= (uint32_t)clock64();
       for (uint32_t i = tid; i < h.vertCount; i += nth) {
         const uint32_t s = h.vertBegin + i;
         float4 p = sv[i], x = __ldcg(P.prev + s), v;
@@ -159,6 +166,7 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
         __stcg(P.vel + s, v);
       }
       __syncthreads();
+      if (tid == 0) stageS[last ? 2 : 1] += (uint32_t)clock64();
     }
     fence_async_smem();
     __syncthreads();
@@ -176,7 +184,13 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
     }
     __syncthreads();
   }
-  if (tid == 0) bulk_wait_all();
+  if (tid == 0) {
+    bulk_wait_all();
+    if (P.stageHost) {
+      uint32_t* o = P.stageHost + 4u * blockIdx.x;
+      o[0] = stageS[0]; o[1] = stageS[1]; o[2] = stageS[2]; o[3] = (uint32_t)clock64() - stageS[3];
+    }
+  }
 }
 
 template <class T>
@@ -215,6 +229,8 @@ struct pbd_batch {
   uint32_t frameStamp = 0, nSplit = 0;
   unsigned* abortHost = nullptr;       // mapped host word + its device alias (bounded wait of a tail piece)
   unsigned* abortHostDev = nullptr;
+  uint32_t* stageHost = nullptr;       // mapped host memory, 4 words per CTA (per-stage cycle accounting)
+  uint32_t* stageHostDev = nullptr;
   long long spinLimit = 0;
   const void* kernel() const {
     if (fast) return (const void*)batch_frame_kernel<1, true>;
@@ -227,6 +243,7 @@ struct pbd_batch {
     cudaFree(d.packed); cudaFree(d.consts); cudaFree(blob); cudaFree(bodies);
     cudaFree(pieces); cudaFree(pieceBegin); cudaFree(pieceDone);
     if (abortHost) cudaFreeHost(abortHost);
+    if (stageHost) cudaFreeHost(stageHost);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -448,6 +465,9 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
     if ((ce = cudaHostAlloc((void**)&B->abortHost, 64, cudaHostAllocMapped)) != cudaSuccess) return cbail(ce, "cudaHostAlloc");
     *B->abortHost = 0u;
     if ((ce = cudaHostGetDevicePointer((void**)&B->abortHostDev, B->abortHost, 0)) != cudaSuccess) return cbail(ce, "cudaHostGetDevicePointer");
+    if ((ce = cudaHostAlloc((void**)&B->stageHost, sizeof(uint32_t) * 4 * (size_t)std::max(1u, B->grid), cudaHostAllocMapped)) != cudaSuccess) return cbail(ce, "cudaHostAlloc");
+    memset(B->stageHost, 0, sizeof(uint32_t) * 4 * (size_t)std::max(1u, B->grid));
+    if ((ce = cudaHostGetDevicePointer((void**)&B->stageHostDev, B->stageHost, 0)) != cudaSuccess) return cbail(ce, "cudaHostGetDevicePointer");
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
     const char* e = getenv("PBD_SPIN_LIMIT_MS");
@@ -470,7 +490,7 @@ int pbd_batch_step_async(pbd_batch* b, float dt, uint32_t frames) {
   P.nBodies = b->nBodies; P.substeps = b->params.substeps > 1u ? b->params.substeps : 1u; P.iterations = b->params.iterations;
   P.recStride = b->recStride;
   P.pieces = b->pieces; P.pieceBegin = b->pieceBegin; P.pieceDone = b->pieceDone;
-  P.spinLimit = b->spinLimit; P.abortHost = b->abortHostDev;
+  P.spinLimit = b->spinLimit; P.abortHost = b->abortHostDev; P.stageHost = b->stageHostDev;
   BCU(cudaEventRecord(b->ev0, b->stream));
   for (uint32_t f = 0; f < frames; ++f) {
     P.frameStamp = ++b->frameStamp;
@@ -509,7 +529,17 @@ int pbd_batch_step(pbd_batch* b, float dt, pbd_step_stats* stats) {
   double ms = 0.0;
   rc = pbd_batch_sync(b, &ms);
   if (rc != PBD_OK) return rc;
-  if (stats) { stats->solveMs += ms; stats->totalMs += wall_ms() - t0; }
+  if (stats) {
+    // the frame is one kernel: predict / commit are shares of its device time (pbd_b200.h pbd_step_stats)
+    double a0 = 0, a1 = 0, a2 = 0, tot = 0;
+    for (uint32_t c = 0; b->stageHost && c < b->grid; ++c) {
+      const volatile uint32_t* o = b->stageHost + 4u * c;
+      a0 += o[0]; a1 += o[1]; a2 += o[2]; tot += o[3];
+    }
+    const double p = tot > 0 ? (a0 + 0.5 * a1) / tot : 0.0, cm = tot > 0 ? (0.5 * a1 + a2) / tot : 0.0;
+    stats->predictMs += ms * p; stats->commitMs += ms * cm; stats->solveMs += ms * (1.0 - p - cm);
+    stats->totalMs += wall_ms() - t0;
+  }
   return PBD_OK;
 }
 

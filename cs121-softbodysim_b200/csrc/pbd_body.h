@@ -71,6 +71,8 @@ class Backend {
   virtual cudaError_t shard_attach_pointers(uint32_t, void*, void*, int) { return cudaErrorNotSupported; }
   // optional per-stage timing (stream backend); returns false if unsupported
   virtual bool stage_ms(double& predict, double& solve, double& commit) { return false; }
+  // fused backends: the predict / commit stages as shares of the last frame's device time; false if unsupported
+  virtual bool stage_share(double& predict, double& commit) { return false; }
 };
 
 Backend* make_stream_backend(uint32_t flags, uint32_t blockThreads);

@@ -374,6 +374,7 @@ int pbd_step(pbd_handle* h, float dt, pbd_step_stats* stats) {
   if (stats) {
     double p = 0, s = 0, c = 0;
     if (h->be->stage_ms(p, s, c)) { stats->predictMs += p; stats->solveMs += s; stats->commitMs += c; }
+    else if (h->be->stage_share(p, c)) { stats->predictMs += devMs * p; stats->commitMs += devMs * c; stats->solveMs += devMs * (1.0 - p - c); }
     else stats->solveMs += devMs;
     stats->totalMs += wall_ms() - t0;
   }

@@ -21,8 +21,9 @@
 //   * one thread: the protocol has strictly one STEP in flight (PBDRemoteWorld.cs:201-246), so the
 //     reference's sim thread + condition variables (Sim.cpp:366-398) have nothing to overlap with;
 //   * the 1 Hz stats line (Sim.cpp:412-417) is kept field for field and extended with substeps/s,
-//     tet-constraints/s and algorithmic GB/s.  predict / commit are fused into the solve kernel on
-//     the GPU, so pred= and commit= print 0.000 and solve= carries the device time of the frame.
+//     tet-constraints/s and algorithmic GB/s.  predict / commit are vertex stages of the ONE frame
+//     kernel on the GPU: pred= and commit= are their shares of the frame's device time (cycle
+//     accounting in the kernel, pbd_b200.h pbd_step_stats), solve= the rest.
 //   * by default the server accepts the next client after a disconnect; --once restores the
 //     reference's "one client per process lifetime" (Net.cpp:82-93).
 //
@@ -188,10 +189,10 @@ bool serve(int fd, const Args& a) {
         const double fps = frames * 1000.0 / (now - lastPrint), n = frames;
         const double subPerS = fps * substeps;
         std::printf("[PBDServer] Mode=%s FPS %.1f | V=%u E=%u T=%u | avg(ms): total=%.3f pred=%.3f solve=%.3f commit=%.3f pack=%.3f"
-                    " | substeps/s=%.0f tet-constraints/s=%.3g GB/s=%.1f (predict/commit fused into solve)\n",
+                    " | substeps/s=%.0f tet-constraints/s=%.3g GB/s=%.1f (pred/solve/commit: shares of one fused frame kernel)\n",
                     pbd_backend_name(h), fps, info.V, info.E, info.T, acc.totalMs / n, acc.predictMs / n, acc.solveMs / n, acc.commitMs / n,
                     acc.packMs / n, subPerS, subPerS * (double)info.T * iterations,
-                    acc.solveMs > 0 ? (double)info.algorithmic_bytes_per_substep * substeps * n / (acc.solveMs * 1e-3) / 1e9 : 0.0);
+                    acc.solveMs > 0 ? (double)info.algorithmic_bytes_per_substep * substeps * n / ((acc.predictMs + acc.solveMs + acc.commitMs) * 1e-3) / 1e9 : 0.0);
         std::fflush(stdout);
         frames = 0;
         acc = pbd_step_stats{};

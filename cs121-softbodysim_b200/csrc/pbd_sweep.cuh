@@ -60,6 +60,11 @@ PBD_DEV uint2 lds_v2(uint32_t a) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
   return v;
 }
+PBD_DEV uint4 lds_v4u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
 PBD_DEV float4 lds_v4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
@@ -455,8 +460,13 @@ PBD_SWEEP_INLINE void sweep_mixed(const TileHdr& h, uint32_t rec, uint32_t svOff
     PBD_STEP_TRACE(ft, g, 0);
   }
 #else
-  for (uint32_t g = 0; g < n; ++g, eGrp += 8u, tGrp += 8u) {
-    const uint2 ge = lds_v2(eGrp), gt = lds_v2(tGrp);
+  // a mixed tile's two group tables are stored as ONE table of {edge begin, edge count, tet begin, tet count}
+  // entries (pbd_tile.cu upload; the two sections are adjacent and together exactly that large): one LDS.128
+  // per step and warp instead of two LDS.64
+  (void)tGrp;
+  for (uint32_t g = 0; g < n; ++g, eGrp += 16u) {
+    const uint4 gq = lds_v4u(eGrp);
+    const uint2 ge = make_uint2(gq.x, gq.y), gt = make_uint2(gq.z, gq.w);
     if (tid < ge.y) {
       const uint32_t o = ge.x << 2;
       project_edge_at<FAST>(sv, eIdA + o, eRestA + o, eLamA + o, alphaE);

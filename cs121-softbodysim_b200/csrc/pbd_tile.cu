@@ -90,6 +90,8 @@ struct TileParams {
   long long spinLimit;          // cycles a CTA may wait for another CTA before it gives up (bounded spins)
   unsigned* abortWord;          // device: set by the first wait that gives up; every later wait bails out at once
   unsigned* abortHost;          // mapped host word: what pbd_sync checks after the frame
+  uint32_t* stageHost;          // mapped host memory, 4 words per CTA: cycles its thread 0 spent in (predict loads,
+                                // fused commit+predict loads, final commit pass, the whole frame) -- pbd_step_stats
   uint32_t stagger;             // cycles by which every second CTA of an SM delays its sweeps (tiles_per_sm >= 2)
 };
 
@@ -268,6 +270,10 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   }
   __syncthreads();
   const uint32_t stagger = staggerS;
+  // per-stage accounting for pbd_step_stats (a16): thread 0 brackets the vertex stages that carry the reference's
+  // predict / commit work with the cycle counter, in shared memory (no registers held across the frame)
+  __shared__ uint32_t stageS[4];
+  if (tid == 0) { stageS[0] = stageS[1] = stageS[2] = 0u; stageS[3] = (uint32_t)clock64(); }
 
   // fetch the record block of this CTA's item `ji` into buffer `b` (thread 0 only)
   auto fetch = [&](uint32_t ji, uint32_t b) {
@@ -338,6 +344,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             __syncthreads();
           }
           if (ft) ft[14] = clock64();
+          if (tid == 0 && mode != LOAD_PLAIN && mode != LOAD_GROUND) stageS[mode == LOAD_PREDICT ? 0 : 1] -= (uint32_t)clock64();
           if (TAGGED) {
             // the values ARE the synchronisation: issue every load of the batch, then wait only for
             // the vertices whose tag is not there yet
@@ -403,6 +410,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             }
           }
           __syncthreads();
+          if (tid == 0 && mode != LOAD_PLAIN && mode != LOAD_GROUND) stageS[mode == LOAD_PREDICT ? 0 : 1] += (uint32_t)clock64();
           if (ft) ft[2] = clock64();
           // ---- prefetch the next tile's record block into the other buffer.  Issued here, behind the
           // barrier that ends the vertex load: every thread has finished the PREVIOUS visit's write-back
@@ -505,10 +513,18 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
     }
   }
   if (tid == 0) bulk_wait_all();
+  auto stage_report = [&](uint32_t tCommit) {   // thread 0, after the final commit pass
+    const uint32_t now = (uint32_t)clock64();
+    uint32_t* o = P.stageHost + 4u * blockIdx.x;
+    o[0] = stageS[0]; o[1] = stageS[1]; o[2] = now - tCommit; o[3] = now - stageS[3];
+  };
+  uint32_t tCommit = 0;
+  if (tid == 0) tCommit = (uint32_t)clock64();
   if (TAGGED) {
     // the final commit waits for the tag of the frame's last visit in every vertex it commits
     const uint32_t seqEnd = (P.iterBase + P.substeps * P.iterations) * P.nPhases;
     vertex_pass<true>(P, k, LOAD_PLAIN, clamp, true, 2u * seqEnd, 2u * seqEnd + 1u);
+    if (tid == 0 && P.stageHost) stage_report(tCommit);
     return;
   }
   if (P.done) {
@@ -529,7 +545,9 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
     }
     __syncthreads();
   }
+  if (tid == 0) tCommit = (uint32_t)clock64();
   vertex_pass<false>(P, k, LOAD_PLAIN, clamp, true);
+  if (tid == 0 && P.stageHost) stage_report(tCommit);
 }
 
 // float4 positions <-> tagged words (upload / host reads only)
@@ -551,6 +569,7 @@ class TileBackend final : public Backend {
     cudaFree(blob_); cudaFree(copies_); cudaFree(phases_); cudaFree(tile0Begin_); cudaFree(barrier_);
     cudaFree(trace_); cudaFree(ftrace_); cudaFree(posT_); cudaFree(invMass_);
     if (abortHost_) cudaFreeHost(abortHost_);
+    if (stageHost_) cudaFreeHost(stageHost_);
   }
   const char* name() const override {
     return tagged_ ? (fast_ ? "b200-tile-tagged-fast" : "b200-tile-tagged") : (fast_ ? "b200-tile-fast" : "b200-tile");
@@ -760,6 +779,17 @@ class TileBackend final : public Backend {
         tg[2 * g] = plan.groups[t.tetGroupBegin + g].begin - t.tetBegin;
         tg[2 * g + 1] = plan.groups[t.tetGroupBegin + g].count;
       }
+      if (t.mixed) {
+        // mixed steps read ONE table of {edge begin, edge count, tet begin, tet count} entries: the two sections
+        // are adjacent, equally long (same group count) and together hold exactly 16 bytes per step
+        if (h.offTetGroups != h.offEdgeGroups + 8u * (pad4(t.edgeGroupCount * 2) / 2) || t.edgeGroupCount != t.tetGroupCount) return cudaErrorUnknown;
+        for (uint32_t g = 0; g < t.edgeGroupCount; ++g) {
+          eg[4 * g] = plan.groups[t.edgeGroupBegin + g].begin - t.edgeBegin;
+          eg[4 * g + 1] = plan.groups[t.edgeGroupBegin + g].count;
+          eg[4 * g + 2] = plan.groups[t.tetGroupBegin + g].begin - t.tetBegin;
+          eg[4 * g + 3] = plan.groups[t.tetGroupBegin + g].count;
+        }
+      }
       uint32_t* ei = reinterpret_cast<uint32_t*>(b + h.offEdgeIdx);
       float* er = reinterpret_cast<float*>(b + h.offEdgeRest);
       for (uint32_t q = 0; q < t.edgeCount; ++q) {
@@ -950,10 +980,34 @@ class TileBackend final : public Backend {
     P.iterBase = iterBase_;
     iterBase_ += f.substeps * f.iterations;
     P.spinLimit = spinLimit_; P.abortWord = barrier_ + 64; P.abortHost = abortHostDev_;
+    if (!stageHost_) {
+      if (cudaHostAlloc((void**)&stageHost_, sizeof(uint32_t) * 4 * kStageCtas, cudaHostAllocMapped) != cudaSuccess ||
+          cudaHostGetDevicePointer((void**)&stageHostDev_, stageHost_, 0) != cudaSuccess) return cudaErrorMemoryAllocation;
+      std::memset(stageHost_, 0, sizeof(uint32_t) * 4 * kStageCtas);
+    }
+    P.stageHost = grid_ <= kStageCtas ? stageHostDev_ : nullptr;
+    stageGrid_ = grid_;
     cudaError_t err = cudaMemsetAsync(barrier_, 0, 2048, s);
     if (err != cudaSuccess) return err;
     void* args[] = {&P};
     return cudaLaunchCooperativeKernel(kernel(), dim3(grid_), dim3(block_), args, smemBytes_, s);
+  }
+
+  // pbd_step_stats (a16): the frame is ONE kernel, so the stages are shares of its device time -- cycles thread 0 of
+  // every CTA spent in the vertex stages that carry the reference's predict (PBDServer.h:75-119 predictMs) and
+  // commit work, summed over the CTAs, over the cycles of the whole frame.  A fused commit+predict stage
+  // (substeps 2..S) is charged half to each.  Valid after the frame's sync; the last frame's figures.
+  bool stage_share(double& predict, double& commit) override {
+    if (!stageHost_ || stageGrid_ == 0 || stageGrid_ > kStageCtas) return false;
+    double a0 = 0, a1 = 0, a2 = 0, tot = 0;
+    for (uint32_t c = 0; c < stageGrid_; ++c) {
+      const volatile uint32_t* o = stageHost_ + 4u * c;
+      a0 += o[0]; a1 += o[1]; a2 += o[2]; tot += o[3];
+    }
+    if (tot <= 0) return false;
+    predict = (a0 + 0.5 * a1) / tot;
+    commit = (0.5 * a1 + a2) / tot;
+    return true;
   }
 
   void debug_dump() override {
@@ -1068,6 +1122,10 @@ class TileBackend final : public Backend {
   float* invMass_ = nullptr;     // ... and the inverse masses
   unsigned* abortHost_ = nullptr;      // mapped host word + its device alias
   unsigned* abortHostDev_ = nullptr;
+  static constexpr uint32_t kStageCtas = 1024;
+  uint32_t* stageHost_ = nullptr;      // mapped host memory, 4 words per CTA (stage_share)
+  uint32_t* stageHostDev_ = nullptr;
+  uint32_t stageGrid_ = 0;
   long long spinLimit_ = 0;
   bool tagged_ = false;
   bool fast_ = false;            // PBD_FLAG_FAST_ARITH

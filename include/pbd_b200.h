@@ -76,9 +76,13 @@ typedef struct pbd_params {
 } pbd_params;
 
 /* perf::StepStats. pbd_step ADDS into these (the caller zero-initialises per frame, as
- * sim_thread_fn does, Sim.cpp:386).  The GPU path fuses predict/ground/commit into the solve
- * kernels, so solveMs carries the device time of the whole frame, predictMs/commitMs stay 0
- * unless PBD_FLAG_STAGE_TIMING is set (stream backend only), totalMs is host wall time of the call. */
+ * sim_thread_fn does, Sim.cpp:386).  The tile and batch backends run the whole frame as ONE kernel with
+ * predict / ground / commit fused into vertex stages of it: predictMs and commitMs are the frame's
+ * device time x the share of CTA cycles spent in the vertex stages that carry that work (a fused
+ * commit+predict stage between two substeps is charged half to each; the waits of the hand-over that
+ * fall inside such a stage are part of it), solveMs is the rest, so the three add up to the frame's
+ * device time.  The stream backend times its stage kernels with events under PBD_FLAG_STAGE_TIMING
+ * (otherwise everything is in solveMs).  totalMs is host wall time of the call. */
 typedef struct pbd_step_stats {
   double predictMs, solveMs, commitMs, packMs, totalMs;
 } pbd_step_stats;

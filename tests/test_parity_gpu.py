@@ -217,6 +217,41 @@ def test_stepper_mirror_reinit_and_stats(backend, capi, po, meshgen):
     st.close()
 
 
+@pytest.mark.parametrize("flags", [0, 4, 12], ids=["counters", "tagged", "tagged-fast"])
+def test_tile_step_stats_carry_predict_and_commit_shares(flags, capi, meshgen):
+    """perf::StepStats (PBDServer.h:75-119) on the fused frame kernel: predictMs / solveMs / commitMs are
+    shares of the ONE kernel's device time (cycle accounting of the vertex stages), so all three are
+    positive, they add up to the frame's device time, and the sweeps dominate."""
+    x0, tets, edges = meshgen.kuhn_grid(20)
+    body = capi.Body(capi.SolverParams.default(substeps=10), x0, edges, tets, device=0,
+                     options=_opt(capi, "tile", order_mode=capi.ORDER_INTERLEAVED, flags=flags))
+    body.step(1 / 60)
+    stats = capi.StepStats()
+    n = 5
+    for _ in range(n):
+        body.step(1 / 60, stats)
+    dev = stats.predictMs + stats.solveMs + stats.commitMs
+    assert stats.predictMs > 0 and stats.commitMs > 0 and stats.solveMs > 0
+    assert stats.predictMs + stats.commitMs < 0.5 * dev, (stats.predictMs, stats.solveMs, stats.commitMs)
+    assert dev <= stats.totalMs and dev > 0.2 * stats.totalMs
+    body.close()
+
+
+def test_batch_step_stats_carry_predict_and_commit_shares(capi, meshgen):
+    """The batch kernel's StepStats: same accounting as the tile kernel (one kernel, stage shares)."""
+    x0, tets, edges = meshgen.kuhn_grid(6)
+    bodies = [(x0, edges, tets)] * 200
+    with capi.Batch(capi.SolverParams.default(substeps=5), bodies, device=0) as batch:
+        batch.step(1 / 60)
+        stats = capi.StepStats()
+        for _ in range(3):
+            batch.step(1 / 60, stats)
+        dev = stats.predictMs + stats.solveMs + stats.commitMs
+        assert stats.predictMs > 0 and stats.commitMs > 0 and stats.solveMs > 0
+        assert stats.predictMs + stats.commitMs < 0.3 * dev, (stats.predictMs, stats.solveMs, stats.commitMs)
+        assert dev <= stats.totalMs
+
+
 FULL_SIZE_MODES = [
     # (id, backend, order, flags)            what bench.py measures is "interleaved-tagged" (alt) and "interleaved-tagged-fast" (value)
     ("stream", "stream", "strict", 0), ("tile-strict", "tile", "strict", 0), ("tile-interleaved", "tile", "interleaved", 0),

@@ -8,3 +8,4 @@ import json; d=json.load(open('gpurun_out/r2_bench_batch.json')); print('batch',
 timeout 600 python bench.py --workload batch4096 --lanes 2 --arith exact --no-cpu-baseline > gpurun_out/q.json 2> gpurun_out/q.err; python -c "
 import json; d=json.load(open('gpurun_out/q.json')); print('batch lanes2 exact', d['value'], d['roofline']['frac'])" || tail -5 gpurun_out/q.err
 timeout 900 python tools/p3_report.py > gpurun_out/p3_residuals.json 2> gpurun_out/p3_report.err; tail -8 gpurun_out/p3_report.err | cut -c 1-250
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; tail -c 700 gpurun_out/r2_bench_reference.json; tail -3 gpurun_out/r2_bench_reference.err
