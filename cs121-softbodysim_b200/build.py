@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpbd_b200.so")
 # (pbd_server.cpp is not part of the library: build_server links it against the library)
-SOURCES = ["pbd_plan.cpp", "pbd_tileplan.cpp", "pbd_stream.cu", "pbd_tile.cu", "pbd_batch.cu", "pbd_capi.cu"]
+SOURCES = ["pbd_plan.cpp", "pbd_tileplan.cpp", "pbd_placement.cpp", "pbd_stream.cu", "pbd_tile.cu", "pbd_batch.cu", "pbd_capi.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "pbd_b200.h")]
 
 NVCC_FLAGS = [

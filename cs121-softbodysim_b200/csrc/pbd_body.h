@@ -41,6 +41,7 @@ struct FrameShape {
   uint32_t iterations = 0;
   int groundEnabled = 0;
   uint32_t nColliders = 0;  // primitive colliders in the clamp stage (pbd_set_colliders)
+  bool tetInert = false;    // alphaTet == 0 this frame: tet multipliers never enter a correction (fast mode may drop them)
 };
 
 class Backend {

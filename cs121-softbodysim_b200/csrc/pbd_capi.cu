@@ -295,7 +295,8 @@ static int enqueue_frames(pbd_handle* h, float dt, uint32_t frames) {
   CU(onDevice.err);
   const StepConsts k = make_consts(h->params, dt);
   CU(cudaMemcpyAsync(h->d.consts, &k, sizeof(k), cudaMemcpyHostToDevice, h->stream));
-  const FrameShape f = h->shape();
+  FrameShape f = h->shape();
+  f.tetInert = k.alphaTet == 0.0f;
   CU(cudaEventRecord(h->ev0, h->stream));
   for (uint32_t i = 0; i < frames; ++i) CU(h->be->enqueue_frame(h->d, f, h->stream));
   CU(cudaEventRecord(h->ev1, h->stream));

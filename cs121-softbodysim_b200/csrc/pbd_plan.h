@@ -101,6 +101,9 @@ struct Plan {
   std::vector<uint32_t> edgePhase, edgeTile, edgeColor;
   std::vector<uint32_t> tetPhase, tetTile, tetColor;
 
+  // shared-memory wavefronts of the sweeps' vertex gathers under this plan's placement (main tiles; edges, tets)
+  uint64_t gatherWavefronts[2] = {0, 0}, gatherIdeal[2] = {0, 0};
+
   double planMs = 0.0;
 };
 
@@ -116,6 +119,28 @@ uint32_t greedy_colour(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t
 // maxGroup = what one block pass of the sweep takes).  Used by the batch backend (one body = one tile).
 void colour_and_order(const uint32_t* ids, uint32_t n, uint32_t arity, uint32_t nVerts, uint32_t maxGroup,
                       std::vector<uint32_t>& order, std::vector<uint32_t>& counts);
+
+// Shared-memory placement of one tile (pbd_placement.cpp).  A colour group = `count` constraints of one
+// arity starting at `begin` in the tile's constraint arrays; the kernel gives thread i of a group its i-th
+// constraint, so eight consecutive constraints share a quarter-warp.
+struct PlaceGroup {
+  uint32_t begin = 0, count = 0, arity = 0;
+};
+struct PlaceStats {
+  uint64_t wavefronts[2] = {0, 0};   // shared-memory wavefronts of the 16-byte vertex gathers (edges, tets) ...
+  uint64_t ideal[2] = {0, 0};        // ... and what they would be without bank conflicts (one per quarter-warp and role)
+};
+// loc: 4 tile-local vertex indices per constraint (0xffffffff beyond the arity), payload: one word per constraint
+// (its id).  Reorders both inside every group and renumbers the tile's vertices so that the eight vertices a
+// quarter-warp gathers in one role fall into different 16-byte bank groups wherever it finds a way:
+// newLocal[old index] = new index (a permutation of 0..nLocal-1); loc is rewritten in the new numbering.
+// effort 0: keep numbering and order (statistics only).  block (a multiple of 8, 0 = the whole tile): a vertex
+// moves only inside its aligned block of that many indices, which keeps the tile's global loads / stores (thread i
+// <-> the slot at index i) as coalesced as they were.  Deterministic.
+void optimise_placement(uint32_t nLocal, const PlaceGroup* groups, uint32_t nGroups, uint32_t* loc, uint32_t* payload,
+                        uint32_t nCons, int effort, uint32_t block, std::vector<uint32_t>& newLocal, PlaceStats* stats);
+// rows of 8 by randomised greedy for given residues (4 bytes per constraint); out = constraint indices in row order
+void pack_rows_greedy(const uint8_t* res, uint32_t arity, uint32_t n, uint32_t seed, int tries, std::vector<uint32_t>& out);
 
 // Returns false and fills err on invalid input (index >= V).
 bool validate_mesh(const MeshView& m, std::string& err);

@@ -209,7 +209,12 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
 
 // ---------------------------------------------------------------- the frame kernel
 
-template <int LANES, bool TAGGED, bool FAST>
+// TETLAM = false (only with FAST): zero volume compliance (the reference's default, PBDServer.h:154) makes alpha == 0, so
+// a tet's multiplier never enters a correction.  The fast mode then does not carry it at all -- 8 bytes per tet and visit of
+// L2 traffic less, one LDS and one STS per projection less (the lambda write-back of a visit alone measured 3 % of the
+// frame).  PBD_ARRAY_TET_LAMBDA keeps whatever it held; the exact mode always accumulates it like the reference.  A
+// compile-time switch: the kernel sits at its register limit and a run-time flag spilled (measured -4 %).
+template <int LANES, bool TAGGED, bool FAST, bool TETLAM = true>
 __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar[2];
@@ -226,6 +231,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   const StepConsts k = *P.consts;
   const uint32_t tid = threadIdx.x, nth = blockDim.x;
   const bool sweeping = P.iterations > 0 && P.nPhases > 0;
+  constexpr bool tetLam = TETLAM;
   const bool clamp = P.iterations > 0;   // the reference clamps once per iteration (Sim.cpp:296)
 
   if (!sweeping) {
@@ -279,10 +285,11 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   auto fetch = [&](uint32_t ji, uint32_t b) {
     const TileCopy c = ji < kItemCopySmem ? itemCopy[ji] : P.copies[itemTile[ji]];
     unsigned char* dst = smem + b * P.recStride;
-    mbar_expect_tx(&mbar[b], c.staticBytes + c.edgeLamBytes + c.tetLamBytes);
+    const uint32_t tetBytes = tetLam ? c.tetLamBytes : 0u;
+    mbar_expect_tx(&mbar[b], c.staticBytes + c.edgeLamBytes + tetBytes);
     bulk_load(dst, P.blob + c.blobOff, c.staticBytes, &mbar[b]);
     if (c.edgeLamBytes) bulk_load(dst + c.staticBytes, P.edgeLam + c.edgeDevBegin, c.edgeLamBytes, &mbar[b]);
-    if (c.tetLamBytes) bulk_load(dst + c.staticBytes + c.edgeLamBytes, P.tetLam + c.tetDevBegin, c.tetLamBytes, &mbar[b]);
+    if (tetBytes) bulk_load(dst + c.staticBytes + c.edgeLamBytes, P.tetLam + c.tetDevBegin, tetBytes, &mbar[b]);
   };
 
   if (tid == 0 && nItems) fetch(0, 0);
@@ -428,12 +435,12 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             while (clock64() - t0 < (long long)stagger) {}
           }
           if (LANES == 1 && (h.flags & 4u)) {
-            sweep_mixed<FAST>(h, recOff, svOff, k.alphaEdge, k.alphaTet, ft);   // edges and tets share the colour steps
+            sweep_mixed<FAST>(h, recOff, svOff, k.alphaEdge, k.alphaTet, ft, tetLam);   // edges and tets share the colour steps
             if (ft) ft[3] = clock64();
           } else {
             sweep_edges<FAST>(h, recOff, svOff, k.alphaEdge, ft);
             if (ft) ft[3] = clock64();
-            sweep_tets<LANES, FAST>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr, k.alphaEdge);
+            sweep_tets<LANES, FAST>(h, recOff, svOff, k.alphaTet, ft ? ft + 20 : nullptr, k.alphaEdge, tetLam);
           }
           if (ft) ft[4] = clock64();
           // ---- write back
@@ -448,10 +455,12 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             __syncthreads();
             if (hasNext) { parityBits ^= 1u << (buf ^ 1u); recReady = true; }
             if (ft) ft[11] = ft[12] = ft[13] = clock64();
+            // (Writing the lambdas back with plain 16-byte stores by every thread instead was measured: no gain --
+            // what the write-back costs is its traffic, not thread 0's issue time.)
             if (tid == 0) {
               const TileCopy c = j < kItemCopySmem ? itemCopy[j] : P.copies[itemTile[j]];
               if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
-              if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
+              if (c.tetLamBytes && tetLam) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
               bulk_commit();
             }
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
@@ -493,7 +502,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             if (ft) ft[13] = clock64();
             const TileCopy c = j < kItemCopySmem ? itemCopy[j] : P.copies[itemTile[j]];
             if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
-            if (c.tetLamBytes) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
+            if (c.tetLamBytes && tetLam) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
             bulk_commit();
             if (nItems == 1) bulk_wait_read();   // the block stays resident and is swept again next iteration
           }
@@ -930,6 +939,7 @@ class TileBackend final : public Backend {
     donePeers_[rank_] = done_;
     attached_ = world_ == 1;
     stagger_ = getenv("PBD_TILE_STAGGER") ? (uint32_t)atoi(getenv("PBD_TILE_STAGGER")) : 0u;
+    dropInert_ = getenv("PBD_TILE_KEEP_LAMBDA") ? 0u : 1u;   // debug / A-B: carry inert multipliers in the fast mode too
     if (getenv("PBD_TILE_TRACE")) {
       traceN_ = 2 * (size_t)(nPhases_ + 1) * 4096;
       if ((err = cudaMalloc((void**)&trace_, sizeof(unsigned long long) * traceN_)) != cudaSuccess) return err;
@@ -949,6 +959,7 @@ class TileBackend final : public Backend {
 
     const void* fn = kernel();
     if ((err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_)) != cudaSuccess) return err;
+    if (kernel(true) != fn && (err = cudaFuncSetAttribute(kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_)) != cudaSuccess) return err;
     int perSM = 0, nSM = 0, coop = 0;
     if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, (int)block_, smemBytes_)) != cudaSuccess) return err;
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, device_);
@@ -990,7 +1001,7 @@ class TileBackend final : public Backend {
     cudaError_t err = cudaMemsetAsync(barrier_, 0, 2048, s);
     if (err != cudaSuccess) return err;
     void* args[] = {&P};
-    return cudaLaunchCooperativeKernel(kernel(), dim3(grid_), dim3(block_), args, smemBytes_, s);
+    return cudaLaunchCooperativeKernel(kernel(f.tetInert), dim3(grid_), dim3(block_), args, smemBytes_, s);
   }
 
   // pbd_step_stats (a16): the frame is ONE kernel, so the stages are shares of its device time -- cycles thread 0 of
@@ -1110,7 +1121,9 @@ class TileBackend final : public Backend {
   }
 
  private:
-  const void* kernel() const {
+  // tetInert: alpha of the tets is 0 this frame (FrameShape)
+  const void* kernel(bool tetInert = false) const {
+    if (tagged_ && fast_ && tetInert && dropInert_) return (const void*)tile_frame_kernel<1, true, true, false>;
     if (tagged_) return fast_ ? (const void*)tile_frame_kernel<1, true, true> : (const void*)tile_frame_kernel<1, true, false>;
     if (fast_) return (const void*)tile_frame_kernel<1, false, true>;
     return lanes_ == 1 ? (const void*)tile_frame_kernel<1, false, false>
@@ -1139,6 +1152,7 @@ class TileBackend final : public Backend {
   long long* ftrace_ = nullptr;
   size_t traceN_ = 0;
   uint32_t stagger_ = 0;
+  uint32_t dropInert_ = 1;
   uint32_t world_ = 1, rank_ = 0, nHome_ = 0, iterBase_ = 0;
   bool attached_ = true;
   std::vector<uint8_t> homeOwner_;

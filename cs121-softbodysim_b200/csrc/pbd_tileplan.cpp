@@ -60,6 +60,9 @@ struct PlanKnobs {
   int tabu;              // PBD_PLAN_TABU=n           tabu-search iterations per class (-1: built-in budgets)
   int minTile;           // PBD_PLAN_MINTILE=n        smallest tile (vertices) before fewer SMs are used instead (default 1024)
   int riders;            // PBD_PLAN_RIDERS=n         PBD_ORDER_RIDING: most riders per tet (1 or 2, default 2)
+  int place;             // PBD_PLAN_PLACE=n          shared-memory placement search (pbd_placement.cpp): 0 = off, default 1
+  int placeBlockHome;    // PBD_PLAN_PLACE_BH=n       ... a vertex of a home tile moves inside its aligned block of n indices (0: anywhere)
+  int placeBlockShifted; // PBD_PLAN_PLACE_BS=n       ... the same for the shifted tiles
 };
 const PlanKnobs& knobs() {
   static const PlanKnobs k = [] {
@@ -78,6 +81,9 @@ const PlanKnobs& knobs() {
     q.tabu = num("PBD_PLAN_TABU", -1);
     q.minTile = std::max(32, num("PBD_PLAN_MINTILE", 1024));
     q.riders = num("PBD_PLAN_RIDERS", 2);
+    q.place = std::max(0, num("PBD_PLAN_PLACE", 1));
+    q.placeBlockHome = std::max(0, num("PBD_PLAN_PLACE_BH", 8));
+    q.placeBlockShifted = std::max(0, num("PBD_PLAN_PLACE_BS", 32));
     return q;
   }();
   return k;
@@ -406,6 +412,7 @@ struct TileBuild {
   bool mixed = false;                        // both lists share ONE colouring: colour s of either type = step s of the visit
   bool presetVerts = false;                  // verts holds the whole partition cell (tagged hand-over: every phase rewrites every vertex)
   uint32_t nRiders = 0;                      // PBD_ORDER_RIDING: edges that ride on this tile's tets (not in ty[0].cons)
+  std::vector<uint32_t> localPerm;           // contiguous tiles after place_tile(): slot rangeBegin + i moves to rangeBegin + localPerm[i]
 };
 
 // Try to empty the highest colour classes: move each of their constraints to a lower colour that
@@ -888,84 +895,57 @@ void colour_joint(const CSet sets[2], TileBuild& tb, uint32_t nLocal, const std:
 // tile-local vertex indices of each role differ modulo 8.  Greedy: fill one quarter-warp at a
 // time with the first remaining constraints whose indices are still free in every role.  The
 // order inside a colour group never changes the result (its constraints share no vertex).
-std::atomic<uint64_t> g_bankWavefronts{0}, g_bankIdeal{0};   // PBD_PLAN_DEBUG statistics
-
 void bank_order(const CSet& cs, const std::vector<uint32_t>& localOf, uint32_t* cons, uint32_t n) {
   if (n <= 1) return;
   const uint32_t ar = cs.arity;
-  std::vector<uint32_t> item(cons, cons + n), out;
-  out.reserve(n);
   // residues of every constraint, one byte per role
   std::vector<uint8_t> res((size_t)n * 4, 0);
   for (uint32_t i = 0; i < n; ++i)
-    for (uint32_t r = 0; r < ar; ++r) res[(size_t)i * 4 + r] = (uint8_t)(localOf[cs.at(item[i])[r]] & 7u);
-  std::vector<uint32_t> alive(n);   // indices into item[] not placed yet
-  std::iota(alive.begin(), alive.end(), 0u);
-  uint32_t lcg = 0x2545f491u;
-  std::vector<uint32_t> row, bestRow, perm;
-  while (!alive.empty()) {
-    const uint32_t m = (uint32_t)alive.size();
-    if (m <= 8) {   // last (partial) row: whatever is left
-      for (uint32_t a2 : alive) out.push_back(item[a2]);
-      break;
-    }
-    bestRow.clear();
-    // randomised greedy with restarts: scan the remaining constraints from a pseudo-random start
-    // with a pseudo-random odd stride (a permutation of the indices when m is a power of two; in
-    // general most indices) and collect constraints whose residues are free in every role
-    const int tries = 24;
-    for (int tr = 0; tr < tries && bestRow.size() < 8; ++tr) {
-      lcg = lcg * 1664525u + 1013904223u;
-      const uint32_t start = (lcg >> 8) % m;
-      row.clear();
-      uint8_t used[4] = {0, 0, 0, 0};
-      for (uint32_t q = 0; q < m && row.size() < 8; ++q) {
-        const uint32_t a2 = alive[(start + q) % m];
-        const uint8_t* rs = &res[(size_t)a2 * 4];
-        bool ok = true;
-        for (uint32_t r = 0; r < ar && ok; ++r) ok = !(used[r] >> rs[r] & 1u);
-        if (!ok) continue;
-        for (uint32_t r = 0; r < ar; ++r) used[r] |= (uint8_t)(1u << rs[r]);
-        row.push_back(a2);
-      }
-      if (row.size() > bestRow.size()) bestRow = row;
-    }
-    // complete a partial row with the constraints that add the fewest collisions
-    if (bestRow.size() < 8) {
-      uint8_t cnt[4][8] = {};
-      std::vector<uint8_t> inRow(n, 0);
-      for (uint32_t a2 : bestRow) { inRow[a2] = 1; for (uint32_t r = 0; r < ar; ++r) cnt[r][res[(size_t)a2 * 4 + r]]++; }
-      while (bestRow.size() < 8) {
-        uint32_t pick = 0xffffffffu, pickCost = 0xffffffffu;
-        for (uint32_t a2 : alive) {
-          if (inRow[a2]) continue;
-          uint32_t cost = 0;
-          for (uint32_t r = 0; r < ar; ++r) cost += cnt[r][res[(size_t)a2 * 4 + r]];
-          if (cost < pickCost) { pickCost = cost; pick = a2; }
-        }
-        if (pick == 0xffffffffu) break;
-        inRow[pick] = 1;
-        for (uint32_t r = 0; r < ar; ++r) cnt[r][res[(size_t)pick * 4 + r]]++;
-        bestRow.push_back(pick);
-      }
-    }
-    std::vector<uint8_t> gone(n, 0);
-    for (uint32_t a2 : bestRow) { out.push_back(item[a2]); gone[a2] = 1; }
-    alive.erase(std::remove_if(alive.begin(), alive.end(), [&](uint32_t a2) { return gone[a2] != 0; }), alive.end());
-  }
+    for (uint32_t r = 0; r < ar; ++r) res[(size_t)i * 4 + r] = (uint8_t)(localOf[cs.at(cons[i])[r]] & 7u);
+  std::vector<uint32_t> pick, out(n);
+  pack_rows_greedy(res.data(), ar, n, 0x2545f491u, 24, pick);
+  for (uint32_t i = 0; i < n; ++i) out[i] = cons[pick[i]];
   std::copy(out.begin(), out.end(), cons);
-  if (knobs().debug) {
-    uint64_t wf = 0, ideal = 0;
-    for (uint32_t q0 = 0; q0 < n; q0 += 8)
-      for (uint32_t r = 0; r < ar; ++r) {
-        uint8_t cnt[8] = {};
-        uint8_t mx = 0;
-        for (uint32_t q = q0; q < std::min(n, q0 + 8); ++q) mx = std::max<uint8_t>(mx, ++cnt[localOf[cs.at(cons[q])[r]] & 7u]);
-        wf += mx;
-        ++ideal;
+}
+
+// Shared-memory placement of one finished (coloured) tile: pbd_placement.cpp renumbers the tile's vertices and
+// reorders every colour group (same groups, same colours: no result changes).  Gathered tiles take the new
+// numbering by reordering their vertex list; a contiguous tile records it in localPerm and the planner
+// renumbers the slots of its range afterwards.  effort 0: statistics only.
+void place_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& localOf, int effort, uint32_t block, PlaceStats& stats) {
+  const uint32_t nLocal = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
+  if (tb.contiguous) for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.rangeBegin + i] = i;
+  else for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.verts[i]] = i;
+  std::vector<PlaceGroup> groups;
+  std::vector<uint32_t> loc, payload;
+  size_t typeBegin[3] = {0, 0, 0};
+  for (int ty = 0; ty < 2; ++ty) {
+    const TypeList& L = tb.ty[ty];
+    const CSet& cs = sets[ty];
+    for (size_t i = 0; i < L.cons.size();) {
+      size_t j = i;
+      while (j < L.cons.size() && L.colour[j] == L.colour[i]) ++j;
+      groups.push_back({(uint32_t)payload.size(), (uint32_t)(j - i), cs.arity});
+      for (size_t k = i; k < j; ++k) {
+        payload.push_back(L.cons[k]);
+        for (uint32_t r = 0; r < 4; ++r) loc.push_back(r < cs.arity ? localOf[cs.at(L.cons[k])[r]] : NONE);
       }
-    g_bankWavefronts += wf;
-    g_bankIdeal += ideal;
+      i = j;
+    }
+    typeBegin[ty + 1] = payload.size();
+  }
+  std::vector<uint32_t> newLocal;
+  optimise_placement(nLocal, groups.data(), (uint32_t)groups.size(), loc.data(), payload.data(), (uint32_t)payload.size(), effort,
+                     block, newLocal, &stats);
+  if (effort <= 0) return;
+  for (int ty = 0; ty < 2; ++ty)   // (colours are unchanged: the groups keep their places)
+    std::copy(payload.begin() + typeBegin[ty], payload.begin() + typeBegin[ty + 1], tb.ty[ty].cons.begin());
+  if (tb.contiguous) {
+    tb.localPerm = newLocal;
+  } else {
+    std::vector<uint32_t> moved(nLocal);
+    for (uint32_t i = 0; i < nLocal; ++i) moved[newLocal[i]] = tb.verts[i];
+    tb.verts.swap(moved);
   }
 }
 
@@ -1810,6 +1790,62 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     }
 
     PBD_PLAN_STAGE("tile colouring");
+    // ---- shared-memory placement of the main tiles (one thread per constraint only: the 2- and 4-lane tet
+    // sweeps and the riding order address shared memory differently).  Again independent per tile.
+    // Home tiles first: their vertices ARE a slot range, so their new numbering is a renumbering of the slots
+    // inside each range, applied to everything that names a slot; then the shifted tiles, whose vertex lists
+    // are re-sorted by the new slots first.  A vertex moves only inside an aligned block of its tile's indices
+    // (home: 8 = one 128-byte line of vertex words, shifted: 32 = one warp): measured without that restriction,
+    // the scattered global loads / stores of the tile visits cost more than the bank conflicts saved.
+    {
+      const int effort = (opts.lanes_per_tet <= 1 && !riding) ? knobs().place : 0;
+      const unsigned nThreads = (m.T + m.E < 200000u) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      std::vector<PlaceStats> st(nThreads);
+      std::vector<std::vector<uint32_t>> los(nThreads > 1 ? nThreads - 1 : 0, std::vector<uint32_t>(m.V, NONE));
+      auto place_phases = [&](uint32_t pBegin, uint32_t pEnd, uint32_t block) {
+        std::vector<TileBuild*> work;
+        for (uint32_t p = pBegin; p < pEnd; ++p)
+          for (auto& tb : mainPh[p])
+            if (!tb.ty[0].cons.empty() || !tb.ty[1].cons.empty()) work.push_back(&tb);
+        std::atomic<size_t> next{0};
+        auto worker = [&](std::vector<uint32_t>& lo, PlaceStats& ps) {
+          for (size_t i; (i = next.fetch_add(1)) < work.size();) place_tile(sets, *work[i], lo, effort, block, ps);
+        };
+        std::vector<std::thread> pool;
+        for (size_t i = 0; i < los.size(); ++i) pool.emplace_back(worker, std::ref(los[i]), std::ref(st[i + 1]));
+        worker(localOf, st[0]);
+        for (auto& th : pool) th.join();
+      };
+      place_phases(0, 1, (uint32_t)knobs().placeBlockHome);
+      std::vector<uint32_t> slotPerm;
+      for (uint32_t t = 0; t < nTile0 && t < mainPh[0].size(); ++t) {
+        const TileBuild& tb = mainPh[0][t];
+        if (tb.localPerm.empty()) continue;
+        if (slotPerm.empty()) { slotPerm.resize(m.V); std::iota(slotPerm.begin(), slotPerm.end(), 0u); }
+        for (uint32_t i = 0; i < tb.rangeCount; ++i) slotPerm[tb.rangeBegin + i] = tb.rangeBegin + tb.localPerm[i];
+      }
+      if (!slotPerm.empty()) {
+        std::vector<uint32_t> moved(m.V);
+        for (uint32_t sl = 0; sl < m.V; ++sl) moved[slotPerm[sl]] = slotToVertex[sl];
+        slotToVertex.swap(moved);
+        for (uint32_t sl = 0; sl < m.V; ++sl) vertexToSlot[slotToVertex[sl]] = sl;
+        for (auto& sl : eSlots) sl = slotPerm[sl];
+        for (auto& sl : tSlots) sl = slotPerm[sl];
+        for (uint32_t p = 0; p < K; ++p) {
+          for (uint32_t sl = 0; sl < m.V; ++sl) moved[slotPerm[sl]] = tileOfS[p][sl];
+          tileOfS[p].swap(moved);
+          moved.resize(m.V);
+          for (auto& tb : mainPh[p]) {
+            for (auto& sl : tb.verts) sl = slotPerm[sl];
+            std::sort(tb.verts.begin(), tb.verts.end());   // (placement of the shifted tiles starts from ascending slots)
+          }
+        }
+      }
+      if (K > 1) place_phases(1, K, (uint32_t)knobs().placeBlockShifted);
+      for (const PlaceStats& ps : st)
+        for (int ty = 0; ty < 2; ++ty) { plan.gatherWavefronts[ty] += ps.wavefronts[ty]; plan.gatherIdeal[ty] += ps.ideal[ty]; }
+    }
+    PBD_PLAN_STAGE("placement");
     // ---- residual phases (constraints interior to no partition)
     const uint32_t avgTile = std::max(64u, (m.V + nTile0 - 1) / std::max(1u, nTile0));
     uint32_t resCap = std::min(65535u, std::min(2u * avgTile, smemBytes / 128u));
@@ -2001,9 +2037,25 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   }
   PBD_PLAN_STAGE("flatten");
   plan.planMs = now_ms() - t0;
+  if (knobs().debug) {
+    // global side of a tile visit: thread i loads / stores the 16-byte word of the slot at tile position i
+    uint64_t warps = 0, sectors = 0, lines = 0;
+    for (const Tile& t : plan.tiles)
+      for (uint32_t i0 = 0; i0 < t.vertCount; i0 += 32) {
+        uint32_t sl[32], n = std::min(32u, t.vertCount - i0);
+        for (uint32_t i = 0; i < n; ++i) sl[i] = t.contiguous ? t.vertBegin + i0 + i : plan.tileVerts[t.vertBegin + i0 + i];
+        std::sort(sl, sl + n);
+        uint32_t ns = 0, nl = 0;
+        for (uint32_t i = 0; i < n; ++i) { ns += i == 0 || (sl[i] >> 1) != (sl[i - 1] >> 1); nl += i == 0 || (sl[i] >> 3) != (sl[i - 1] >> 3); }
+        ++warps; sectors += ns; lines += nl;
+      }
+    fprintf(stderr, "[plan] vertex words per warp access: %.2f 32-byte sectors, %.2f 128-byte lines (16 / 4 = contiguous)\n",
+            (double)sectors / (double)std::max<uint64_t>(1, warps), (double)lines / (double)std::max<uint64_t>(1, warps));
+  }
   if (knobs().debug)
-    fprintf(stderr, "[plan] shared-memory gathers: %.3f wavefronts per quarter-warp role (1.0 = conflict-free)\n",
-            (double)g_bankWavefronts.exchange(0) / (double)std::max<uint64_t>(1, g_bankIdeal.exchange(0)));
+    fprintf(stderr, "[plan] shared-memory gathers, wavefronts per quarter-warp role (1.0 = conflict-free): edges %.3f, tets %.3f\n",
+            (double)plan.gatherWavefronts[0] / (double)std::max<uint64_t>(1, plan.gatherIdeal[0]),
+            (double)plan.gatherWavefronts[1] / (double)std::max<uint64_t>(1, plan.gatherIdeal[1]));
   return true;
 }
 

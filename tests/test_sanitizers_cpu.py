@@ -1,5 +1,5 @@
 """Host-side code under sanitizers (SURVEY.md 5 "race detection / sanitizers"):
-the schedule planner (csrc/pbd_plan.cpp + pbd_tileplan.cpp, multithreaded tile colouring) is built
+the schedule planner (csrc/pbd_plan.cpp + pbd_tileplan.cpp + pbd_placement.cpp, multithreaded tile colouring and placement) is built
 host-only with -fsanitize=address,undefined and -fsanitize=thread and driven by tools/plan_sanitize.cpp
 through every order mode; the reference-side adapter (integration/CudaStepper.cpp) must compile against
 the reference's own header with -Wall -Wextra -Wpedantic -Werror."""
@@ -12,7 +12,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = [os.path.join(ROOT, "tools", "plan_sanitize.cpp"),
        os.path.join(ROOT, "cs121-softbodysim_b200", "csrc", "pbd_plan.cpp"),
-       os.path.join(ROOT, "cs121-softbodysim_b200", "csrc", "pbd_tileplan.cpp")]
+       os.path.join(ROOT, "cs121-softbodysim_b200", "csrc", "pbd_tileplan.cpp"),
+       os.path.join(ROOT, "cs121-softbodysim_b200", "csrc", "pbd_placement.cpp")]
 
 
 @pytest.mark.parametrize("name,flags,n", [("asan_ubsan", "-fsanitize=address,undefined", "12"), ("tsan", "-fsanitize=thread", "20")])

@@ -24,11 +24,17 @@ def main():
     ap.add_argument("--strict", action="store_true")
     ap.add_argument("--riding", action="store_true")
     ap.add_argument("--partitions", type=int, default=0)
+    ap.add_argument("--tiles-per-sm", type=int, default=0)
+    ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--tile-vertices", type=int, default=0)
+    ap.add_argument("--no-tagged", action="store_true")
     a = ap.parse_args()
     x0, tets, edges = meshgen.kuhn_grid(a.n)
     om = capi.ORDER_STRICT if a.strict else capi.ORDER_RIDING if a.riding else capi.ORDER_INTERLEAVED
     t0 = time.time()
-    p = capi.Plan(x0, edges, tets, capi.Options(backend=capi.BACKEND_TILE, order_mode=om, partitions=a.partitions))
+    p = capi.Plan(x0, edges, tets, capi.Options(backend=capi.BACKEND_TILE, order_mode=om, partitions=a.partitions,
+                                             tiles_per_sm=a.tiles_per_sm, block_threads=a.block_threads, tile_vertices=a.tile_vertices,
+                                             flags=0 if a.no_tagged else capi.FLAG_TAGGED_HANDOVER))
     i = p.info()
     print(f"Kuhn n={a.n}: V={len(x0)} E={len(edges)} T={len(tets)}  order={'strict' if a.strict else 'interleaved'}  "
           f"tile visits/iteration={i['tiles']}  planned in {time.time() - t0:.1f} s")
