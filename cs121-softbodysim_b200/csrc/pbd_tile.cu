@@ -214,10 +214,17 @@ __device__ __forceinline__ void vertex_pass(const TileParams& P, const StepConst
 // L2 traffic less, one LDS and one STS per projection less (the lambda write-back of a visit alone measured 3 % of the
 // frame).  PBD_ARRAY_TET_LAMBDA keeps whatever it held; the exact mode always accumulates it like the reference.  A
 // compile-time switch: the kernel sits at its register limit and a run-time flag spilled (measured -4 %).
-template <int LANES, bool TAGGED, bool FAST, bool TETLAM = true>
+// RES = true (only with TAGGED; three record buffers): a CTA with exactly four tile visits per iteration -- the one-wave
+// case, four shifted partitions -- keeps the record blocks of visits 0 and 2 RESIDENT in shared memory for the whole frame
+// (fetched once, their lambdas written back once, after the tile's last visit) and streams the blocks of visits 1 and 3
+// through the third buffer, which is free while a resident visit runs.  Half the record traffic (static block + lambdas,
+// ~26 of the ~56 KB a visit moves through L2) disappears; what a visit costs follows those bytes (the lambda write-back
+// alone measured 3 % of the frame).  CTAs with another visit count fall back to the two streaming buffers.
+template <int LANES, bool TAGGED, bool FAST, bool TETLAM = true, bool RES = false>
 __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) {
+  static_assert(!RES || TAGGED, "resident record blocks ride on the tagged write-back path");
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long mbar[2];
+  __shared__ __align__(8) unsigned long long mbar[3];
   __shared__ TileCopy itemCopy[kItemCopySmem];   // copy descriptors of this CTA's tiles: no global latency when prefetching
   __shared__ uint32_t itemTile[kMaxItems];
   __shared__ uint32_t nItemsS;
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
   __shared__ unsigned* donePeerS[kMaxRanks];
   if (threadIdx.x < kMaxRanks) { posPeerS[threadIdx.x] = P.posPeers[threadIdx.x]; donePeerS[threadIdx.x] = P.donePeers[threadIdx.x]; }
   const bool multi = P.world > 1;
-  const uint32_t svOff = 2u * P.recStride;
+  const uint32_t svOff = (RES ? 3u : 2u) * P.recStride;
   float4* const sv = reinterpret_cast<float4*>(smem + svOff);
 
   const StepConsts k = *P.consts;
@@ -259,6 +266,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
     nItemsS = n;
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -292,7 +300,8 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
     if (tetBytes) bulk_load(dst + c.staticBytes + c.edgeLamBytes, P.tetLam + c.tetDevBegin, tetBytes, &mbar[b]);
   };
 
-  if (tid == 0 && nItems) fetch(0, 0);
+  const bool res = RES && nItems == 4;   // visits 0, 2: buffers 0, 1 (resident); visits 1, 3: buffer 2
+  if (tid == 0 && nItems) { fetch(0, 0); if (res) fetch(2, 1); }
 
   unsigned epoch = 0;
   uint32_t item = 0;      // items processed so far by this CTA
@@ -334,6 +343,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           // ---- prefetch the next tile's block into the other buffer
           const uint32_t jn = (j + 1 == nItems) ? 0u : j + 1;
           const bool hasNext = item + 1 < totalItems;
+          const uint32_t nb = res ? ((jn & 1u) ? 2u : (jn >> 1)) : (buf ^ 1u);   // the next visit's buffer
           // ---- vertices L2 -> shared memory (all of a thread's loads are issued before the first use)
           // ---- point-to-point sync: wait until the tiles that last wrote my vertices have stored them
           if (!TAGGED && P.done) {
@@ -424,10 +434,12 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
           // (which reads that buffer's gathered-slot list) by then, and the lambda write-back that read
           // it was issued a whole vertex load ago.  Its global writes need to be complete only before the
           // same tile's lambdas are fetched again, nItems - 1 visits later.
-          if (tid == 0 && hasNext && nItems > 1) {
+          // (resident mode: only a resident visit prefetches -- the streamed block of the next visit; the block after a
+          // streamed visit is resident)
+          if (tid == 0 && hasNext && nItems > 1 && !(res && (j & 1u))) {
             bulk_wait_read();
             if (nItems >= 4) bulk_wait_pending<2>(); else if (nItems == 3) bulk_wait_pending<1>(); else bulk_wait_all();
-            fetch(jn, buf ^ 1u);
+            fetch(jn, nb);
           }
           // ---- sweeps
           if (stagger) {
@@ -451,16 +463,23 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
             // it was requested a whole sweep ago.  A thread writes back exactly the shared-memory
             // entries (i = tid mod block size) that it overwrites itself when it loads the next tile.
             fence_async_smem();
-            if (tid == 0 && hasNext) while (!mbar_try_wait(&mbar[buf ^ 1u], (parityBits >> (buf ^ 1u)) & 1u)) {}
+            // a resident block is waited for once, before its first visit
+            const bool waitNext = hasNext && (!res || (jn & 1u) || item + 1 < nItems);
+            if (tid == 0 && waitNext) while (!mbar_try_wait(&mbar[nb], (parityBits >> nb) & 1u)) {}
             __syncthreads();
-            if (hasNext) { parityBits ^= 1u << (buf ^ 1u); recReady = true; }
+            if (waitNext) parityBits ^= 1u << nb;
+            if (hasNext) recReady = true;
             if (ft) ft[11] = ft[12] = ft[13] = clock64();
             // (Writing the lambdas back with plain 16-byte stores by every thread instead was measured: no gain --
             // what the write-back costs is its traffic, not thread 0's issue time.)
             if (tid == 0) {
-              const TileCopy c = j < kItemCopySmem ? itemCopy[j] : P.copies[itemTile[j]];
-              if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
-              if (c.tetLamBytes && tetLam) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
+              // resident block: its lambdas leave shared memory once, after the tile's last visit of the frame; every
+              // visit commits a (possibly empty) group, so the prefetch's wait_group counts stay what they were
+              if (!res || (j & 1u) || item + nItems >= totalItems) {
+                const TileCopy c = j < kItemCopySmem ? itemCopy[j] : P.copies[itemTile[j]];
+                if (c.edgeLamBytes) bulk_store(P.edgeLam + c.edgeDevBegin, rec + h.offEdgeLam, c.edgeLamBytes);
+                if (c.tetLamBytes && tetLam) bulk_store(P.tetLam + c.tetDevBegin, rec + h.offTetLam, c.tetLamBytes);
+              }
               bulk_commit();
             }
             const uint32_t* vidx = reinterpret_cast<const uint32_t*>(smem + recOff + h.offVertIdx);
@@ -468,7 +487,7 @@ __global__ void __launch_bounds__(512, 1) tile_frame_kernel(const TileParams P) 
               const uint32_t e = contiguous ? 0u : vidx[i];
               tagged_store((contiguous ? P.posT + h.vertBegin + i : reinterpret_cast<uint4*>(posPeerS[e >> 28]) + (e & 0x0fffffffu)), sv[i], writeTag, sysScope);
             }
-            buf ^= 1u;
+            buf = nb;
             j = jn;
             ++item;
             if (ft) { ft[5] = clock64(); ft[6] = h.nEdgeGroups; ft[7] = h.nTetGroups; ft[8] = h.vertCount; ft[9] = h.nEdges; ft[10] = h.nTets; }
@@ -694,7 +713,7 @@ class TileBackend final : public Backend {
     // ---- record blocks
     std::vector<TileCopy> copies(plan.tiles.size());
     std::vector<unsigned char> blob;
-    uint32_t recMax = 64;
+    uint32_t recMax = 64, recMaxNoTetLam = 64;
     // Tagged hand-over across GPUs: PUSH model.  A tile stores each vertex into the memory of the rank
     // that reads it NEXT (the owner of the tile that holds the vertex in the following phase), so every
     // load -- and every retry while a tag is not there yet -- is local; only posted 16-byte stores cross
@@ -765,6 +784,7 @@ class TileBackend final : public Backend {
       if (staticBytes != tile_static_bytes(nVG, t.edgeGroupCount, t.tetGroupCount, t.edgeCount, t.tetCount, t.ride != 0)) return cudaErrorUnknown;
       if (t.ride && (t.edgeCount >= 0xffffu || plan.tetRide.size() != 2 * (size_t)plan.T)) return cudaErrorInvalidConfiguration;
       recMax = std::max(recMax, off);
+      recMaxNoTetLam = std::max(recMaxNoTetLam, h.offTetLam);
 
       const size_t base = blob.size();
       blob.resize(base + staticBytes, 0);
@@ -878,6 +898,9 @@ class TileBackend final : public Backend {
     }
     recStride_ = (recMax + 127u) & ~127u;
     smemBytes_ = 2 * (size_t)recStride_ + sizeof(float4) * (size_t)std::max(plan.tileVertexCapacity, 1u);
+    // the resident-block kernel runs without the tet multipliers: its three buffers end before that section
+    recStrideRes_ = (recMaxNoTetLam + 127u) & ~127u;
+    smemBytesRes_ = 3 * (size_t)recStrideRes_ + sizeof(float4) * (size_t)std::max(plan.tileVertexCapacity, 1u);
 
     std::vector<PhaseDesc> pd(plan.phases.size());
     std::vector<uint32_t> tileList, homeList;
@@ -957,16 +980,33 @@ class TileBackend final : public Backend {
       posPeers_[rank_] = reinterpret_cast<float4*>(posT_);   // what peers map and address: the tagged words (same 16 B per vertex)
     }
 
-    const void* fn = kernel();
-    if ((err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_)) != cudaSuccess) return err;
-    if (kernel(true) != fn && (err = cudaFuncSetAttribute(kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_)) != cudaSuccess) return err;
     int perSM = 0, nSM = 0, coop = 0;
-    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, (int)block_, smemBytes_)) != cudaSuccess) return err;
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, device_);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_);
+    const uint32_t wantTiles = std::max(1u, opts_.tiles_per_sm ? opts_.tiles_per_sm : tilesPerSm_);
+    {
+      const void* fn = kernel();
+      if ((err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_)) != cudaSuccess) return err;
+      if (kernel(true) != fn && (err = cudaFuncSetAttribute(kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes_)) != cudaSuccess) return err;
+      if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, (int)block_, smemBytes_)) != cudaSuccess) return err;
+    }
     if (!coop || perSM < 1) return cudaErrorCooperativeLaunchTooLarge;
-    const uint32_t wantPerSm = std::max(1u, std::min(opts_.tiles_per_sm ? opts_.tiles_per_sm : tilesPerSm_, (uint32_t)perSM));
+    const uint32_t wantPerSm = std::max(1u, std::min(wantTiles, (uint32_t)perSM));
     grid_ = std::max(1u, std::min(maxTilesPerPhase_, wantPerSm * (uint32_t)nSM));
+    // Resident record blocks (the RES kernel; fast arithmetic without inert tet multipliers only -- with them three
+    // buffers do not leave room for two CTAs per SM): four phases of at most one tile per CTA, and the same grid must
+    // stay co-resident with the third buffer.
+    if (tagged_ && fast_ && dropInert_ && world_ == 1 && pd.size() == 4 && maxTilesPerPhase_ <= grid_ && !getenv("PBD_TILE_NORESIDENT")) {
+      resident_ = true;
+      int perRes = 0;
+      const void* fr = kernel(true);
+      const bool ok = cudaFuncSetAttribute(fr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytesRes_) == cudaSuccess &&
+                      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perRes, fr, (int)block_, smemBytesRes_) == cudaSuccess &&
+                      (uint32_t)perRes * (uint32_t)nSM >= grid_;
+      if (!ok) { cudaGetLastError(); resident_ = false; }
+      if (getenv("PBD_TILE_TRACE")) fprintf(stderr, "[pbd-tile] resident record blocks: %s (3 x %u + %zu vertex bytes per CTA, %d CTAs per SM)\n",
+                                            resident_ ? "on" : "off", recStrideRes_, smemBytesRes_ - 3 * (size_t)recStrideRes_, perRes);
+    }
     // every CTA's per-iteration tile list must fit the kernel's item table
     uint64_t items = 0;
     for (const PhaseDesc& p : pd) items += (p.tileCount + grid_ - 1) / grid_;
@@ -982,7 +1022,8 @@ class TileBackend final : public Backend {
     P.colliders = d.colliders; P.nColliders = d.nColliders;
     P.trace = trace_; P.ftrace = ftrace_;
     P.nTile0 = nTile0_; P.nPhases = nPhases_; P.substeps = f.substeps; P.iterations = f.iterations;
-    P.recStride = recStride_;
+    const bool resKernel = resident_ && f.tetInert;   // == what kernel(f.tetInert) returns
+    P.recStride = resKernel ? recStrideRes_ : recStride_;
     P.stagger = stagger_;
     P.done = useFlags_ ? done_ : nullptr;
     if (!attached_) return cudaErrorNotReady;   // pbd_shard_attach_* first
@@ -1001,7 +1042,7 @@ class TileBackend final : public Backend {
     cudaError_t err = cudaMemsetAsync(barrier_, 0, 2048, s);
     if (err != cudaSuccess) return err;
     void* args[] = {&P};
-    return cudaLaunchCooperativeKernel(kernel(f.tetInert), dim3(grid_), dim3(block_), args, smemBytes_, s);
+    return cudaLaunchCooperativeKernel(kernel(f.tetInert), dim3(grid_), dim3(block_), args, resKernel ? smemBytesRes_ : smemBytes_, s);
   }
 
   // pbd_step_stats (a16): the frame is ONE kernel, so the stages are shares of its device time -- cycles thread 0 of
@@ -1123,7 +1164,8 @@ class TileBackend final : public Backend {
  private:
   // tetInert: alpha of the tets is 0 this frame (FrameShape)
   const void* kernel(bool tetInert = false) const {
-    if (tagged_ && fast_ && tetInert && dropInert_) return (const void*)tile_frame_kernel<1, true, true, false>;
+    if (tagged_ && fast_ && tetInert && dropInert_)
+      return resident_ ? (const void*)tile_frame_kernel<1, true, true, false, true> : (const void*)tile_frame_kernel<1, true, true, false>;
     if (tagged_) return fast_ ? (const void*)tile_frame_kernel<1, true, true> : (const void*)tile_frame_kernel<1, true, false>;
     if (fast_) return (const void*)tile_frame_kernel<1, false, true>;
     return lanes_ == 1 ? (const void*)tile_frame_kernel<1, false, false>
@@ -1142,6 +1184,7 @@ class TileBackend final : public Backend {
   long long spinLimit_ = 0;
   bool tagged_ = false;
   bool fast_ = false;            // PBD_FLAG_FAST_ARITH
+  bool resident_ = false;        // RES kernels: three record buffers, visits 0 and 2 of every CTA keep theirs for the frame
   uint32_t tilesPerSm_ = 1;
   unsigned char* blob_ = nullptr;
   TileCopy* copies_ = nullptr;
@@ -1166,7 +1209,8 @@ class TileBackend final : public Backend {
   size_t doneBytes_ = 0;
   bool useFlags_ = false;
   uint32_t block_ = 512, grid_ = 1, nPhases_ = 0, nTile0_ = 0, maxTilesPerPhase_ = 0, lanes_ = 4, recStride_ = 128;
-  size_t smemBytes_ = 0;
+  size_t smemBytes_ = 0, smemBytesRes_ = 0;
+  uint32_t recStrideRes_ = 128;
   uint64_t bytes_ = 0;
 };
 

@@ -2038,6 +2038,14 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
   PBD_PLAN_STAGE("flatten");
   plan.planMs = now_ms() - t0;
   if (knobs().debug) {
+    uint64_t sum = 0;
+    uint32_t mxE = 0, mxT = 0, mxV = 0;
+    for (const Tile& t : plan.tiles) {
+      sum += tile_record_bytes(t.contiguous ? 0u : t.vertCount, t.edgeGroupCount, t.tetGroupCount, t.edgeCount, t.tetCount, t.ride != 0);
+      mxE = std::max(mxE, t.edgeCount); mxT = std::max(mxT, t.tetCount); mxV = std::max(mxV, t.vertCount);
+    }
+    fprintf(stderr, "[plan] record block: max %u bytes, mean %.0f (largest tile: %u edges, %u tets, %u vertices; %zu tiles)\n", plan.tileRecordBytes,
+            (double)sum / (double)std::max<size_t>(1, plan.tiles.size()), mxE, mxT, mxV, plan.tiles.size());
     // global side of a tile visit: thread i loads / stores the 16-byte word of the slot at tile position i
     uint64_t warps = 0, sectors = 0, lines = 0;
     for (const Tile& t : plan.tiles)
