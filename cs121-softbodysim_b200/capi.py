@@ -108,12 +108,14 @@ class Info(C.Structure):
                 ("edge_colors", C.c_uint32), ("tet_colors", C.c_uint32),
                 ("edge_phases", C.c_uint32), ("tet_phases", C.c_uint32), ("tiles", C.c_uint32),
                 ("launches_per_frame", C.c_uint32), ("grid_blocks", C.c_uint32), ("block_threads", C.c_uint32),
-                ("partitions", C.c_uint32), ("lanes_per_tet", C.c_uint32), ("reserved32", C.c_uint32 * 2),
+                ("partitions", C.c_uint32), ("lanes_per_tet", C.c_uint32), ("gather_wavefronts_permille", C.c_uint32 * 2),
                 ("device_bytes", C.c_uint64), ("algorithmic_bytes_per_substep", C.c_uint64),
                 ("plan_ms", C.c_double), ("upload_ms", C.c_double)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
+        d["gather_wavefronts_permille"] = list(d["gather_wavefronts_permille"])
+        return d
 
 
 _lib = None

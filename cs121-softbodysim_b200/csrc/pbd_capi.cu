@@ -159,6 +159,8 @@ void base_info(const Plan& p, const pbd_params* prm, pbd_info& out) {
   out.tiles = (uint32_t)p.tiles.size();
   out.partitions = p.partitions;
   out.plan_ms = p.planMs;
+  for (int ty = 0; ty < 2; ++ty)
+    out.gather_wavefronts_permille[ty] = p.gatherIdeal[ty] ? (uint32_t)((1000ull * p.gatherWavefronts[ty] + p.gatherIdeal[ty] / 2) / p.gatherIdeal[ty]) : 0u;
   out.algorithmic_bytes_per_substep = algorithmic_bytes_per_substep(p.V, p.E, p.T, prm ? prm->iterations : 6);
 }
 

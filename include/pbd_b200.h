@@ -151,7 +151,9 @@ typedef struct pbd_info {
   uint32_t grid_blocks, block_threads;
   uint32_t partitions;          /* tile backend: shifted vertex partitions (main phases per sweep) */
   uint32_t lanes_per_tet;       /* tile backend: lanes cooperating on one tet                      */
-  uint32_t reserved32[2];
+  uint32_t gather_wavefronts_permille[2]; /* tile backend, one thread per constraint: 1000 x shared-memory wavefronts per
+                                             quarter-warp vertex gather of the sweeps under this schedule's placement
+                                             (edges, tets; 1000 = free of bank conflicts; csrc/pbd_placement.cpp); 0 = n/a */
   uint64_t device_bytes;        /* HBM held by this handle                                    */
   uint64_t algorithmic_bytes_per_substep; /* 104 V + I (20 E + 28 T + 84 V), SURVEY.md 8(d)   */
   double plan_ms;               /* host time spent building the schedule                     */

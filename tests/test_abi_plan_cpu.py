@@ -137,6 +137,36 @@ def test_colour_steps_fit_one_block_pass(order, capi, meshgen):
     assert steps_per_visit <= (14 if order == "interleaved" else 9)
 
 
+def test_placement_search_keeps_the_colour_groups_and_cuts_bank_conflicts(capi, meshgen):
+    """csrc/pbd_placement.cpp renumbers a tile's vertices and reorders its colour groups so that the 16-byte vertex
+    gathers of a quarter-warp fall into different bank groups.  It must change nothing else: the same constraints in
+    the same (phase, tile, colour step) as with PBD_PLAN_PLACE=0 (planner knobs are read once per process, so the
+    comparison plan comes from a child process), and the wavefront count per gather that pbd_info reports must drop."""
+    import json, subprocess, sys
+    x0, tets, edges = meshgen.kuhn_grid(20)
+    opt = dict(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_INTERLEAVED, flags=capi.FLAG_TAGGED_HANDOVER, tile_vertices=600)
+    p = capi.Plan(x0, edges, tets, capi.Options(**opt))
+    _check_schedule(edges, tets, p)
+    on = p.info()["gather_wavefronts_permille"]
+    child = (
+        "import importlib, json, sys, zlib, numpy as np\n"
+        "capi = importlib.import_module('cs121-softbodysim_b200.capi'); mg = importlib.import_module('cs121-softbodysim_b200.meshgen')\n"
+        "x0, tets, edges = mg.kuhn_grid(20)\n"
+        f"p = capi.Plan(x0, edges, tets, capi.Options(**{opt!r}))\n"
+        "sl = [a for t in (False, True) for a in p.slots(t)]\n"
+        "print(json.dumps({'permille': p.info()['gather_wavefronts_permille'], 'crc': [zlib.crc32(np.ascontiguousarray(a).tobytes()) for a in sl]}))\n")
+    env = dict(os.environ, PBD_PLAN_PLACE="0")
+    r = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    off = json.loads(r.stdout.strip().splitlines()[-1])
+    import zlib
+    mine = [zlib.crc32(np.ascontiguousarray(a).tobytes()) for t in (False, True) for a in p.slots(t)]
+    assert mine == off["crc"], "the placement search moved a constraint to another phase, tile or colour step"
+    # measured on this mesh: edges 1.62 -> ~1.15, tets 1.85 -> ~1.5 wavefronts per quarter-warp gather
+    assert 1000 <= on[0] < off["permille"][0] and 1000 <= on[1] < off["permille"][1], (on, off["permille"])
+    assert on[0] <= 1250 and on[1] <= 1650, on
+
+
 def test_stream_colour_counts_match_survey_probe(capi, meshgen, golden):
     """greedy first-fit needs 30 tet + 15 edge colours on the Kuhn grid and
     101 tet + 54 edge colours on default_Tet."""

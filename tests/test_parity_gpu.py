@@ -579,6 +579,47 @@ def test_fast_arith_within_tolerance(mesh, mode, flags, capi, po, meshgen, golde
             assert np.isfinite(fast.get_array(what)).all()
 
 
+def test_fast_resident_blocks_and_inert_multipliers(capi, po, meshgen, monkeypatch):
+    """Two traffic savings of the fast tagged kernel (csrc/pbd_tile.cu, RES / TETLAM template switches):
+    (a) resident record blocks -- visits 0 and 2 of a CTA keep their block in shared memory for the whole frame -- change
+        where data lives, not what is computed: positions, velocities and the edge multipliers are BIT-identical to the
+        streaming kernel (PBD_TILE_NORESIDENT, read when the body is created);
+    (b) with zero volume compliance (alpha == 0, the reference default) a tet's multiplier never enters a correction and
+        is not carried: PBD_ARRAY_TET_LAMBDA keeps its initial zeros, positions are bit-identical to the same kernel
+        carrying it (PBD_TILE_KEEP_LAMBDA); with a non-zero compliance the multipliers are carried and agree with the
+        exact mode to rounding."""
+    x0, tets, edges = meshgen.kuhn_grid(12)
+    opt = dict(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_INTERLEAVED, tile_vertices=300)
+    fast = capi.FLAG_TAGGED_HANDOVER | capi.FLAG_FAST_ARITH
+
+    def run(prm, flags, frames=4, **env):
+        for k in ("PBD_TILE_NORESIDENT", "PBD_TILE_KEEP_LAMBDA"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with capi.Body(prm, x0, edges, tets, device=0, options=capi.Options(flags=flags, **opt)) as b:
+            assert b.info()["partitions"] == 4
+            b.step_async(1 / 60, frames)
+            b.sync()
+            return {w: b.get_array(w) for w in (capi.ARRAY_EDGE_LAMBDA, capi.ARRAY_TET_LAMBDA, capi.ARRAY_VELOCITY)} | {"pos": b.read_positions()}
+
+    prm = capi.SolverParams.default(substeps=5)
+    assert prm.volumeCompliance == 0.0 and prm.edgeCompliance > 0.0
+    res, stream, keep = run(prm, fast), run(prm, fast, PBD_TILE_NORESIDENT="1"), run(prm, fast, PBD_TILE_KEEP_LAMBDA="1")
+    for k in ("pos", capi.ARRAY_VELOCITY, capi.ARRAY_EDGE_LAMBDA):
+        assert np.array_equal(res[k], stream[k]), f"resident vs streaming record blocks differ in {k}"
+        assert np.array_equal(res[k], keep[k]), f"dropping the inert tet multipliers changed {k}"
+    assert not res[capi.ARRAY_TET_LAMBDA].any() and keep[capi.ARRAY_TET_LAMBDA].any()
+    assert res[capi.ARRAY_EDGE_LAMBDA].any()
+    # non-zero volume compliance: the multipliers matter, are carried, and match the exact mode to rounding
+    prm2 = capi.SolverParams.default(substeps=5, volumeCompliance=1e-6)
+    f2, e2 = run(prm2, fast, frames=1), run(prm2, capi.FLAG_TAGGED_HANDOVER, frames=1)
+    lt, le = f2[capi.ARRAY_TET_LAMBDA].astype(np.float64), e2[capi.ARRAY_TET_LAMBDA].astype(np.float64)
+    assert lt.any() and np.abs(lt - le).max() <= 1e-4 * np.abs(le).max()
+    diag = np.linalg.norm(x0.max(0) - x0.min(0))
+    assert np.sqrt(np.mean(np.sum((f2["pos"].astype(np.float64) - e2["pos"]) ** 2, 1))) / diag <= 2e-6
+
+
 @pytest.mark.parametrize("mode,flags", FAST_MODES)
 def test_fast_arith_parameter_and_degenerate_paths(mode, flags, capi, po, meshgen):
     """The skip conditions of the reference (all-massless constraint, zero-length edge, flat tet) and
