@@ -484,7 +484,9 @@ def main():
 
 ARITH_DOC = {
     "fast": "PBD_FLAG_FAST_ARITH: FFMA + SFU rcp/rsqrt forms of the projections, validated by tolerance (P2 <= 1e-4 rel. RMS after 10 "
-            "frames, P3 residuals after 1000 frames; tests/test_parity_gpu.py::test_fast_arith_*), not bit for bit",
+            "frames, P3 residuals after 1000 frames; tests/test_parity_gpu.py::test_fast_arith_*), not bit for bit; with zero volume "
+            "compliance (alpha = 0, the reference default) the tet multipliers never enter a correction and are not carried "
+            "(PBD_ARRAY_TET_LAMBDA stays as it was; positions bit-identical to carrying them, test_fast_resident_blocks_and_inert_multipliers)",
     "exact": "IEEE binary32 without FMA in the reference's evaluation order: BIT-EXACT against the oracle replaying the disclosed order",
 }
 
@@ -649,7 +651,8 @@ def measure_body(ctx, args, workload, mode, sharded, cpu_baseline, steps=None, s
         "clocks": clocks,
         "init_ms": init_ms, "plan_ms": info["plan_ms"], "wall_ms_timed_region": wall_ms,
         "schedule": {k: info[k] for k in ("edge_colors", "tet_colors", "edge_phases", "tet_phases", "tiles", "partitions",
-                                          "lanes_per_tet", "launches_per_frame", "grid_blocks", "block_threads")},
+                                          "lanes_per_tet", "launches_per_frame", "grid_blocks", "block_threads",
+                                          "gather_wavefronts_permille")},
         "sane": sane,
     }
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count

@@ -1811,7 +1811,10 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     // (home: 8 = one 128-byte line of vertex words, shifted: 32 = one warp): measured without that restriction,
     // the scattered global loads / stores of the tile visits cost more than the bank conflicts saved.
     {
-      const int effort = (opts.lanes_per_tet <= 1 && !riding) ? knobs().place : 0;
+      // (bodies beyond ~2.5M tets skip the search unless PBD_PLAN_PLACE asks for it: it costs ~2 s per million tets on
+      // 8 host threads for the few percent the bank conflicts are worth, and every rank of a sharded body plans the whole body)
+      const bool big = (uint64_t)m.T + m.E > 6000000ull && !getenv("PBD_PLAN_PLACE");
+      const int effort = (opts.lanes_per_tet <= 1 && !riding && !big) ? knobs().place : 0;
       const unsigned nThreads = (m.T + m.E < 200000u) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
       std::vector<PlaceStats> st(nThreads);
       std::vector<std::vector<uint32_t>> los(nThreads > 1 ? nThreads - 1 : 0, std::vector<uint32_t>(m.V, NONE));
