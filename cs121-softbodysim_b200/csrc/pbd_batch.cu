@@ -217,6 +217,7 @@ struct pbd_batch {
   uint32_t recStride = 128, grid = 1, maxVerts = 0;
   size_t smemBytes = 0;
   uint32_t edgeColorsMax = 0, tetColorsMax = 0;
+  uint64_t gatherWavefronts[2] = {0, 0}, gatherIdeal[2] = {0, 0};
   std::vector<uint32_t> edgeOrder, tetOrder;   // per body, body-local constraint indices, concatenated
   uint64_t bytes = 0;
   double planMs = 0.0, uploadMs = 0.0;
@@ -240,7 +241,7 @@ struct pbd_batch {
 
   ~pbd_batch() {
     cudaFree(d.pos); cudaFree(d.prev); cudaFree(d.vel); cudaFree(d.edgeLam); cudaFree(d.tetLam);
-    cudaFree(d.packed); cudaFree(d.consts); cudaFree(blob); cudaFree(bodies);
+    cudaFree(d.packed); cudaFree(d.consts); cudaFree(d.slotOf); cudaFree(blob); cudaFree(bodies);
     cudaFree(pieces); cudaFree(pieceBegin); cudaFree(pieceDone);
     if (abortHost) cudaFreeHost(abortHost);
     if (stageHost) cudaFreeHost(stageHost);
@@ -266,6 +267,8 @@ int bfail(int code, const std::string& msg, int* status = nullptr) {
 
 struct Coloured {
   std::vector<uint32_t> eOrder, eCounts, tOrder, tCounts;
+  std::vector<uint32_t> newLocal;   // body vertex -> its index in the body's shared-memory array / slot range (pbd_placement.cpp)
+  PlaceStats gathers;
 };
 
 }  // namespace
@@ -325,6 +328,7 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
   // ---- host: per-body derived state (reference init helpers, caller's order) + colouring
   const double tPlan = wall_ms();
   std::vector<float4> pos(Vtot), prev(Vtot);
+  std::vector<uint32_t> slotOf(Vtot);   // caller vertex (concatenated) -> slot: a body's vertices are renumbered inside its range
   std::vector<unsigned char> blob;
   std::vector<BodyDesc> descs(nBodies);
   B->edgeOrder.resize(Etot);
@@ -337,11 +341,6 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
     std::vector<float> w, eRest, tRest;
     host_inverse_mass(m, nullptr, 0, w);
     host_rest_state(m, eRest, tRest);
-    for (uint32_t v = 0; v < Vb; ++v) {
-      const float* q = m.x0 + 3 * (size_t)v;
-      pos[vOff[b] + v] = make_float4(q[0], q[1], q[2], w[v]);
-      prev[vOff[b] + v] = make_float4(q[0], q[1], q[2], 0.0f);
-    }
     std::string key(reinterpret_cast<const char*>(&Vb), 4);
     key.append(reinterpret_cast<const char*>(m.edges), sizeof(uint32_t) * 2 * (size_t)Eb);
     key.append(reinterpret_cast<const char*>(m.tets), sizeof(uint32_t) * 4 * (size_t)Tb);
@@ -350,9 +349,43 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
       col = std::make_shared<Coloured>();
       colour_and_order(m.edges, Eb, 2, Vb, 512, col->eOrder, col->eCounts);   // 512 = the kernel's block size
       colour_and_order(m.tets, Tb, 4, Vb, 512 / B->lanes, col->tOrder, col->tCounts);
+      // where the body's vertices sit in shared memory and which constraints of a colour group share a quarter-warp:
+      // the placement search of the tile backend on the whole body (one thread per constraint only).  A body lives in
+      // shared memory for the whole frame, so every sweep of the frame gathers through these bank groups.
+      {
+        std::vector<PlaceGroup> groups;
+        std::vector<uint32_t> loc, payload;
+        for (int ty = 0; ty < 2; ++ty) {
+          const std::vector<uint32_t>& ord = ty ? col->tOrder : col->eOrder;
+          const std::vector<uint32_t>& cnt = ty ? col->tCounts : col->eCounts;
+          const uint32_t ar = ty ? 4u : 2u;
+          const uint32_t* ids = ty ? m.tets : m.edges;
+          uint32_t at = 0;
+          for (uint32_t c : cnt) {
+            groups.push_back({(uint32_t)payload.size(), c, ar});
+            for (uint32_t q = 0; q < c; ++q, ++at) {
+              payload.push_back(ord[at]);
+              for (uint32_t r = 0; r < 4; ++r) loc.push_back(r < ar ? ids[(size_t)ar * ord[at] + r] : 0xffffffffu);
+            }
+          }
+        }
+        const int effort = (B->lanes == 1 && !getenv("PBD_BATCH_NOPLACE")) ? 1 : 0;
+        optimise_placement(Vb, groups.data(), (uint32_t)groups.size(), loc.data(), payload.data(), (uint32_t)payload.size(), effort, 0u,
+                           col->newLocal, &col->gathers);
+        std::copy(payload.begin(), payload.begin() + Eb, col->eOrder.begin());
+        std::copy(payload.begin() + Eb, payload.end(), col->tOrder.begin());
+      }
     }
+    const std::vector<uint32_t>& nl = col->newLocal;
+    for (int ty = 0; ty < 2; ++ty) { B->gatherWavefronts[ty] += col->gathers.wavefronts[ty]; B->gatherIdeal[ty] += col->gathers.ideal[ty]; }
     std::copy(col->eOrder.begin(), col->eOrder.end(), B->edgeOrder.begin() + eOff[b]);
     std::copy(col->tOrder.begin(), col->tOrder.end(), B->tetOrder.begin() + tOff[b]);
+    for (uint32_t v = 0; v < Vb; ++v) {
+      const float* q = m.x0 + 3 * (size_t)v;
+      pos[vOff[b] + nl[v]] = make_float4(q[0], q[1], q[2], w[v]);
+      prev[vOff[b] + nl[v]] = make_float4(q[0], q[1], q[2], 0.0f);
+      slotOf[vOff[b] + v] = (uint32_t)(vOff[b] + nl[v]);
+    }
     const uint32_t nEG = (uint32_t)col->eCounts.size(), nTG = (uint32_t)col->tCounts.size();
     // the sweeps project a colour group in ONE pass of the 512-thread block: a larger group would lose constraints
     for (uint32_t cnt : col->eCounts) if (cnt > 512u) { bfail(PBD_ERR_INVALID, "internal: edge colour group exceeds the block", status); return nullptr; }
@@ -392,15 +425,15 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
     float* er = reinterpret_cast<float*>(p + h.offEdgeRest);
     for (uint32_t q = 0; q < Eb; ++q) {
       const uint32_t e = col->eOrder[q];
-      ei[q] = m.edges[2 * (size_t)e] | (m.edges[2 * (size_t)e + 1] << 16);
+      ei[q] = nl[m.edges[2 * (size_t)e]] | (nl[m.edges[2 * (size_t)e + 1]] << 16);
       er[q] = eRest[e];
     }
     uint32_t* ti = reinterpret_cast<uint32_t*>(p + h.offTetIdx);
     float* tr = reinterpret_cast<float*>(p + h.offTetRest);
     for (uint32_t q = 0; q < Tb; ++q) {
       const uint32_t* id = m.tets + 4 * (size_t)col->tOrder[q];
-      ti[2 * q] = id[0] | (id[1] << 16);
-      ti[2 * q + 1] = id[2] | (id[3] << 16);
+      ti[2 * q] = nl[id[0]] | (nl[id[1]] << 16);
+      ti[2 * q + 1] = nl[id[2]] | (nl[id[3]] << 16);
       tr[q] = tRest[col->tOrder[q]];
     }
     BodyDesc& c = descs[b];
@@ -421,6 +454,7 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
   if ((ce = cudaEventCreate(&B->ev0)) != cudaSuccess || (ce = cudaEventCreate(&B->ev1)) != cudaSuccess) return cbail(ce, "cudaEventCreate");
   if ((ce = upload_vec(&d.pos, pos, B->bytes)) != cudaSuccess) return cbail(ce, "upload pos");
   if ((ce = upload_vec(&d.prev, prev, B->bytes)) != cudaSuccess) return cbail(ce, "upload prev");
+  if ((ce = upload_vec(&d.slotOf, slotOf, B->bytes)) != cudaSuccess) return cbail(ce, "upload slotOf");
   if ((ce = cudaMalloc((void**)&d.vel, sizeof(float4) * (Vtot + 1))) != cudaSuccess) return cbail(ce, "cudaMalloc vel");
   if ((ce = cudaMemset(d.vel, 0, sizeof(float4) * (Vtot + 1))) != cudaSuccess) return cbail(ce, "memset vel");
   if ((ce = cudaMalloc((void**)&d.edgeLam, sizeof(float) * ((size_t)eDev + 4))) != cudaSuccess) return cbail(ce, "cudaMalloc edgeLam");
@@ -577,6 +611,8 @@ int pbd_batch_get_info(const pbd_batch* b, pbd_info* out) {
   out->algorithmic_bytes_per_substep = algorithmic_bytes_per_substep((uint32_t)b->Vtot, (uint32_t)b->Etot, (uint32_t)b->Ttot, b->params.iterations);
   out->plan_ms = b->planMs;
   out->upload_ms = b->uploadMs;
+  for (int ty = 0; ty < 2; ++ty)
+    out->gather_wavefronts_permille[ty] = b->gatherIdeal[ty] ? (uint32_t)((1000ull * b->gatherWavefronts[ty] + b->gatherIdeal[ty] / 2) / b->gatherIdeal[ty]) : 0u;
   return PBD_OK;
 }
 
