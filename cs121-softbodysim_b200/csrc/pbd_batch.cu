@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(512, 1) batch_frame_kernel(const BatchParams P
           __syncthreads();
         }
         sweep_edges<FAST>(h, 0, svOff, k.alphaEdge, nullptr);
-        sweep_tets<LANES, FAST>(h, 0, svOff, k.alphaTet, nullptr);
+        // (fast arithmetic, alpha == 0: the tet multipliers never enter a correction and are not accumulated, as in the tile kernel)
+        sweep_tets<LANES, FAST>(h, 0, svOff, k.alphaTet, nullptr, 0.0f, !(FAST && k.alphaTet == 0.0f));
       }
       const bool last = sub + 1 == piece.subEnd;
       if (tid == 0) stageS[last ? 2 : 1] -= (uint32_t)clock64();
@@ -268,6 +269,7 @@ int bfail(int code, const std::string& msg, int* status = nullptr) {
 struct Coloured {
   std::vector<uint32_t> eOrder, eCounts, tOrder, tCounts;
   std::vector<uint32_t> newLocal;   // body vertex -> its index in the body's shared-memory array / slot range (pbd_placement.cpp)
+  std::vector<uint8_t> tetPerm;     // fast arithmetic: role permutation of every tet, parallel to tOrder (empty: none)
   PlaceStats gathers;
 };
 
@@ -370,8 +372,10 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
           }
         }
         const int effort = (B->lanes == 1 && !getenv("PBD_BATCH_NOPLACE")) ? 1 : 0;
+        std::vector<uint8_t> perm(B->fast && effort && !getenv("PBD_PLAN_NORELABEL") ? payload.size() : 0);
         optimise_placement(Vb, groups.data(), (uint32_t)groups.size(), loc.data(), payload.data(), (uint32_t)payload.size(), effort, 0u,
-                           col->newLocal, &col->gathers);
+                           col->newLocal, &col->gathers, perm.empty() ? nullptr : perm.data());
+        if (!perm.empty()) col->tetPerm.assign(perm.begin() + Eb, perm.end());
         std::copy(payload.begin(), payload.begin() + Eb, col->eOrder.begin());
         std::copy(payload.begin() + Eb, payload.end(), col->tOrder.begin());
       }
@@ -432,9 +436,12 @@ pbd_batch* pbd_batch_create(const pbd_params* params, uint32_t nBodies, const ui
     float* tr = reinterpret_cast<float*>(p + h.offTetRest);
     for (uint32_t q = 0; q < Tb; ++q) {
       const uint32_t* id = m.tets + 4 * (size_t)col->tOrder[q];
-      ti[2 * q] = nl[id[0]] | (nl[id[1]] << 16);
-      ti[2 * q + 1] = nl[id[2]] | (nl[id[3]] << 16);
-      tr[q] = tRest[col->tOrder[q]];
+      // (fast arithmetic: the placement search may have given the tet's vertices other roles; an odd permutation negates
+      // the signed volume, so the record carries the negated rest volume)
+      const uint8_t code = col->tetPerm.empty() ? (uint8_t)0xE4 : col->tetPerm[q];
+      ti[2 * q] = nl[id[code & 3u]] | (nl[id[(code >> 2) & 3u]] << 16);
+      ti[2 * q + 1] = nl[id[(code >> 4) & 3u]] | (nl[id[(code >> 6) & 3u]] << 16);
+      tr[q] = tet_perm_is_odd(code) ? -tRest[col->tOrder[q]] : tRest[col->tOrder[q]];
     }
     BodyDesc& c = descs[b];
     c.blobOff = base; c.staticBytes = staticBytes;

@@ -568,7 +568,13 @@ int pbd_get_array(pbd_handle* h, int what, float* out) {
     case PBD_ARRAY_EDGE_REST: return scal(d.edgeRest, d.E, p.edgeDevCount, p.edgeOrder, p.edgeDev);
     case PBD_ARRAY_EDGE_LAMBDA: return scal(d.edgeLam, d.E, p.edgeDevCount, p.edgeOrder, p.edgeDev);
     case PBD_ARRAY_TET_REST: return scal(d.tetRest, d.T, p.tetDevCount, p.tetOrder, p.tetDev);
-    case PBD_ARRAY_TET_LAMBDA: return scal(d.tetLam, d.T, p.tetDevCount, p.tetOrder, p.tetDev);
+    case PBD_ARRAY_TET_LAMBDA: {
+      const int rc = scal(d.tetLam, d.T, p.tetDevCount, p.tetOrder, p.tetDev);
+      // relabelled tets (fast arithmetic, odd role permutation) carry their multiplier with the opposite sign
+      if (rc == PBD_OK && !p.tetPerm.empty())
+        for (uint32_t k = 0; k < d.T; ++k) if (tet_perm_is_odd(p.tetPerm[k])) out[p.tetOrder[k]] = -out[p.tetOrder[k]];
+      return rc;
+    }
     default: return fail(PBD_ERR_INVALID, "unknown array id");
   }
 }

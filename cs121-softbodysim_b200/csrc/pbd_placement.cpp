@@ -114,28 +114,25 @@ void pack_rows_greedy(const uint8_t* res, uint32_t ar, uint32_t n, uint32_t seed
 
 namespace {
 
-// Edges: rows by bipartite edge colouring.  Node sets = the 8 classes of the a-endpoints and the 8
-// classes of the b-endpoints; every edge constraint is an arc (class a, class b); a proper arc
-// colouring with D = maximum degree colours exists (Koenig) and every colour class is a matching =
-// a row without a collision in either role.  The D matchings are then compacted into ceil(n/8)
-// rows, all full but the last (the kernel addresses a group densely): arcs of the smallest
-// matchings fill the holes of the larger ones where they add the fewest collisions.
-void pack_rows_koenig(const uint8_t* res, uint32_t n, std::vector<uint32_t>& out) {
-  out.clear();
-  if (n == 0) return;
+// Proper arc colouring of a bipartite multigraph (nodes 0..7 on either side, arc e = (ax[e], ay[e])) with D = its
+// maximum degree colours (Koenig): colOf[e] in [0, D).  Arcs are coloured one by one; when the colour free at x is
+// taken at y, the two-coloured alternating path starting at y is flipped (it cannot end at x).  Returns D.
+uint32_t bipartite_arc_colouring(const uint8_t* ax, const uint8_t* ay, uint32_t stride, uint32_t n, std::vector<uint32_t>& colOf) {
   uint32_t degA[8] = {}, degB[8] = {};
-  for (uint32_t i = 0; i < n; ++i) { degA[res[4 * (size_t)i]]++; degB[res[4 * (size_t)i + 1]]++; }
-  uint32_t D = 0;
+  for (uint32_t i = 0; i < n; ++i) { degA[ax[(size_t)i * stride]]++; degB[ay[(size_t)i * stride]]++; }
+  uint32_t D = 1;
   for (int k = 0; k < 8; ++k) D = std::max({D, degA[k], degB[k]});
-  // atA[x * D + c] = arc of colour c at a-class x (NONE: colour free there)
-  std::vector<uint32_t> atA((size_t)8 * D, NONE), atB((size_t)8 * D, NONE), colOf(n, NONE), path;
+  // atA[x * D + c] = arc of colour c at left node x (NONE: colour free there)
+  std::vector<uint32_t> atA((size_t)8 * D, NONE), atB((size_t)8 * D, NONE), path;
+  colOf.assign(n, NONE);
+  auto X = [&](uint32_t e) { return (uint32_t)ax[(size_t)e * stride]; };
+  auto Y = [&](uint32_t e) { return (uint32_t)ay[(size_t)e * stride]; };
   for (uint32_t e = 0; e < n; ++e) {
-    const uint32_t x = res[4 * (size_t)e], y = res[4 * (size_t)e + 1];
+    const uint32_t x = X(e), y = Y(e);
     uint32_t ca = 0, cb = 0;
     while (atA[x * D + ca] != NONE) ++ca;   // a free colour exists at both ends: fewer than D arcs are coloured there
     while (atB[y * D + cb] != NONE) ++cb;
     if (atB[y * D + ca] != NONE) {
-      // colour ca is taken at y: flip the (ca, cb) alternating path that starts at y; it cannot reach x
       path.clear();
       uint32_t node = y, want = ca;
       bool sideB = true;
@@ -143,21 +140,34 @@ void pack_rows_koenig(const uint8_t* res, uint32_t n, std::vector<uint32_t>& out
         const uint32_t f = sideB ? atB[node * D + want] : atA[node * D + want];
         if (f == NONE) break;
         path.push_back(f);
-        node = sideB ? res[4 * (size_t)f] : res[4 * (size_t)f + 1];
+        node = sideB ? X(f) : Y(f);
         sideB = !sideB;
         want = want == ca ? cb : ca;
       }
-      for (uint32_t f : path) { atA[res[4 * (size_t)f] * D + colOf[f]] = NONE; atB[res[4 * (size_t)f + 1] * D + colOf[f]] = NONE; }
+      for (uint32_t f : path) { atA[X(f) * D + colOf[f]] = NONE; atB[Y(f) * D + colOf[f]] = NONE; }
       for (uint32_t f : path) {
         colOf[f] = colOf[f] == ca ? cb : ca;
-        atA[res[4 * (size_t)f] * D + colOf[f]] = f;
-        atB[res[4 * (size_t)f + 1] * D + colOf[f]] = f;
+        atA[X(f) * D + colOf[f]] = f;
+        atB[Y(f) * D + colOf[f]] = f;
       }
     }
     colOf[e] = ca;
     atA[x * D + ca] = e;
     atB[y * D + ca] = e;
   }
+  return D;
+}
+
+// Edges: rows by bipartite edge colouring.  Node sets = the 8 classes of the a-endpoints and the 8
+// classes of the b-endpoints; every edge constraint is an arc (class a, class b); every colour class of a
+// proper arc colouring is a matching = a row without a collision in either role.  The D matchings are then
+// compacted into ceil(n/8) rows, all full but the last (the kernel addresses a group densely): arcs of the
+// smallest matchings fill the holes of the larger ones where they add the fewest collisions.
+void pack_rows_koenig(const uint8_t* res, uint32_t n, std::vector<uint32_t>& out) {
+  out.clear();
+  if (n == 0) return;
+  std::vector<uint32_t> colOf;
+  const uint32_t D = bipartite_arc_colouring(res, res + 1, 4, n, colOf);
   std::vector<std::vector<uint32_t>> rows(D);
   for (uint32_t e = 0; e < n; ++e) rows[colOf[e]].push_back(e);
   std::stable_sort(rows.begin(), rows.end(), [](const std::vector<uint32_t>& p, const std::vector<uint32_t>& q) { return p.size() > q.size(); });
@@ -187,6 +197,94 @@ void pack_rows_koenig(const uint8_t* res, uint32_t n, std::vector<uint32_t>& out
   for (auto& row : rows) out.insert(out.end(), row.begin(), row.end());
 }
 
+// Tets whose four vertices may take the four roles in ANY order (fast arithmetic: a permutation of a tet's vertices
+// changes its signed volume by the permutation's sign only; the caller negates the rest volume of odd ones).  A row of
+// eight tets is then collision-free in all four roles as soon as no class occurs more than four times among its 32
+// vertices: the multigraph tet -- class has maximum degree 4 and its arc colouring with 4 colours hands every tet one
+// vertex per role and every role eight different classes.  So rows are chosen for flat class histograms (greedy, then
+// pairwise exchanges) -- a one-dimensional condition instead of the four-dimensional matching of fixed roles.
+// cls4: the classes of every tet's vertices; out: tets in row order; roleOf[4 t + i] = role of tet t's i-th vertex.
+void pack_rows_relabel(const uint8_t* cls4, uint32_t n, std::vector<uint32_t>& out, std::vector<uint8_t>& roleOf) {
+  out.clear();
+  roleOf.assign((size_t)n * 4, 0);
+  for (uint32_t t = 0; t < n; ++t) for (uint8_t i = 0; i < 4; ++i) roleOf[(size_t)t * 4 + i] = i;
+  if (n == 0) return;
+  const uint32_t R = (n + 7) / 8;
+  std::vector<uint32_t> rowOfT(n, NONE), fill(R, 0);
+  std::vector<uint8_t> hist((size_t)R * 8, 0);
+  auto over_if_added = [&](uint32_t r, uint32_t t) {
+    uint8_t add[8] = {};
+    for (int i = 0; i < 4; ++i) add[cls4[(size_t)t * 4 + i]]++;
+    int o = 0;
+    for (int k = 0; k < 8; ++k) {
+      const int before = hist[(size_t)r * 8 + k], after = before + add[k];
+      o += std::max(0, after - 4) - std::max(0, before - 4);
+    }
+    return o;
+  };
+  auto put = [&](uint32_t r, uint32_t t, int sign) {
+    for (int i = 0; i < 4; ++i) hist[(size_t)r * 8 + cls4[(size_t)t * 4 + i]] += (uint8_t)sign;
+  };
+  // greedy: every row takes, eight times, the free tet that overfills its histogram least (ties: the lowest index)
+  std::vector<uint32_t> freeT(n);
+  std::iota(freeT.begin(), freeT.end(), 0u);
+  for (uint32_t r = 0; r < R; ++r) {
+    const uint32_t want = r + 1 < R ? 8u : n - 8u * (R - 1);
+    while (fill[r] < want) {
+      uint32_t best = 0;
+      int bestO = 1 << 30;
+      for (uint32_t q = 0; q < freeT.size() && bestO > 0; ++q) {
+        const int o = over_if_added(r, freeT[q]);
+        if (o < bestO) { bestO = o; best = q; }
+      }
+      const uint32_t t = freeT[best];
+      freeT.erase(freeT.begin() + best);
+      rowOfT[t] = r; put(r, t, 1); fill[r]++;
+    }
+  }
+  // exchanges between rows while they lower the total overfill
+  auto row_over = [&](uint32_t r) { int o = 0; for (int k = 0; k < 8; ++k) o += std::max(0, (int)hist[(size_t)r * 8 + k] - 4); return o; };
+  for (int pass = 0; pass < 3; ++pass) {
+    bool any = false;
+    for (uint32_t t = 0; t < n; ++t) {
+      const uint32_t r = rowOfT[t];
+      if (row_over(r) == 0) continue;
+      for (uint32_t u = 0; u < n; ++u) {
+        const uint32_t q = rowOfT[u];
+        if (q == r) continue;
+        const int before = row_over(r) + row_over(q);
+        put(r, t, -1); put(q, u, -1); put(r, u, 1); put(q, t, 1);
+        if (row_over(r) + row_over(q) < before) { rowOfT[t] = q; rowOfT[u] = r; any = true; break; }
+        put(r, u, -1); put(q, t, -1); put(r, t, 1); put(q, u, 1);
+      }
+    }
+    if (!any) break;
+  }
+  // roles inside every row: arc colouring of tet -- class; colours beyond the four roles (a class more than four times
+  // in the row) fall back to a role the tet has not used yet
+  std::vector<std::vector<uint32_t>> rows(R);
+  for (uint32_t t = 0; t < n; ++t) rows[rowOfT[t]].push_back(t);
+  std::vector<uint8_t> ax, ay;
+  std::vector<uint32_t> colOf;
+  for (uint32_t r = 0; r < R; ++r) {
+    const std::vector<uint32_t>& row = rows[r];
+    ax.clear(); ay.clear();
+    for (uint32_t q = 0; q < row.size(); ++q)
+      for (int i = 0; i < 4; ++i) { ax.push_back((uint8_t)q); ay.push_back(cls4[(size_t)row[q] * 4 + i]); }
+    bipartite_arc_colouring(ax.data(), ay.data(), 1, (uint32_t)ax.size(), colOf);
+    for (uint32_t q = 0; q < row.size(); ++q) {
+      uint32_t used = 0;
+      for (int i = 0; i < 4; ++i) if (colOf[4 * q + i] < 4) used |= 1u << colOf[4 * q + i];
+      for (int i = 0; i < 4; ++i) {
+        uint32_t c = colOf[4 * q + i];
+        if (c >= 4) { c = 0; while (used >> c & 1u) ++c; used |= 1u << c; }
+        roleOf[(size_t)row[q] * 4 + i] = (uint8_t)c;
+      }
+      out.push_back(row[q]);
+    }
+  }
+}
+
 struct Optimiser {
   uint32_t nLocal, nCons;
   uint32_t block = 0;   // class swaps stay inside aligned blocks of this many indices (a multiple of 8; 0: anywhere)
@@ -194,6 +292,8 @@ struct Optimiser {
   uint32_t nGroups;
   uint32_t* loc;        // 4 per constraint, tile-local vertex indices (NONE beyond the arity); reordered in place
   uint32_t* payload;    // 1 per constraint; reordered with loc
+  uint8_t* perm = nullptr;   // 1 per constraint or null: relabelling allowed; out: bits 2r..2r+1 = which of the constraint's
+                             // ORIGINAL vertices (0..3) sits in role r now
   std::vector<uint8_t> cls;          // class (0..7) of every local vertex
   std::vector<uint32_t> incOff, inc; // vertex -> constraint * 4 + role
   std::vector<uint32_t> groupOf, rowOf;   // per constraint
@@ -323,12 +423,13 @@ struct Optimiser {
   void swap_positions(uint32_t c, uint32_t d) {
     for (uint32_t r = 0; r < 4; ++r) std::swap(loc[4 * (size_t)c + r], loc[4 * (size_t)d + r]);
     std::swap(payload[c], payload[d]);
+    if (perm) std::swap(perm[c], perm[d]);
     // rowOf stays with the POSITION; the incidence lists name positions: rebuild lazily (caller)
   }
 
   // rows of every group from scratch, for the current classes
   void pack_all() {
-    std::vector<uint8_t> res;
+    std::vector<uint8_t> res, tmpPerm;
     std::vector<uint32_t> order, tmpLoc, tmpPay;
     for (uint32_t g = 0; g < nGroups; ++g) {
       const PlaceGroup& G = groups[g];
@@ -336,12 +437,29 @@ struct Optimiser {
       res.assign((size_t)G.count * 4, 0);
       for (uint32_t i = 0; i < G.count; ++i)
         for (uint32_t r = 0; r < G.arity; ++r) res[(size_t)i * 4 + r] = cls[loc[4 * (size_t)(G.begin + i) + r]];
+      std::vector<uint8_t> roleOf;
+      const bool relabel = perm != nullptr && G.arity == 4;
       if (G.arity == 2) pack_rows_koenig(res.data(), G.count, order);
+      else if (relabel) pack_rows_relabel(res.data(), G.count, order, roleOf);
       else pack_rows_greedy(res.data(), G.arity, G.count, 0x2545f491u + g, 32, order);
+      if (relabel) {
+        // move every tet's vertices into their roles (on top of whatever relabelling it carries already)
+        for (uint32_t i = 0; i < G.count; ++i) {
+          uint32_t v[4];
+          uint8_t src[4];
+          const uint32_t c = G.begin + i;
+          for (uint32_t j = 0; j < 4; ++j) { v[roleOf[(size_t)i * 4 + j]] = loc[4 * (size_t)c + j]; src[roleOf[(size_t)i * 4 + j]] = (uint8_t)(perm[c] >> (2 * j) & 3u); }
+          uint8_t code = 0;
+          for (uint32_t r = 0; r < 4; ++r) { loc[4 * (size_t)c + r] = v[r]; code |= (uint8_t)(src[r] << (2 * r)); }
+          perm[c] = code;
+        }
+      }
       tmpLoc.assign(loc + 4 * (size_t)G.begin, loc + 4 * (size_t)(G.begin + G.count));
       tmpPay.assign(payload + G.begin, payload + G.begin + G.count);
+      if (perm) tmpPerm.assign(perm + G.begin, perm + G.begin + G.count);
       for (uint32_t i = 0; i < G.count; ++i) {
         std::memcpy(loc + 4 * (size_t)(G.begin + i), &tmpLoc[4 * (size_t)order[i]], 16);
+        if (perm) perm[G.begin + i] = tmpPerm[order[i]];
         payload[G.begin + i] = tmpPay[order[i]];
       }
     }
@@ -390,7 +508,7 @@ struct Optimiser {
 }  // namespace
 
 void optimise_placement(uint32_t nLocal, const PlaceGroup* groups, uint32_t nGroups, uint32_t* loc, uint32_t* payload,
-                        uint32_t nCons, int effort, uint32_t block, std::vector<uint32_t>& newLocal, PlaceStats* stats) {
+                        uint32_t nCons, int effort, uint32_t block, std::vector<uint32_t>& newLocal, PlaceStats* stats, uint8_t* perm) {
   // PBD_PLACE_DUMP=<path>[:k]: write the k-th problem this process sees to <path> (input of tools/place_bench.cpp)
   if (const char* dump = getenv("PBD_PLACE_DUMP")) {
     static std::atomic<int> seen{0};
@@ -410,7 +528,9 @@ void optimise_placement(uint32_t nLocal, const PlaceGroup* groups, uint32_t nGro
   newLocal.resize(nLocal);
   std::iota(newLocal.begin(), newLocal.end(), 0u);
   Optimiser o;
-  o.nLocal = nLocal; o.nCons = nCons; o.block = block & ~7u; o.groups = groups; o.nGroups = nGroups; o.loc = loc; o.payload = payload;
+  o.nLocal = nLocal; o.nCons = nCons; o.block = block & ~7u; o.perm = perm;
+  o.groups = groups; o.nGroups = nGroups; o.loc = loc; o.payload = payload;
+  if (perm) std::memset(perm, 0xE4, nCons);   // identity: role r holds the constraint's r-th vertex
   o.cls.resize(nLocal);
   for (uint32_t v = 0; v < nLocal; ++v) o.cls[v] = (uint8_t)(v & 7u);
   o.groupOf.resize(nCons);

@@ -96,6 +96,10 @@ struct Plan {
   // 0xffffffff = none); empty otherwise.  riders = number of edges that ride.
   std::vector<uint32_t> tetRide;
   uint32_t riders = 0;
+  // fast arithmetic: per tet schedule position, the role permutation its record carries (see optimise_placement; empty:
+  // every tet as the caller gave it).  tetLocal is already in role order; an odd code means the record holds the negated
+  // rest volume and the tet's multiplier lives with the opposite sign.
+  std::vector<uint8_t> tetPerm;
 
   // introspection, caller indexing
   std::vector<uint32_t> edgePhase, edgeTile, edgeColor;
@@ -137,8 +141,20 @@ struct PlaceStats {
 // effort 0: keep numbering and order (statistics only).  block (a multiple of 8, 0 = the whole tile): a vertex
 // moves only inside its aligned block of that many indices, which keeps the tile's global loads / stores (thread i
 // <-> the slot at index i) as coalesced as they were.  Deterministic.
+// perm (one byte per constraint, or null): the four vertices of a TET may take its four roles in any order
+// (PBD_FLAG_FAST_ARITH); out: bits 2r..2r+1 = which of the tet's original vertices sits in role r (0xE4 = unchanged).
+// An odd permutation flips the sign of the tet's volume: the record builder negates its rest volume (and the sign
+// of its multiplier follows).
 void optimise_placement(uint32_t nLocal, const PlaceGroup* groups, uint32_t nGroups, uint32_t* loc, uint32_t* payload,
-                        uint32_t nCons, int effort, uint32_t block, std::vector<uint32_t>& newLocal, PlaceStats* stats);
+                        uint32_t nCons, int effort, uint32_t block, std::vector<uint32_t>& newLocal, PlaceStats* stats,
+                        uint8_t* perm = nullptr);
+// sign of a role permutation coded as above: true = odd
+inline bool tet_perm_is_odd(uint8_t code) {
+  int inv = 0;
+  for (int a = 0; a < 4; ++a)
+    for (int b = a + 1; b < 4; ++b) inv += ((code >> (2 * a)) & 3) > ((code >> (2 * b)) & 3);
+  return (inv & 1) != 0;
+}
 // rows of 8 by randomised greedy for given residues (4 bytes per constraint); out = constraint indices in row order
 void pack_rows_greedy(const uint8_t* res, uint32_t arity, uint32_t n, uint32_t seed, int tries, std::vector<uint32_t>& out);
 

@@ -853,7 +853,11 @@ class TileBackend final : public Backend {
         }
         tix[2 * q] = (uint32_t)l[0] | ((uint32_t)l[1] << 16);
         tix[2 * q + 1] = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
-        trs[q] = tRest[plan.tetDev[kk]];
+        // (a tet the planner relabelled by an odd permutation -- fast arithmetic only -- sees its signed volume negated:
+        // its record carries the negated rest volume, and its multiplier lives with the opposite sign)
+        const bool flipped = !plan.tetPerm.empty() && tet_perm_is_odd(plan.tetPerm[kk]);
+        if (flipped && !fast_) return cudaErrorInvalidConfiguration;   // the exact arithmetic follows the reference's evaluation order
+        trs[q] = flipped ? -tRest[plan.tetDev[kk]] : tRest[plan.tetDev[kk]];
       }
       if (t.ride) {
         uint32_t* rd = reinterpret_cast<uint32_t*>(b + offTetRide);

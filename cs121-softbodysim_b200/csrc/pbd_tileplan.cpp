@@ -61,6 +61,7 @@ struct PlanKnobs {
   int minTile;           // PBD_PLAN_MINTILE=n        smallest tile (vertices) before fewer SMs are used instead (default 1024)
   int riders;            // PBD_PLAN_RIDERS=n         PBD_ORDER_RIDING: most riders per tet (1 or 2, default 2)
   bool sigSort;          // PBD_PLAN_NOSIGSORT=1      home-tile slots in caller order instead of sorted by their shifted tiles
+  bool relabel;          // PBD_PLAN_NORELABEL=1      fast arithmetic: keep every tet's vertices in their roles
   int place;             // PBD_PLAN_PLACE=n          shared-memory placement search (pbd_placement.cpp): 0 = off, default 1
   int placeBlockHome;    // PBD_PLAN_PLACE_BH=n       ... a vertex of a home tile moves inside its aligned block of n indices (0: anywhere)
   int placeBlockShifted; // PBD_PLAN_PLACE_BS=n       ... the same for the shifted tiles
@@ -83,6 +84,7 @@ const PlanKnobs& knobs() {
     q.minTile = std::max(32, num("PBD_PLAN_MINTILE", 1024));
     q.riders = num("PBD_PLAN_RIDERS", 2);
     q.sigSort = !flag("PBD_PLAN_NOSIGSORT");
+    q.relabel = !flag("PBD_PLAN_NORELABEL");
     q.place = std::max(0, num("PBD_PLAN_PLACE", 1));
     q.placeBlockHome = std::max(0, num("PBD_PLAN_PLACE_BH", 8));
     q.placeBlockShifted = std::max(0, num("PBD_PLAN_PLACE_BS", 32));
@@ -414,6 +416,7 @@ struct TileBuild {
   bool mixed = false;                        // both lists share ONE colouring: colour s of either type = step s of the visit
   bool presetVerts = false;                  // verts holds the whole partition cell (tagged hand-over: every phase rewrites every vertex)
   uint32_t nRiders = 0;                      // PBD_ORDER_RIDING: edges that ride on this tile's tets (not in ty[0].cons)
+  std::vector<uint8_t> tetPerm;              // parallel to ty[1].cons after place_tile() with relabelling: role permutation codes (empty: none)
   std::vector<uint32_t> localPerm;           // contiguous tiles after place_tile(): slot rangeBegin + i moves to rangeBegin + localPerm[i]
 };
 
@@ -914,7 +917,8 @@ void bank_order(const CSet& cs, const std::vector<uint32_t>& localOf, uint32_t* 
 // reorders every colour group (same groups, same colours: no result changes).  Gathered tiles take the new
 // numbering by reordering their vertex list; a contiguous tile records it in localPerm and the planner
 // renumbers the slots of its range afterwards.  effort 0: statistics only.
-void place_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& localOf, int effort, uint32_t block, PlaceStats& stats) {
+// relabel: the tets' vertices may change roles (fast arithmetic; the permutation codes go to tb.tetPerm).
+void place_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& localOf, int effort, uint32_t block, bool relabel, PlaceStats& stats) {
   const uint32_t nLocal = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
   if (tb.contiguous) for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.rangeBegin + i] = i;
   else for (uint32_t i = 0; i < nLocal; ++i) localOf[tb.verts[i]] = i;
@@ -937,9 +941,11 @@ void place_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& localO
     typeBegin[ty + 1] = payload.size();
   }
   std::vector<uint32_t> newLocal;
+  std::vector<uint8_t> perm(relabel && effort > 0 ? payload.size() : 0);
   optimise_placement(nLocal, groups.data(), (uint32_t)groups.size(), loc.data(), payload.data(), (uint32_t)payload.size(), effort,
-                     block, newLocal, &stats);
+                     block, newLocal, &stats, perm.empty() ? nullptr : perm.data());
   if (effort <= 0) return;
+  if (!perm.empty()) tb.tetPerm.assign(perm.begin() + typeBegin[1], perm.begin() + typeBegin[2]);
   for (int ty = 0; ty < 2; ++ty)   // (colours are unchanged: the groups keep their places)
     std::copy(payload.begin() + typeBegin[ty], payload.begin() + typeBegin[ty + 1], tb.ty[ty].cons.begin());
   if (tb.contiguous) {
@@ -1815,6 +1821,9 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       // 8 host threads for the few percent the bank conflicts are worth, and every rank of a sharded body plans the whole body)
       const bool big = (uint64_t)m.T + m.E > 6000000ull && !getenv("PBD_PLAN_PLACE");
       const int effort = (opts.lanes_per_tet <= 1 && !riding && !big) ? knobs().place : 0;
+      // fast arithmetic: a tet's vertices may take its four roles in any order (same classes, same rows of edges, same
+      // slot numbering as the exact mode's plan -- only the tets' rows and roles differ)
+      const bool relabel = (opts.flags & PBD_FLAG_FAST_ARITH) != 0u && knobs().relabel;
       const unsigned nThreads = (m.T + m.E < 200000u) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
       std::vector<PlaceStats> st(nThreads);
       std::vector<std::vector<uint32_t>> los(nThreads > 1 ? nThreads - 1 : 0, std::vector<uint32_t>(m.V, NONE));
@@ -1825,7 +1834,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
             if (!tb.ty[0].cons.empty() || !tb.ty[1].cons.empty()) work.push_back(&tb);
         std::atomic<size_t> next{0};
         auto worker = [&](std::vector<uint32_t>& lo, PlaceStats& ps) {
-          for (size_t i; (i = next.fetch_add(1)) < work.size();) place_tile(sets, *work[i], lo, effort, block, ps);
+          for (size_t i; (i = next.fetch_add(1)) < work.size();) place_tile(sets, *work[i], lo, effort, block, relabel, ps);
         };
         std::vector<std::thread> pool;
         for (size_t i = 0; i < los.size(); ++i) pool.emplace_back(worker, std::ref(los[i]), std::ref(st[i + 1]));
@@ -1911,6 +1920,12 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     plan.edgeDev.reserve(m.E); plan.tetDev.reserve(m.T);
     plan.edgePhase.assign(m.E, 0); plan.edgeTile.assign(m.E, 0); plan.edgeColor.assign(m.E, 0);
     plan.tetPhase.assign(m.T, 0); plan.tetTile.assign(m.T, 0); plan.tetColor.assign(m.T, 0);
+    {
+      bool anyPerm = false;
+      for (uint32_t p = 0; p < K && !anyPerm; ++p)
+        for (auto& tb : mainPh[p]) if (!tb.tetPerm.empty()) { anyPerm = true; break; }
+      if (anyPerm) plan.tetPerm.assign(m.T, (uint8_t)0xE4);
+    }
     for (uint32_t t = 0; t < nTile0; ++t) plan.tileVertexCapacity = std::max(plan.tileVertexCapacity, tile0Begin[t + 1] - tile0Begin[t]);
     uint32_t devCur[2] = {0, 0};
     std::vector<uint32_t> ridePos(riding ? m.E : 0u, NONE);   // rider edge -> its schedule position
@@ -1976,7 +1991,9 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
                 cPhase[c] = (uint32_t)plan.phases.size();
                 cTile[c] = (uint32_t)plan.tiles.size();
                 cCol[c] = sIdx;
-                for (uint32_t a = 0; a < cs.arity; ++a) local.push_back((uint16_t)localOf[cs.at(c)[a]]);
+                const uint8_t code = (ty == 1 && !tb.tetPerm.empty()) ? tb.tetPerm[k] : (uint8_t)0xE4;
+                if (ty == 1 && !plan.tetPerm.empty()) plan.tetPerm[order.size()] = code;
+                for (uint32_t a = 0; a < cs.arity; ++a) local.push_back((uint16_t)localOf[cs.at(c)[(code >> (2 * a)) & 3u]]);
                 order.push_back(c);
                 dev.push_back(devCur[ty]++);
               }
@@ -2002,7 +2019,9 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
               cPhase[c] = (uint32_t)plan.phases.size();
               cTile[c] = (uint32_t)plan.tiles.size();
               cCol[c] = L.colour[k];
-              for (uint32_t a = 0; a < cs.arity; ++a) local.push_back((uint16_t)localOf[cs.at(c)[a]]);
+              const uint8_t code = (ty == 1 && !tb.tetPerm.empty()) ? tb.tetPerm[k] : (uint8_t)0xE4;
+              if (ty == 1 && !plan.tetPerm.empty()) plan.tetPerm[order.size()] = code;
+              for (uint32_t a = 0; a < cs.arity; ++a) local.push_back((uint16_t)localOf[cs.at(c)[(code >> (2 * a)) & 3u]]);
               order.push_back(c);
               dev.push_back(devCur[ty]++);
             }

@@ -12,7 +12,7 @@
 #include "../cs121-softbodysim_b200/csrc/pbd_plan.h"
 
 int main(int argc, char** argv) {
-  if (argc < 2) { fprintf(stderr, "usage: place_bench dump.bin [effort] [block]\n"); return 2; }
+  if (argc < 2) { fprintf(stderr, "usage: place_bench dump.bin [effort] [block] [relabel]\n"); return 2; }
   FILE* f = fopen(argv[1], "rb");
   if (!f) { perror(argv[1]); return 1; }
   uint32_t hdr[3];
@@ -24,12 +24,14 @@ int main(int argc, char** argv) {
   for (uint32_t i = 0; i < hdr[2]; ++i) payload[i] = i;
   const int effort = argc > 2 ? atoi(argv[2]) : 1;
   const uint32_t block = argc > 3 ? (uint32_t)atoi(argv[3]) : 0u;
+  const bool relabel = argc > 4 && atoi(argv[4]) != 0;   // tets may permute their vertices (fast arithmetic)
   printf("tile: %u vertices, %u groups, %u constraints\n", hdr[0], hdr[1], hdr[2]);
   for (int e : {0, effort}) {
     std::vector<uint32_t> l = loc, p = payload, nl;
+    std::vector<uint8_t> pm(hdr[2]);
     pbd::PlaceStats st;
     const auto t0 = std::chrono::steady_clock::now();
-    pbd::optimise_placement(hdr[0], groups.data(), hdr[1], l.data(), p.data(), hdr[2], e, block, nl, &st);
+    pbd::optimise_placement(hdr[0], groups.data(), hdr[1], l.data(), p.data(), hdr[2], e, block, nl, &st, relabel && e ? pm.data() : nullptr);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     printf("effort %d: edges %.3f (%llu / %llu)  tets %.3f (%llu / %llu)   %.1f ms\n", e, (double)st.wavefronts[0] / std::max<uint64_t>(1, st.ideal[0]),
            (unsigned long long)st.wavefronts[0], (unsigned long long)st.ideal[0], (double)st.wavefronts[1] / std::max<uint64_t>(1, st.ideal[1]),
