@@ -306,6 +306,8 @@ struct Optimiser {
   std::vector<uint16_t> gcap;  // per group: ceil(count / 8)
   Lcg rng{0x9e3779b9u};
 
+  bool merged(uint32_t g) const { return perm != nullptr && groups[g].arity == 4; }
+
   void build_incidence() {
     incOff.assign((size_t)nLocal + 1, 0);
     for (uint32_t c = 0; c < nCons; ++c)
@@ -325,7 +327,7 @@ struct Optimiser {
   int64_t move_hist(uint32_t v, uint8_t from, uint8_t to) {
     int64_t d = 0;
     for (uint32_t a = incOff[v]; a < incOff[v + 1]; ++a) {
-      const uint32_t c = inc[a] >> 2, r = inc[a] & 3u, g = groupOf[c];
+      const uint32_t c = inc[a] >> 2, g = groupOf[c], r = merged(g) ? 0u : (inc[a] & 3u);
       uint16_t* h = &gcnt[((size_t)g * 4 + r) * 8];
       const uint16_t cap = gcap[g];
       d -= 2 * (int64_t)h[from] - 1; if (h[from] > cap) d -= 64; h[from]--;
@@ -342,16 +344,17 @@ struct Optimiser {
   void balance_classes(int passes, uint32_t candidates) {
     gcnt.assign((size_t)nGroups * 32, 0);
     gcap.resize(nGroups);
-    for (uint32_t g = 0; g < nGroups; ++g) gcap[g] = (uint16_t)((groups[g].count + 7) / 8);
+    // (relabelled tets: the roles are dealt out per row afterwards, so a group's four roles share ONE histogram, four times as deep)
+    for (uint32_t g = 0; g < nGroups; ++g) gcap[g] = (uint16_t)((merged(g) ? 4u : 1u) * ((groups[g].count + 7) / 8));
     for (uint32_t c = 0; c < nCons; ++c)
       for (uint32_t r = 0; r < 4; ++r)
-        if (loc[4 * (size_t)c + r] != NONE) gcnt[((size_t)groupOf[c] * 4 + r) * 8 + cls[loc[4 * (size_t)c + r]]]++;
+        if (loc[4 * (size_t)c + r] != NONE) gcnt[((size_t)groupOf[c] * 4 + (merged(groupOf[c]) ? 0u : r)) * 8 + cls[loc[4 * (size_t)c + r]]]++;
     std::vector<uint32_t> hot;
     for (int pass = 0; pass < passes; ++pass) {
       hot.clear();
       for (uint32_t v = 0; v < nLocal; ++v)
         for (uint32_t a = incOff[v]; a < incOff[v + 1]; ++a) {
-          const uint32_t c = inc[a] >> 2, r = inc[a] & 3u, g = groupOf[c];
+          const uint32_t c = inc[a] >> 2, g = groupOf[c], r = merged(g) ? 0u : (inc[a] & 3u);
           if (gcnt[((size_t)g * 4 + r) * 8 + cls[v]] > gcap[g]) { hot.push_back(v); break; }
         }
       if (hot.empty()) break;

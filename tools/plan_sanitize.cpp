@@ -58,7 +58,10 @@ int main(int argc, char** argv) {
   struct Case { uint32_t order, tileVerts, partitions, lanes, flags; };
   const Case cases[] = {{PBD_ORDER_STRICT, 0, 0, 0, 0}, {PBD_ORDER_INTERLEAVED, 0, 0, 0, 0}, {PBD_ORDER_RIDING, 0, 0, 0, 0},
                         {PBD_ORDER_RIDING, 150, 3, 0, PBD_FLAG_TAGGED_HANDOVER}, {PBD_ORDER_INTERLEAVED, 90, 5, 4, 0},
-                        {PBD_ORDER_STRICT, 64, 2, 2, 0}};
+                        {PBD_ORDER_STRICT, 64, 2, 2, 0},
+                        // the placement search with relabelled tets (fast arithmetic), home and shifted tiles
+                        {PBD_ORDER_INTERLEAVED, 0, 0, 0, PBD_FLAG_TAGGED_HANDOVER | PBD_FLAG_FAST_ARITH},
+                        {PBD_ORDER_INTERLEAVED, 120, 0, 1, PBD_FLAG_TAGGED_HANDOVER | PBD_FLAG_FAST_ARITH}};
   for (const Case& c : cases) {
     pbd_options o;
     memset(&o, 0, sizeof o);
@@ -72,6 +75,13 @@ int main(int argc, char** argv) {
     for (uint32_t t : plan.tetOrder) seenT[t]++;
     for (uint8_t s : seenE) rc |= s != 1;
     for (uint8_t s : seenT) rc |= s != 1;
+    // a relabelled tet still names its own four vertices, each once (tetLocal is in role order)
+    if (!plan.tetPerm.empty())
+      for (uint32_t k = 0; k < m.T; ++k) {
+        uint32_t used = 0;
+        for (int r = 0; r < 4; ++r) used |= 1u << ((plan.tetPerm[k] >> (2 * r)) & 3u);
+        rc |= used != 15u;
+      }
     printf("order %u tv %u K %u lanes %u flags %u: %zu tiles, %zu phases, %u riders, %.0f ms\n", c.order, c.tileVerts, c.partitions, c.lanes,
            c.flags, plan.tiles.size(), plan.phases.size(), plan.riders, plan.planMs);
   }
