@@ -984,7 +984,7 @@ void order_groups(const CSet sets[2], TileBuild& tb, const std::vector<uint32_t>
 }
 
 void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& localOf, std::vector<uint32_t>& scratch,
-                 const uint32_t caps[2], uint32_t mixedThreads = 0) {
+                 const uint32_t caps[2], uint32_t mixedThreads = 0, bool orderGroups = true) {
   uint32_t nLocal;
   if (tb.contiguous) {
     nLocal = tb.rangeCount;
@@ -1011,7 +1011,7 @@ void finish_tile(const CSet sets[2], TileBuild& tb, std::vector<uint32_t>& local
     TypeList& L = tb.ty[ty];
     if (L.cons.empty()) continue;
     if (!tb.mixed) colour_list(sets[ty], L, nLocal, localOf, scratch, caps[ty]);
-    order_groups(sets, tb, localOf, ty);
+    if (orderGroups) order_groups(sets, tb, localOf, ty);   // (main tiles the placement search will reorder anyway skip this)
   }
 }
 
@@ -1678,6 +1678,13 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       PBD_PLAN_STAGE("  tile balance");
     }
     PBD_PLAN_STAGE("assignment");
+    // shared-memory placement search after the colouring (pbd_placement.cpp): one thread per constraint only (the 2- and
+    // 4-lane tet sweeps and the riding order address shared memory differently); bodies beyond ~2.5M tets skip it unless
+    // PBD_PLAN_PLACE asks for it -- it costs ~2 s per million tets on 8 host threads for the few percent the bank
+    // conflicts are worth, and every rank of a sharded body plans the whole body
+    const bool bigBody = (uint64_t)m.T + m.E > 6000000ull && !getenv("PBD_PLAN_PLACE");
+    const int placeEffort = (opts.lanes_per_tet <= 1 && !riding && !bigBody) ? knobs().place : 0;
+    const bool willPlace = placeEffort > 0;
     // ---- finish the main tiles (independent of each other: spread over host threads; the result
     // does not depend on the thread count)
     bool fits = true;
@@ -1721,7 +1728,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
         for (size_t i; (i = next.fetch_add(1)) < work.size();) {
           if (!ok.load(std::memory_order_relaxed)) break;   // some tile does not fit: this attempt is void anyway
           TileBuild& tb = *work[i];
-          finish_tile(sets, tb, lo, sc, caps, mixedThreads);
+          finish_tile(sets, tb, lo, sc, caps, mixedThreads, !willPlace);
           const uint32_t nv = tb.contiguous ? tb.rangeCount : (uint32_t)tb.verts.size();
           if (nv > 65535u || tile_bytes(tb, riding) > smemBytes) ok = false;
         }
@@ -1779,8 +1786,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
                 tb.ty[1] = std::move(trial.ty[1]);
               }
             }
-            order_groups(sets, tb, lo, 0);
-            order_groups(sets, tb, lo, 1);
+            if (!willPlace) { order_groups(sets, tb, lo, 0); order_groups(sets, tb, lo, 1); }
             continue;
           }
           for (uint32_t attempt2 = 0; attempt2 < 4 && L.nColours > goal; ++attempt2) {
@@ -1789,7 +1795,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
             colour_list(sets[ty], trial, nLocal, lo, sc, caps[ty], 160, goal, 0x85ebca6bu * (attempt2 + 1));
             if (trial.nColours < L.nColours) L = std::move(trial);
           }
-          order_groups(sets, tb, lo, ty);
+          if (!willPlace) order_groups(sets, tb, lo, ty);
         }
       };
       // two jobs may share a tile (its edge list and its tet list): they touch different TypeLists
@@ -1817,10 +1823,7 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     // (home: 8 = one 128-byte line of vertex words, shifted: 32 = one warp): measured without that restriction,
     // the scattered global loads / stores of the tile visits cost more than the bank conflicts saved.
     {
-      // (bodies beyond ~2.5M tets skip the search unless PBD_PLAN_PLACE asks for it: it costs ~2 s per million tets on
-      // 8 host threads for the few percent the bank conflicts are worth, and every rank of a sharded body plans the whole body)
-      const bool big = (uint64_t)m.T + m.E > 6000000ull && !getenv("PBD_PLAN_PLACE");
-      const int effort = (opts.lanes_per_tet <= 1 && !riding && !big) ? knobs().place : 0;
+      const int effort = placeEffort;
       // fast arithmetic: a tet's vertices may take its four roles in any order (same classes, same rows of edges, same
       // slot numbering as the exact mode's plan -- only the tets' rows and roles differ)
       const bool relabel = (opts.flags & PBD_FLAG_FAST_ARITH) != 0u && knobs().relabel;
