@@ -105,18 +105,19 @@ struct SpinGuard {
   uint32_t polls = 0;
   long long t0 = 0;
 };
-__device__ __forceinline__ bool spin_expired(SpinGuard& g, const TileParams& P) {
+__device__ __forceinline__ bool spin_expired(SpinGuard& g, unsigned* abortWord, unsigned* abortHost, long long spinLimit) {
   if ((++g.polls & 1023u) != 0u) return false;
   if (g.polls == 1024u) g.t0 = clock64();
-  if (ld_acquire(P.abortWord) != 0u) return true;
-  if (clock64() - g.t0 > P.spinLimit) {
-    atomicExch(P.abortWord, 1u);
-    *reinterpret_cast<volatile unsigned*>(P.abortHost) = 1u;
+  if (ld_acquire(abortWord) != 0u) return true;
+  if (clock64() - g.t0 > spinLimit) {
+    atomicExch(abortWord, 1u);
+    *reinterpret_cast<volatile unsigned*>(abortHost) = 1u;
     __threadfence_system();
     return true;
   }
   return false;
 }
+__device__ __forceinline__ bool spin_expired(SpinGuard& g, const TileParams& P) { return spin_expired(g, P.abortWord, P.abortHost, P.spinLimit); }
 // done counters and barrier epochs only ever grow and may wrap: compare by signed distance
 __device__ __forceinline__ bool reached(unsigned have, unsigned need) { return (int)(have - need) >= 0; }
 
@@ -160,11 +161,25 @@ __device__ __forceinline__ void st_tagged(uint4* p, float4 q, uint32_t tag, bool
 __device__ __forceinline__ float4 tagged_value(uint4 r, float w) {
   return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), w);
 }
+// (out of line, and with scalar arguments only -- a reference to the launch parameters would force a copy of them into local
+// memory: the slow path of a vertex load, taken when the word's tag was not there yet.  Keeping its spin and the
+// bounded-wait bookkeeping out of the unrolled load loops shortens the kernel and frees registers around them.)
+__device__ __noinline__ float4 tagged_wait_slow(const uint4* word, uint32_t expect, float w, bool sys, unsigned* abortWord,
+                                                unsigned* abortHost, long long spinLimit) {
+  SpinGuard g;
+  uint4 r;
+  do { r = ld_tagged(word, sys); } while (r.w != expect && !spin_expired(g, abortWord, abortHost, spinLimit));
+  return tagged_value(r, w);
+}
 __device__ __forceinline__ float4 tagged_wait_load(const TileParams& P, const uint4* word, uint32_t expect, float w, bool sys) {
+#ifdef PBD_X_INLINE_WAIT
   SpinGuard g;
   uint4 r;
   do { r = ld_tagged(word, sys); } while (r.w != expect && !spin_expired(g, P));
   return tagged_value(r, w);
+#else
+  return tagged_wait_slow(word, expect, w, sys, P.abortWord, P.abortHost, P.spinLimit);
+#endif
 }
 __device__ __forceinline__ float4 tagged_load_any(const TileParams& P, uint32_t s) {   // own earlier write: no wait
   return tagged_value(ld_tagged(P.posT + s, P.world > 1), __ldg(P.invMass + s));
