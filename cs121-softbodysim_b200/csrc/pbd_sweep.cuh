@@ -109,7 +109,7 @@ PBD_DEV void project_tet_rec(uint32_t sv, uint2 id, float r, float l, uint32_t l
   const uint32_t c = sv + ((id.y & 0xffffu) << 4), d = sv + ((id.y >> 16) << 4);
   float4 pa = lds_v4(a), pb = lds_v4(b), pc = lds_v4(c), pd = lds_v4(d);
   float nl;
-  if (FAST ? tet_delta_fast(pa, pb, pc, pd, r, l, alpha, nl) : tet_delta(pa, pb, pc, pd, r, l, alpha, nl)) {
+  if (FAST ? tet_delta_fast(pa, pb, pc, pd, r, l, alpha, nl, !useLam) : tet_delta(pa, pb, pc, pd, r, l, alpha, nl)) {
     sts_v4(a, pa); sts_v4(b, pb); sts_v4(c, pc); sts_v4(d, pd);
     if (useLam) sts_f32(lamA, nl);
   }
@@ -157,7 +157,7 @@ PBD_DEV void project_tet_unit_fast(uint32_t sv, uint32_t idA, uint32_t restA, ui
   {
     float4 qa = pa, qb = pb, qc = pc, qd = pd;
     float nl;
-    if (tet_delta_fast(qa, qb, qc, qd, r, l, alphaT, nl)) { pa = qa; pb = qb; pc = qc; pd = qd; if (useLam) sts_f32(lamA, nl); }
+    if (tet_delta_fast(qa, qb, qc, qd, r, l, alphaT, nl, !useLam)) { pa = qa; pb = qb; pc = qc; pd = qd; if (useLam) sts_f32(lamA, nl); }
   }
   if (has0) {
     float4 q0, q1;
@@ -463,7 +463,7 @@ PBD_SWEEP_INLINE void sweep_mixed(const TileHdr& h, uint32_t rec, uint32_t svOff
     PBD_STEP_TRACE(ft, g, 0);
   }
 #else
-  // a mixed tile's two group tables are stored as ONE table of {edge begin, edge count, tet begin, tet count}
+  // a mixed tile's two group tables are stored as ONE table of {edge begin, edge count, tet begin, first tet thread}
   // entries (pbd_tile.cu upload; the two sections are adjacent and together exactly that large): one LDS.128
   // per step and warp instead of two LDS.64
   (void)tGrp;
@@ -474,7 +474,14 @@ PBD_SWEEP_INLINE void sweep_mixed(const TileHdr& h, uint32_t rec, uint32_t svOff
     if (tid < ge.y) {
       const uint32_t o = ge.x << 2;
       project_edge_at<FAST>(sv, eIdA + o, eRestA + o, eLamA + o, alphaE);
+#ifndef PBD_X_TET_COUNT_ENTRY
+    // the entry's fourth word is the block's FIRST tet thread (block size - tet count, written by the upload): comparing
+    // the count with blockDim.x - 1 - tid made the tet warps -- the ones the step's barrier waits for -- rebuild that
+    // number in every step (a constant-bank load and two integer instructions ahead of their first shared load)
+    } else if (tid >= gt.y) {
+#else
     } else if (rtid < gt.y) {
+#endif
       const uint32_t o = gt.x << 2;
       if (FAST && ride && kRegRiders) {
         project_tet_unit_fast(sv, tIdA + 2u * o, tRestA + o, tLamA + o, alphaT, rideA + o, eRest0, eLam0, alphaE, useTetLam);
@@ -484,7 +491,11 @@ PBD_SWEEP_INLINE void sweep_mixed(const TileHdr& h, uint32_t rec, uint32_t svOff
       }
     }
     __syncthreads();
+#ifndef PBD_X_TET_COUNT_ENTRY
+    PBD_STEP_TRACE(ft, g, ge.y + ((blockDim.x - gt.y) << 16));
+#else
     PBD_STEP_TRACE(ft, g, ge.y + (gt.y << 16));
+#endif
   }
 #endif
 }

@@ -824,14 +824,18 @@ class TileBackend final : public Backend {
         tg[2 * g + 1] = plan.groups[t.tetGroupBegin + g].count;
       }
       if (t.mixed) {
-        // mixed steps read ONE table of {edge begin, edge count, tet begin, tet count} entries: the two sections
+        // mixed steps read ONE table of {edge begin, edge count, tet begin, first tet thread} entries: the two sections
         // are adjacent, equally long (same group count) and together hold exactly 16 bytes per step
         if (h.offTetGroups != h.offEdgeGroups + 8u * (pad4(t.edgeGroupCount * 2) / 2) || t.edgeGroupCount != t.tetGroupCount) return cudaErrorUnknown;
         for (uint32_t g = 0; g < t.edgeGroupCount; ++g) {
           eg[4 * g] = plan.groups[t.edgeGroupBegin + g].begin - t.edgeBegin;
           eg[4 * g + 1] = plan.groups[t.edgeGroupBegin + g].count;
           eg[4 * g + 2] = plan.groups[t.tetGroupBegin + g].begin - t.tetBegin;
+#ifndef PBD_X_TET_COUNT_ENTRY
+          eg[4 * g + 3] = block_ - plan.groups[t.tetGroupBegin + g].count;   // the first tet thread (tets sit on the block's last threads)
+#else
           eg[4 * g + 3] = plan.groups[t.tetGroupBegin + g].count;
+#endif
         }
       }
       uint32_t* ei = reinterpret_cast<uint32_t*>(b + h.offEdgeIdx);
