@@ -208,9 +208,11 @@ PBD_DEV bool edge_delta_fast(const float4 p0, const float4 p1, float rest, float
 // denominator drop out -- bit-neutral, one instruction less on the dependent path.
 // The dependent path is what a colour step waits for (a block has ~3 tet warps per step and its barrier waits for
 // them), so its length counts, not the instruction count: the three cross-product terms of wS come first and the
-// -(nb + nc + nd) term, ready two additions later, last; and everything that does not need the reciprocal -- the four
-// w_k * (-C / 6) -- is formed while the SFU computes it, so that ONE multiplication and the FFMAs follow MUFU.RCP
-// instead of three and the FFMAs.  (PBD_X_OLD_TETCHAIN: the previous order, for A/B timing.)
+// -(nb + nc + nd) term, ready two additions later, last; and the four w_k * (-C / 6) are formed while the SFU computes
+// the reciprocal, so that ONE multiplication and the FFMAs follow MUFU.RCP instead of three and the FFMAs: +1.2 % on the
+// headline.  Measured and not kept: forming the twelve n_k w_k t products under the reciprocal as well (one FFMA after
+// MUFU.RCP: -1.5 %, twelve more instructions on the warps everybody waits for); folding the 1/36 into the scalar when the
+// multiplier is inert (would end the bit-identity with the kernel that carries it).
 PBD_DEV bool tet_delta_fast(float4& pa, float4& pb, float4& pc, float4& pd, float rest, float lambda, float alpha,
                             float& newLambda, bool inert = false) {
   const float k6 = 1.0f / 6.0f, k36 = 1.0f / 36.0f;
@@ -224,34 +226,19 @@ PBD_DEV bool tet_delta_fast(float4& pa, float4& pb, float4& pc, float4& pd, floa
   const float ndx = cross_f(bay, caz, baz, cay), ndy = cross_f(baz, cax, bax, caz), ndz = cross_f(bax, cay, bay, cax);
   // na = (pd - pb) x (pc - pb) = -(nb + nc + nd)   (Sim.cpp:146); ma = -na
   const float max_ = fadd(fadd(nbx, ncx), ndx), may = fadd(fadd(nby, ncy), ndy), maz = fadd(fadd(nbz, ncz), ndz);
-#ifdef PBD_X_OLD_TETCHAIN
-  float wS = fmul(wa, dot3_f(max_, may, maz, max_, may, maz));
-  wS = ffma(wb, dot3_f(nbx, nby, nbz, nbx, nby, nbz), wS);
-  wS = ffma(wc, dot3_f(ncx, ncy, ncz, ncx, ncy, ncz), wS);
-  wS = ffma(wd, dot3_f(ndx, ndy, ndz, ndx, ndy, ndz), wS);     // 36 * sum w_k |g_k|^2
-#else
   float wS = fmul(wb, dot3_f(nbx, nby, nbz, nbx, nby, nbz));
   wS = ffma(wc, dot3_f(ncx, ncy, ncz, ncx, ncy, ncz), wS);
   wS = ffma(wd, dot3_f(ndx, ndy, ndz, ndx, ndy, ndz), wS);
   wS = ffma(wa, dot3_f(max_, may, maz, max_, may, maz), wS);   // 36 * sum w_k |g_k|^2
-#endif
   const bool ok = !(wS < 36.0e-20f);                            // also false when every w is 0 (Sim.cpp:143,155)
   const float C = ffma(dot3_f(ndx, ndy, ndz, dax, day, daz), k6, -rest);   // volume - rest
-#ifdef PBD_X_OLD_TETCHAIN
-  (void)inert;
-  const float num = ffma(alpha, lambda, C);
-  const float dl = fmul(-num, rcp_fast(ffma(wS, k36, alpha)));
-  newLambda = fadd(lambda, dl);
-  const float dl6 = fmul(dl, k6);
-  const float sa = fmul(wa, dl6), sb = fmul(wb, dl6), sc = fmul(wc, dl6), sd = fmul(wd, dl6);
-#else
+  // dl = -num / (wS / 36 + alpha); s_k = w_k dl / 6
   const float num = inert ? C : ffma(alpha, lambda, C);
   const float rc = rcp_fast(inert ? fmul(wS, k36) : ffma(wS, k36, alpha));
   const float t = fmul(num, -k6);
   const float ta = fmul(wa, t), tb = fmul(wb, t), tc = fmul(wc, t), td = fmul(wd, t);
   newLambda = fadd(lambda, fmul(-num, rc));
   const float sa = fmul(ta, rc), sb = fmul(tb, rc), sc = fmul(tc, rc), sd = fmul(td, rc);
-#endif
   pa.x = ffma(max_, -sa, pa.x); pa.y = ffma(may, -sa, pa.y); pa.z = ffma(maz, -sa, pa.z);
   pb.x = ffma(nbx, sb, pb.x); pb.y = ffma(nby, sb, pb.y); pb.z = ffma(nbz, sb, pb.z);
   pc.x = ffma(ncx, sc, pc.x); pc.y = ffma(ncy, sc, pc.y); pc.z = ffma(ncz, sc, pc.z);

@@ -8,6 +8,7 @@
 // Reference lines restated: CProgram/src/Sim.cpp:104-129 (edge), :136-172 (tet), via pbd_math.cuh.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 
 #include "pbd_math.cuh"
 
@@ -82,10 +83,24 @@ PBD_DEV uint32_t smem_window(const void* p) {
   return r;
 }
 
+// Shared address of the vertex a packed 16-bit tile-local index names: sv + 16 * index.  Written as AND / SHR + multiply-add
+// in PTX (ptxas: LOP3 or SHF, then LEA) -- the C form (x & 0xffff) << 4 is canonicalised to shift, mask, add: three dependent
+// instructions between the index load and the vertex gather instead of two: +2.0 % on the headline (fast), measured.
+PBD_DEV uint32_t vert_lo(uint32_t sv, uint32_t id) {
+  uint32_t a;
+  asm("{\n\t.reg .u32 t;\n\tand.b32 t, %1, 0xffff;\n\tmad.lo.u32 %0, t, 16, %2;\n\t}" : "=r"(a) : "r"(id), "r"(sv));
+  return a;
+}
+PBD_DEV uint32_t vert_hi(uint32_t sv, uint32_t id) {
+  uint32_t a;
+  asm("{\n\t.reg .u32 t;\n\tshr.u32 t, %1, 16;\n\tmad.lo.u32 %0, t, 16, %2;\n\t}" : "=r"(a) : "r"(id), "r"(sv));
+  return a;
+}
+
 // one edge / one tet whose record sits at the given shared addresses; sv = address of the tile's vertex 0
 template <bool FAST>
 PBD_DEV void project_edge_rec(uint32_t sv, uint32_t id, float r, float l, uint32_t lamA, float alpha) {
-  const uint32_t a = sv + ((id & 0xffffu) << 4), b = sv + ((id >> 16) << 4);
+  const uint32_t a = vert_lo(sv, id), b = vert_hi(sv, id);
   const float4 p0 = lds_v4(a), p1 = lds_v4(b);
   float4 q0, q1;
   float nl;
@@ -105,8 +120,7 @@ PBD_DEV void project_edge_at(uint32_t sv, uint32_t idA, uint32_t restA, uint32_t
 // neither read nor accumulated (see tile_frame_kernel: its range is not moved between global and shared memory either)
 template <bool FAST>
 PBD_DEV void project_tet_rec(uint32_t sv, uint2 id, float r, float l, uint32_t lamA, float alpha, bool useLam = true) {
-  const uint32_t a = sv + ((id.x & 0xffffu) << 4), b = sv + ((id.x >> 16) << 4);
-  const uint32_t c = sv + ((id.y & 0xffffu) << 4), d = sv + ((id.y >> 16) << 4);
+  const uint32_t a = vert_lo(sv, id.x), b = vert_hi(sv, id.x), c = vert_lo(sv, id.y), d = vert_hi(sv, id.y);
   float4 pa = lds_v4(a), pb = lds_v4(b), pc = lds_v4(c), pd = lds_v4(d);
   float nl;
   if (FAST ? tet_delta_fast(pa, pb, pc, pd, r, l, alpha, nl, !useLam) : tet_delta(pa, pb, pc, pd, r, l, alpha, nl)) {
@@ -146,8 +160,7 @@ PBD_DEV void project_tet_unit_fast(uint32_t sv, uint32_t idA, uint32_t restA, ui
   const uint2 id = lds_v2(idA);
   const float r = lds_f32(restA), l = useLam ? lds_f32(lamA) : 0.0f;
   const uint32_t rp = lds_u32(rideWordA);
-  const uint32_t a = sv + ((id.x & 0xffffu) << 4), b = sv + ((id.x >> 16) << 4);
-  const uint32_t c = sv + ((id.y & 0xffffu) << 4), d = sv + ((id.y >> 16) << 4);
+  const uint32_t a = vert_lo(sv, id.x), b = vert_hi(sv, id.x), c = vert_lo(sv, id.y), d = vert_hi(sv, id.y);
   float4 pa = lds_v4(a), pb = lds_v4(b), pc = lds_v4(c), pd = lds_v4(d);
   const uint32_t p0 = (rp & 0xffffu) << 2, p1 = (rp >> 16) << 2;
   const bool has0 = p0 != (0xffffu << 2), has1 = p1 != (0xffffu << 2);
@@ -466,37 +479,35 @@ PBD_SWEEP_INLINE void sweep_mixed(const TileHdr& h, uint32_t rec, uint32_t svOff
   // a mixed tile's two group tables are stored as ONE table of {edge begin, edge count, tet begin, first tet thread}
   // entries (pbd_tile.cu upload; the two sections are adjacent and together exactly that large): one LDS.128
   // per step and warp instead of two LDS.64
-  (void)tGrp;
-  for (uint32_t g = 0; g < n; ++g, eGrp += 16u) {
-    // (fetching the NEXT step's entry before this step's barrier was measured too: -2.2 % fast, -3.9 % exact)
-    const uint4 gq = lds_v4u(eGrp);
-    const uint2 ge = make_uint2(gq.x, gq.y), gt = make_uint2(gq.z, gq.w);
-    if (tid < ge.y) {
-      const uint32_t o = ge.x << 2;
-      project_edge_at<FAST>(sv, eIdA + o, eRestA + o, eLamA + o, alphaE);
-#ifndef PBD_X_TET_COUNT_ENTRY
-    // the entry's fourth word is the block's FIRST tet thread (block size - tet count, written by the upload): comparing
-    // the count with blockDim.x - 1 - tid made the tet warps -- the ones the step's barrier waits for -- rebuild that
-    // number in every step (a constant-bank load and two integer instructions ahead of their first shared load)
-    } else if (tid >= gt.y) {
-#else
-    } else if (rtid < gt.y) {
-#endif
-      const uint32_t o = gt.x << 2;
-      if (FAST && ride && kRegRiders) {
-        project_tet_unit_fast(sv, tIdA + 2u * o, tRestA + o, tLamA + o, alphaT, rideA + o, eRest0, eLam0, alphaE, useTetLam);
-      } else {
-        project_tet_at<FAST>(sv, tIdA + 2u * o, tRestA + o, tLamA + o, alphaT, useTetLam);
-        if (ride) project_riders<FAST>(sv, rideA, o, eIdx0, eRest0, eLam0, alphaE);
+  (void)tGrp; (void)rtid;
+  // The step's barrier waits for the tet warps (~100 dependent instructions against the edges' ~40), so whatever sits
+  // between the entry load and a tet thread's first shared load is on the step's critical path: the tet test compares
+  // with the entry's fourth word = the block's first tet thread (block size - tet count, written by the upload --
+  // comparing a count with blockDim.x - 1 - tid made the compiler rebuild that number in every step), and the
+  // per-tile `ride` switch is taken once per visit, not once per step.
+  // (Measured and not kept: the tet test ahead of the edge test, -1.4 %; fetching the NEXT step's entry before this
+  // step's barrier, -2.2 % fast, -3.9 % exact.)
+  auto steps = [&](auto withRiders) {
+    constexpr bool RIDE = decltype(withRiders)::value;
+    for (uint32_t g = 0; g < n; ++g, eGrp += 16u) {
+      const uint4 gq = lds_v4u(eGrp);
+      if (tid < gq.y) {
+        const uint32_t o = gq.x << 2;
+        project_edge_at<FAST>(sv, eIdA + o, eRestA + o, eLamA + o, alphaE);
+      } else if (tid >= gq.w) {
+        const uint32_t o = gq.z << 2;
+        if (FAST && RIDE && kRegRiders) {
+          project_tet_unit_fast(sv, tIdA + 2u * o, tRestA + o, tLamA + o, alphaT, rideA + o, eRest0, eLam0, alphaE, useTetLam);
+        } else {
+          project_tet_at<FAST>(sv, tIdA + 2u * o, tRestA + o, tLamA + o, alphaT, useTetLam);
+          if (RIDE) project_riders<FAST>(sv, rideA, o, eIdx0, eRest0, eLam0, alphaE);
+        }
       }
+      __syncthreads();
+      PBD_STEP_TRACE(ft, g, gq.y + ((blockDim.x - gq.w) << 16));
     }
-    __syncthreads();
-#ifndef PBD_X_TET_COUNT_ENTRY
-    PBD_STEP_TRACE(ft, g, ge.y + ((blockDim.x - gt.y) << 16));
-#else
-    PBD_STEP_TRACE(ft, g, ge.y + (gt.y << 16));
-#endif
-  }
+  };
+  if (ride) steps(std::true_type{}); else steps(std::false_type{});
 #endif
 }
 

@@ -831,11 +831,7 @@ class TileBackend final : public Backend {
           eg[4 * g] = plan.groups[t.edgeGroupBegin + g].begin - t.edgeBegin;
           eg[4 * g + 1] = plan.groups[t.edgeGroupBegin + g].count;
           eg[4 * g + 2] = plan.groups[t.tetGroupBegin + g].begin - t.tetBegin;
-#ifndef PBD_X_TET_COUNT_ENTRY
           eg[4 * g + 3] = block_ - plan.groups[t.tetGroupBegin + g].count;   // the first tet thread (tets sit on the block's last threads)
-#else
-          eg[4 * g + 3] = plan.groups[t.tetGroupBegin + g].count;
-#endif
         }
       }
       uint32_t* ei = reinterpret_cast<uint32_t*>(b + h.offEdgeIdx);
