@@ -185,6 +185,8 @@ PBD_DEV float dot3_f(float ax, float ay, float az, float bx, float by, float bz)
   return ffma(az, bz, ffma(ay, by, fmul(ax, bx)));
 }
 
+// (The same reordering as in tet_delta_fast below -- rs / (wSum + alpha) times w0, w1 formed beside the `num` chain -- was
+// measured on the edges too: -0.5 %, tools/gpu_r2_exp32.sh.  The edge warps are not the ones a mixed step waits for.)
 PBD_DEV bool edge_delta_fast(const float4 p0, const float4 p1, float rest, float lambda, float alpha, float4& q0,
                              float4& q1, float& newLambda) {
   const float w0 = p0.w, w1 = p1.w;
