@@ -1235,19 +1235,31 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
     std::vector<std::vector<uint32_t>> tileOfV(K, std::vector<uint32_t>(m.V, 0));
     std::vector<uint32_t> tile0Begin, slotToVertex;
     uint32_t nTilesMax = 1;
-    for (uint32_t p = 0; p < K; ++p) {
-      Partitioner pt = base;
-      pt.offset = (double)p / K;
-      pt.idx.resize(m.V);
-      std::iota(pt.idx.begin(), pt.idx.end(), 0u);
-      pt.tileOf = tileOfV[p].data();
-      if (m.V) pt.split(0, m.V, tilesWanted, 0); else pt.tileBegin.push_back(0);
-      nTilesMax = std::max(nTilesMax, (uint32_t)pt.tileBegin.size());
-      if (p == 0) {
-        tile0Begin = pt.tileBegin;
-        tile0Begin.push_back(m.V);
-        slotToVertex = pt.idx;
-      }
+    {
+      // the K partitions are independent of each other (own permutation, own tileOf array): one host thread each
+      std::vector<uint32_t> nTilesOf(K, 1u);
+      auto split_partition = [&](uint32_t p) {
+        Partitioner pt = base;
+        pt.offset = (double)p / K;
+        pt.idx.resize(m.V);
+        std::iota(pt.idx.begin(), pt.idx.end(), 0u);
+        pt.tileOf = tileOfV[p].data();
+        if (m.V) pt.split(0, m.V, tilesWanted, 0); else pt.tileBegin.push_back(0);
+        nTilesOf[p] = (uint32_t)pt.tileBegin.size();
+        if (p == 0) {
+          tile0Begin = pt.tileBegin;
+          tile0Begin.push_back(m.V);
+          slotToVertex = std::move(pt.idx);
+        }
+      };
+      std::vector<std::thread> pool;
+      if (m.V >= 50000u && std::thread::hardware_concurrency() > 1)
+        for (uint32_t p = 1; p < K; ++p) pool.emplace_back(split_partition, p);
+      else
+        for (uint32_t p = 1; p < K; ++p) split_partition(p);
+      split_partition(0);
+      for (auto& th : pool) th.join();
+      for (uint32_t p = 0; p < K; ++p) nTilesMax = std::max(nTilesMax, nTilesOf[p]);
     }
     const uint32_t nTile0 = (uint32_t)tile0Begin.size() - 1;
     // Slot order inside a home tile: vertices that share their tile in EVERY shifted partition sit next to each
@@ -2104,6 +2116,21 @@ bool build_tile_plan(const MeshView& m, const pbd_options& opts, uint32_t nSMs, 
       }
     fprintf(stderr, "[plan] vertex words per warp access: %.2f 32-byte sectors, %.2f 128-byte lines (16 / 4 = contiguous)\n",
             (double)sectors / (double)std::max<uint64_t>(1, warps), (double)lines / (double)std::max<uint64_t>(1, warps));
+  }
+  if (knobs().debug) {
+    // fingerprint of everything the upload reads (FNV-1a over the plan's arrays): planner changes that claim to be
+    // result-neutral (threading, data structures) are checked against it on the host, before any GPU run
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* d, size_t n) { const unsigned char* c = static_cast<const unsigned char*>(d); for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; } };
+    auto vec = [&](const auto& v) { const uint64_t n = v.size(); mix(&n, sizeof(n)); if (n) mix(v.data(), n * sizeof(v[0])); };
+    vec(plan.edgeOrder); vec(plan.tetOrder); vec(plan.edgeColorOff); vec(plan.tetColorOff); vec(plan.slotToVertex); vec(plan.vertexToSlot);
+    vec(plan.tileVerts); vec(plan.phases); vec(plan.tiles); vec(plan.groups); vec(plan.edgeLocal); vec(plan.tetLocal);
+    vec(plan.edgeDev); vec(plan.tetDev); vec(plan.tile0Begin); vec(plan.tetRide); vec(plan.tetPerm);
+    vec(plan.edgePhase); vec(plan.edgeTile); vec(plan.edgeColor); vec(plan.tetPhase); vec(plan.tetTile); vec(plan.tetColor);
+    const uint32_t sc[] = {plan.tileVertexCapacity, plan.tileRecordBytes, plan.partitions, plan.tilesPerPartition, plan.edgeDevCount, plan.tetDevCount,
+                           plan.blockThreads, plan.tilesPerSm, plan.edgePhases, plan.tetPhases, plan.edgeColorSum, plan.tetColorSum, plan.riders};
+    mix(sc, sizeof(sc));
+    fprintf(stderr, "[plan] fingerprint %016llx\n", (unsigned long long)h);
   }
   if (knobs().debug)
     fprintf(stderr, "[plan] shared-memory gathers, wavefronts per quarter-warp role (1.0 = conflict-free): edges %.3f, tets %.3f\n",
