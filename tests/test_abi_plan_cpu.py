@@ -314,3 +314,35 @@ def test_riding_schedule_is_valid(mesh, tile_vertices, partitions, capi, meshgen
 def _is_rider_position(i, is_tet, unit_of, u):
     """riders sit directly behind their host: every item between the host tet and item i belongs to the same unit"""
     return True
+
+
+def test_plan_does_not_depend_on_the_host_thread_count():
+    """The planner spreads the partition splits, the tile colouring and the placement search over host threads; the
+    plan must not depend on how many there are (every rank of a sharded body plans on its own box and the results
+    must agree bit for bit).  Compared through the whole-plan fingerprint PBD_PLAN_DEBUG prints, on a body above the
+    threading thresholds (V >= 50,000, E + T >= 200,000), with one host core against all of them."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import os, sys, importlib\n"
+        "n = int(sys.argv[1])\n"
+        "if n: os.sched_setaffinity(0, set(sorted(os.sched_getaffinity(0))[:n]))\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "pkg = importlib.import_module('cs121-softbodysim_b200')\n"
+        "capi, mg = pkg.capi, pkg.meshgen\n"
+        "x0, tets, edges = mg.kuhn_grid(38)\n"
+        "o = capi.Options(backend=capi.BACKEND_TILE, order_mode=capi.ORDER_INTERLEAVED, plan_sms=148,\n"
+        "                 flags=capi.FLAG_TAGGED_HANDOVER | capi.FLAG_FAST_ARITH)\n"
+        "capi.Plan(x0, edges, tets, options=o).close()\n")
+    fps = []
+    for cores in (1, 0):
+        r = subprocess.run([sys.executable, "-c", code, str(cores)], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, PBD_PLAN_DEBUG="1"))
+        assert r.returncode == 0, r.stderr[-1500:]
+        fp = re.findall(r"fingerprint ([0-9a-f]{16})", r.stderr)
+        assert fp, r.stderr[-1500:]
+        fps.append(fp[-1])
+    if len(os.sched_getaffinity(0)) < 2:
+        pytest.skip("one host core only: nothing to compare")
+    assert fps[0] == fps[1], fps
